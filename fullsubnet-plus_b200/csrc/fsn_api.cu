@@ -1,0 +1,566 @@
+// C ABI of fsnplus_b200 (include/fsnplus_b200.h): model object, parameter store keyed by the reference's
+// state_dict names, packing into kernel layouts, and the forward orchestration.
+#include "../../include/fsnplus_b200.h"
+#include "fsn_common.cuh"
+#include "fsn_kernels.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace fsn;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(x)                                                                                               \
+    do {                                                                                                    \
+        cudaError_t e_ = (x);                                                                               \
+        if (e_ != cudaSuccess) return fail(FSN_ECUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n, bool zero) {
+        if (n <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) return (int)e;
+        bytes = n;
+        if (zero) e = cudaMemset(p, 0, n);
+        return (int)e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct ParamSpec { std::string key; int64_t numel; };
+
+struct fsn_model {
+    fsn_config cfg;
+    std::vector<ParamSpec> specs;
+    std::map<std::string, std::vector<float>> host;   // raw fp32 parameters (reference layout)
+    std::map<std::string, float*> dev;                // same, on device
+    DevBuf arena;
+    bool finalized = false;
+    int Isb = 0;                                      // sub-band LSTM input size
+    // packed LSTM weights
+    DevBuf sb_frag[4], sb_bias[4], sb_tc5_stream, sb_tc5_bias;
+    DevBuf fb_frag[4], fb_bias[4];
+    bool tc5_ok = false;
+    // workspaces (grow-only, keyed by the last (B, T))
+    int wsB = 0, wsT = 0;
+    DevBuf fbin, fbout, xa, xb, y1, y2, stats, mu, ximg, cstate, magpad, fbx, hseq, stage_in[3], stage_out;
+    int64_t launches = 0;
+    int last_impl = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// parameter registry: exactly the reference's state_dict
+// ---------------------------------------------------------------------------------------------
+static void add(std::vector<ParamSpec>& v, const std::string& k, int64_t n) { v.push_back({k, n}); }
+
+static void lstm_specs(std::vector<ParamSpec>& v, const std::string& pre, int I, int H, int L, int O) {
+    for (int l = 0; l < L; ++l) {
+        const std::string s = std::to_string(l);
+        add(v, pre + ".sequence_model.weight_ih_l" + s, (int64_t)4 * H * (l == 0 ? I : H));
+        add(v, pre + ".sequence_model.weight_hh_l" + s, (int64_t)4 * H * H);
+        add(v, pre + ".sequence_model.bias_ih_l" + s, 4 * H);
+        add(v, pre + ".sequence_model.bias_hh_l" + s, 4 * H);
+    }
+    add(v, pre + ".fc_output_layer.weight", (int64_t)O * H);
+    add(v, pre + ".fc_output_layer.bias", O);
+}
+
+static void build_specs(fsn_model* m) {
+    const fsn_config& c = m->cfg;
+    const int F = c.num_freqs;
+    auto& v = m->specs;
+    if (c.model_kind == FSN_KIND_PLUS) {
+        const char* sfx[3] = {"", "_real", "_imag"};
+        const char* cn[3] = {"smallConv1d", "middleConv1d", "largeConv1d"};
+        for (int b = 0; b < 3; ++b) {
+            const std::string p = std::string("channel_attention") + sfx[b];
+            for (int i = 0; i < 3; ++i) {
+                add(v, p + "." + cn[i] + ".0.weight", (int64_t)F * c.kersize[i]);
+                add(v, p + "." + cn[i] + ".0.bias", F);
+            }
+            add(v, p + ".feature_concate_fc.weight", 3);
+            add(v, p + ".feature_concate_fc.bias", 1);
+            add(v, p + ".fc1.weight", (int64_t)(F / 2) * F);
+            add(v, p + ".fc1.bias", F / 2);
+            add(v, p + ".fc2.weight", (int64_t)F * (F / 2));
+            add(v, p + ".fc2.bias", F);
+        }
+        for (int b = 0; b < 3; ++b) {
+            const std::string p = std::string("fb_model") + sfx[b];
+            for (int i = 0; i < 8; ++i) {
+                const std::string q = p + ".sequence_model." + std::to_string(i);
+                add(v, q + ".conv1x1.weight", (int64_t)512 * F);
+                add(v, q + ".conv1x1.bias", 512);
+                add(v, q + ".prelu1.weight", 1);
+                add(v, q + ".norm1.weight", 512);
+                add(v, q + ".norm1.bias", 512);
+                add(v, q + ".depthwise_conv.weight", 512 * 3);
+                add(v, q + ".depthwise_conv.bias", 512);
+                add(v, q + ".prelu2.weight", 1);
+                add(v, q + ".norm2.weight", 512);
+                add(v, q + ".norm2.bias", 512);
+                add(v, q + ".sconv.weight", (int64_t)F * 512);
+                add(v, q + ".sconv.bias", F);
+            }
+            add(v, p + ".fc_output_layer.weight", (int64_t)F * F);
+            add(v, p + ".fc_output_layer.bias", F);
+        }
+        m->Isb = (2 * c.sb_num_neighbors + 1) + 3 * (2 * c.fb_num_neighbors + 1);
+    } else {
+        lstm_specs(v, "fb_model", F, c.fb_hidden, c.num_layers, F);
+        m->Isb = (2 * c.sb_num_neighbors + 1) + (2 * c.fb_num_neighbors + 1);
+    }
+    lstm_specs(v, "sb_model", m->Isb, c.sb_hidden, c.num_layers, c.output_size);
+}
+
+// ---------------------------------------------------------------------------------------------
+// packing
+// ---------------------------------------------------------------------------------------------
+static uint16_t h_bits(float f) { __half h = __float2half_rn(f); uint16_t b; std::memcpy(&b, &h, 2); return b; }
+
+// mma.sync fragment order (k_lstm_mma.cu): [group of 8 units][k16 step][lane][i.b0 i.b1 f.b0 f.b1 | g.b0 g.b1 o.b0 o.b1]
+static void pack_mma_layer(const float* w_ih, const float* w_hh, int Kin, int Kin_pad, int H, std::vector<uint32_t>& out) {
+    const int K = Kin_pad + H, ksteps = K / 16, groups = H / 8;
+    out.assign((size_t)groups * ksteps * 32 * 8, 0u);
+    auto wcat = [&](int row, int k) -> float {
+        if (k < Kin_pad) return k < Kin ? w_ih[(size_t)row * Kin + k] : 0.f;
+        return w_hh[(size_t)row * H + (k - Kin_pad)];
+    };
+    for (int g = 0; g < groups; ++g)
+        for (int ks = 0; ks < ksteps; ++ks)
+            for (int lane = 0; lane < 32; ++lane) {
+                uint32_t* dst = &out[(((size_t)g * ksteps + ks) * 32 + lane) * 8];
+                const int n = g * 8 + lane / 4, k0 = ks * 16 + (lane % 4) * 2;
+                for (int q = 0; q < 4; ++q) {
+                    const int row = q * H + n;
+                    dst[2 * q] = (uint32_t)h_bits(wcat(row, k0)) | ((uint32_t)h_bits(wcat(row, k0 + 1)) << 16);
+                    dst[2 * q + 1] = (uint32_t)h_bits(wcat(row, k0 + 8)) | ((uint32_t)h_bits(wcat(row, k0 + 9)) << 16);
+                }
+            }
+}
+
+static int upload(DevBuf& b, const void* src, size_t bytes) {
+    int e = b.ensure(bytes, false);
+    if (e) return e;
+    return (int)cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice);
+}
+
+static int pack_lstm(fsn_model* m, const std::string& pre, int I, int Ipad, int H, int L, DevBuf* frag, DevBuf* bias) {
+    for (int l = 0; l < L; ++l) {
+        const std::string s = std::to_string(l);
+        const auto& wi = m->host[pre + ".sequence_model.weight_ih_l" + s];
+        const auto& wh = m->host[pre + ".sequence_model.weight_hh_l" + s];
+        const auto& bi = m->host[pre + ".sequence_model.bias_ih_l" + s];
+        const auto& bh = m->host[pre + ".sequence_model.bias_hh_l" + s];
+        std::vector<uint32_t> f;
+        pack_mma_layer(wi.data(), wh.data(), l == 0 ? I : H, l == 0 ? Ipad : H, H, f);
+        int e = upload(frag[l], f.data(), f.size() * 4);
+        if (e) return e;
+        std::vector<float> b(4 * H);
+        for (int i = 0; i < 4 * H; ++i) b[i] = bi[i] + bh[i];
+        e = upload(bias[l], b.data(), b.size() * 4);
+        if (e) return e;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int fsn_version(void) { return 100; }
+extern "C" const char* fsn_last_error(void) { return g_err; }
+
+extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
+    if (!cfg || !out) return fail(FSN_EINVAL, "null argument");
+    const fsn_config& c = *cfg;
+    if (c.model_kind != FSN_KIND_PLUS && c.model_kind != FSN_KIND_FSN) return fail(FSN_EINVAL, "unknown model_kind %d", c.model_kind);
+    if (c.num_freqs < 4 || c.look_ahead < 0 || c.sb_num_neighbors < 0 || c.fb_num_neighbors < 0) return fail(FSN_EINVAL, "bad geometry");
+    if (c.sb_num_neighbors >= c.num_freqs || c.fb_num_neighbors >= c.num_freqs) return fail(FSN_EINVAL, "reflect padding needs neighbors < num_freqs");
+    if (c.num_layers < 1 || c.num_layers > 4) return fail(FSN_EINVAL, "num_layers must be 1..4");
+    if (c.sb_hidden % 16 || c.sb_hidden < 16) return fail(FSN_EINVAL, "sb_model_hidden_size must be a multiple of 16");
+    if (c.model_kind == FSN_KIND_FSN && (c.fb_hidden % 16 || c.fb_hidden < 16)) return fail(FSN_EINVAL, "fb_model_hidden_size must be a multiple of 16");
+    if (c.output_size < 1 || c.output_size > 8) return fail(FSN_EINVAL, "output_size must be 1..8");
+    if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE)
+        return fail(FSN_EINVAL, "norm_type %d not implemented on the GPU path yet (offline_laplace_norm only)", c.norm_type);
+    if (c.model_kind == FSN_KIND_PLUS)
+        for (int i = 0; i < 3; ++i)
+            if (c.kersize[i] < 1 || c.kersize[i] > 16) return fail(FSN_EINVAL, "kersize must be in 1..16");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FSN_ECUDA, "no CUDA device: fsnplus_b200 has no CPU fallback");
+    fsn_model* m = new fsn_model();
+    m->cfg = c;
+    build_specs(m);
+    if (m->Isb > 64) { delete m; return fail(FSN_EINVAL, "sub-band input size %d > 64 not supported", m->Isb); }
+    *out = m;
+    return FSN_OK;
+}
+
+extern "C" void fsn_model_destroy(fsn_model* m) {
+    if (!m) return;
+    DevBuf* all[] = {&m->arena, &m->sb_tc5_stream, &m->sb_tc5_bias, &m->fbin, &m->fbout, &m->xa, &m->xb, &m->y1, &m->y2, &m->stats,
+                     &m->mu, &m->ximg, &m->cstate, &m->magpad, &m->fbx, &m->hseq, &m->stage_in[0], &m->stage_in[1], &m->stage_in[2],
+                     &m->stage_out};
+    for (auto* b : all) b->release();
+    for (int i = 0; i < 4; ++i) { m->sb_frag[i].release(); m->sb_bias[i].release(); m->fb_frag[i].release(); m->fb_bias[i].release(); }
+    delete m;
+}
+
+extern "C" int fsn_model_num_params(const fsn_model* m) { return m ? (int)m->specs.size() : 0; }
+extern "C" int fsn_model_param_info(const fsn_model* m, int i, const char** key, int64_t* numel) {
+    if (!m || i < 0 || i >= (int)m->specs.size()) return fail(FSN_EINVAL, "bad index");
+    if (key) *key = m->specs[i].key.c_str();
+    if (numel) *numel = m->specs[i].numel;
+    return FSN_OK;
+}
+
+extern "C" int fsn_model_set_param(fsn_model* m, const char* key, const float* h, int64_t numel) {
+    if (!m || !key || !h) return fail(FSN_EINVAL, "null argument");
+    for (const auto& s : m->specs)
+        if (s.key == key) {
+            if (s.numel != numel) return fail(FSN_EINVAL, "size mismatch for %s: expected %lld, got %lld", key, (long long)s.numel, (long long)numel);
+            m->host[key].assign(h, h + numel);
+            m->finalized = false;
+            return FSN_OK;
+        }
+    return fail(FSN_EINVAL, "unexpected key %s", key);
+}
+
+extern "C" int fsn_model_finalize(fsn_model* m) {
+    if (!m) return fail(FSN_EINVAL, "null model");
+    size_t total = 0;
+    for (const auto& s : m->specs) {
+        if (!m->host.count(s.key)) return fail(FSN_ESTATE, "missing parameter %s", s.key.c_str());
+        total += ((size_t)s.numel * 4 + 255) & ~(size_t)255;
+    }
+    if (m->arena.ensure(total, false)) return fail(FSN_ECUDA, "cudaMalloc of %zu bytes failed", total);
+    size_t off = 0;
+    for (const auto& s : m->specs) {
+        float* d = reinterpret_cast<float*>(static_cast<char*>(m->arena.p) + off);
+        CK(cudaMemcpy(d, m->host[s.key].data(), (size_t)s.numel * 4, cudaMemcpyHostToDevice));
+        m->dev[s.key] = d;
+        off += ((size_t)s.numel * 4 + 255) & ~(size_t)255;
+    }
+    const fsn_config& c = m->cfg;
+    if (pack_lstm(m, "sb_model", m->Isb, 64, c.sb_hidden, c.num_layers, m->sb_frag, m->sb_bias)) return fail(FSN_ECUDA, "packing sb_model failed");
+    if (c.model_kind == FSN_KIND_FSN) {
+        const int Ipad = (c.num_freqs + 15) / 16 * 16;
+        if (pack_lstm(m, "fb_model", c.num_freqs, Ipad, c.fb_hidden, c.num_layers, m->fb_frag, m->fb_bias)) return fail(FSN_ECUDA, "packing fb_model failed");
+    }
+    m->tc5_ok = lstm_tc5_supported(c.num_layers, c.sb_hidden, m->Isb, c.output_size);
+    if (m->tc5_ok) {
+        const int H = c.sb_hidden;
+        const int64_t bytes = fsn_tc5_weight_stream_bytes(m->Isb, H);
+        std::vector<uint16_t> st((size_t)bytes / 2);
+        fsn_tc5_pack_weights(m->Isb, H, m->host["sb_model.sequence_model.weight_ih_l0"].data(),
+                             m->host["sb_model.sequence_model.weight_hh_l0"].data(),
+                             m->host["sb_model.sequence_model.weight_ih_l1"].data(),
+                             m->host["sb_model.sequence_model.weight_hh_l1"].data(), st.data());
+        if (upload(m->sb_tc5_stream, st.data(), (size_t)bytes)) return fail(FSN_ECUDA, "upload of tcgen05 weight stream failed");
+        std::vector<float> bp((size_t)2 * 4 * H);
+        for (int l = 0; l < 2; ++l) {
+            const auto& bi = m->host["sb_model.sequence_model.bias_ih_l" + std::to_string(l)];
+            const auto& bh = m->host["sb_model.sequence_model.bias_hh_l" + std::to_string(l)];
+            for (int j = 0; j < H / 16; ++j)
+                for (int n = 0; n < 64; ++n) {
+                    const int row = (n / 16) * H + 16 * j + (n % 16);
+                    bp[(size_t)l * 4 * H + j * 64 + n] = bi[row] + bh[row];
+                }
+        }
+        if (upload(m->sb_tc5_bias, bp.data(), bp.size() * 4)) return fail(FSN_ECUDA, "upload failed");
+    }
+    m->finalized = true;
+    return FSN_OK;
+}
+
+static const float* P(fsn_model* m, const std::string& k) { return m->dev.at(k); }
+
+static int ensure_ws(fsn_model* m, int B, int T) {
+    const fsn_config& c = m->cfg;
+    const int F = c.num_freqs, Tp = T + c.look_ahead, Pp = (Tp + 3) & ~3;
+    const int nbr = (c.model_kind == FSN_KIND_PLUS) ? 3 : 1;
+    const size_t act = (size_t)nbr * B * F * Pp * 4;
+    const int rows = B * F, ntiles = (rows + 127) / 128;
+    int e = 0;
+    e |= m->fbin.ensure(act, true);
+    e |= m->fbout.ensure(act, true);
+    e |= m->mu.ensure((size_t)B * 4, true);
+    // images are re-zeroed whenever the geometry changes (rows beyond B*F and k >= I must stay zero)
+    const size_t img_bytes = (size_t)ntiles * Tp * 16384;
+    if (m->wsB != B || m->wsT != T) { m->ximg.release(); }
+    e |= m->ximg.ensure(img_bytes, true);
+    int ra = 0;
+    size_t cs = lstm_mma_cstate_bytes(c.num_layers, rows, c.sb_hidden, &ra);
+    size_t cs5 = lstm_tc5_cstate_bytes(ntiles, c.sb_hidden);
+    e |= m->cstate.ensure(cs > cs5 ? cs : cs5, true);
+    if (c.model_kind == FSN_KIND_PLUS) {
+        e |= m->xa.ensure(act, true);
+        e |= m->xb.ensure(act, true);
+        const size_t hid = (size_t)3 * B * 512 * Pp * 4;
+        e |= m->y1.ensure(hid, true);
+        e |= m->y2.ensure(hid, true);
+        e |= m->stats.ensure((size_t)8 * 2 * 3 * B * 2 * sizeof(double), true);
+    } else {
+        const int Ipad = (F + 15) / 16 * 16, rows_pad = (B + 63) / 64 * 64;
+        e |= m->magpad.ensure((size_t)B * F * Pp * 4, true);
+        e |= m->fbx.ensure((size_t)Tp * rows_pad * Ipad * 2, true);
+        e |= m->hseq.ensure((size_t)B * c.fb_hidden * Pp * 4, true);
+        int ra2 = 0;
+        size_t csf = lstm_mma_cstate_bytes(c.num_layers, B, c.fb_hidden, &ra2);
+        if (csf > m->cstate.bytes) e |= m->cstate.ensure(csf, true);
+    }
+    if (e) return fail(FSN_ECUDA, "workspace allocation failed for B=%d T=%d", B, T);
+    m->wsB = B; m->wsT = T;
+    return FSN_OK;
+}
+
+static int pick_impl(const fsn_model* m) {
+    int impl = m->cfg.lstm_impl;
+    const char* env = getenv("FSN_LSTM_IMPL");
+    if (env && *env) impl = atoi(env);
+    if (impl == FSN_LSTM_AUTO) impl = m->tc5_ok ? FSN_LSTM_TCGEN05 : FSN_LSTM_MMA;
+    return impl;
+}
+
+static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s) {
+    const fsn_config& c = m->cfg;
+    const int F = c.num_freqs, Tp = T + c.look_ahead, rows = B * F, ntiles = (rows + 127) / 128;
+    const int impl = pick_impl(m);
+    m->last_impl = impl;
+    if (impl == FSN_LSTM_TCGEN05) {
+        if (!m->tc5_ok) return fail(FSN_EINVAL, "tcgen05 LSTM needs 2 layers, hidden %% 64 == 0 and <= 384, input <= 64, output_size 2");
+        LstmTc5Launch a{};
+        a.wstream = static_cast<const __half*>(m->sb_tc5_stream.p);
+        a.bias = static_cast<const float*>(m->sb_tc5_bias.p);
+        a.fc_w = P(m, "sb_model.fc_output_layer.weight");
+        a.fc_b = P(m, "sb_model.fc_output_layer.bias");
+        a.H = c.sb_hidden; a.I = m->Isb; a.rows = rows; a.Tp = Tp;
+        a.img = static_cast<const __half*>(m->ximg.p); a.ntiles = ntiles;
+        a.cstate = static_cast<float*>(m->cstate.p);
+        a.out = d_out; a.F = F; a.la = c.look_ahead; a.fast = c.fast_math;
+        int e = launch_lstm_tc5(a, s);
+        if (e) return fail(FSN_ECUDA, "tcgen05 LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    } else {
+        LstmMmaLaunch a{};
+        for (int l = 0; l < c.num_layers; ++l) {
+            a.w.wfrag[l] = static_cast<const uint4*>(m->sb_frag[l].p);
+            a.w.bias[l] = static_cast<const float*>(m->sb_bias[l].p);
+        }
+        a.w.fc_w = P(m, "sb_model.fc_output_layer.weight");
+        a.w.fc_b = P(m, "sb_model.fc_output_layer.bias");
+        a.L = c.num_layers; a.H = c.sb_hidden; a.I = m->Isb; a.Ipad = 64;
+        a.rows = rows; a.Tp = Tp;
+        a.img = static_cast<const __half*>(m->ximg.p); a.ntiles = ntiles;
+        a.cstate = static_cast<float*>(m->cstate.p);
+        lstm_mma_cstate_bytes(c.num_layers, rows, c.sb_hidden, &a.rows_alloc);
+        a.out = d_out; a.O = c.output_size; a.F = F; a.la = c.look_ahead; a.act = c.sb_act;
+        a.fast = c.fast_math;
+        int e = launch_lstm_mma(a, s);
+        if (e) return fail(FSN_ECUDA, "mma LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    }
+    m->launches++;
+    return FSN_OK;
+}
+
+extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                                 float* d_out, void* stream) {
+    if (!m || !d_mag || !d_out) return fail(FSN_EINVAL, "null argument");
+    if (!m->finalized) return fail(FSN_ESTATE, "fsn_model_finalize has not been called");
+    const fsn_config& c = m->cfg;
+    if (B < 1 || T < 1) return fail(FSN_EINVAL, "bad batch/frames");
+    if (c.model_kind == FSN_KIND_PLUS && (!d_real || !d_imag)) return fail(FSN_EINVAL, "FullSubNet_Plus.forward needs mag, real and imag");
+    const int F = c.num_freqs, Tp = T + c.look_ahead, Pp = (Tp + 3) & ~3;
+    if (c.model_kind == FSN_KIND_PLUS)
+        for (int i = 0; i < 3; ++i)
+            if (Tp < c.kersize[i]) return fail(FSN_EINVAL, "sequence shorter than the TSSE kernel size");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = ensure_ws(m, B, T);
+    if (rc) return rc;
+    m->launches = 0;
+
+    SbPackLaunch sp{};
+    sp.B = B; sp.F = F; sp.Tp = Tp; sp.Ns = c.sb_num_neighbors; sp.Nf = c.fb_num_neighbors; sp.P = Pp;
+    sp.mu = static_cast<float*>(m->mu.p);
+    sp.ximg = static_cast<__half*>(m->ximg.p);
+    sp.ntiles = (B * F + 127) / 128;
+
+    if (c.model_kind == FSN_KIND_PLUS) {
+        const char* sfx[3] = {"", "_real", "_imag"};
+        const char* cn[3] = {"smallConv1d", "middleConv1d", "largeConv1d"};
+        TsseLaunch ta{};
+        ta.x[0] = d_mag; ta.x[1] = d_real; ta.x[2] = d_imag;
+        ta.nbranch = 3; ta.B = B; ta.F = F; ta.T = T; ta.Tp = Tp; ta.P = Pp; ta.attention = 1;
+        for (int i = 0; i < 3; ++i) ta.ksz[i] = c.kersize[i];
+        for (int b = 0; b < 3; ++b) {
+            const std::string p = std::string("channel_attention") + sfx[b];
+            for (int i = 0; i < 3; ++i) {
+                ta.p[b].conv_w[i] = P(m, p + "." + cn[i] + ".0.weight");
+                ta.p[b].conv_b[i] = P(m, p + "." + cn[i] + ".0.bias");
+            }
+            ta.p[b].cat_w = P(m, p + ".feature_concate_fc.weight"); ta.p[b].cat_b = P(m, p + ".feature_concate_fc.bias");
+            ta.p[b].fc1_w = P(m, p + ".fc1.weight"); ta.p[b].fc1_b = P(m, p + ".fc1.bias");
+            ta.p[b].fc2_w = P(m, p + ".fc2.weight"); ta.p[b].fc2_b = P(m, p + ".fc2.bias");
+        }
+        ta.out = static_cast<float*>(m->fbin.p);
+        launch_tsse_norm(ta, s); m->launches++;
+
+        const int Z = 3 * B;
+        double* stats = static_cast<double*>(m->stats.p);
+        CK(cudaMemsetAsync(stats, 0, (size_t)8 * 2 * Z * 2 * sizeof(double), s));
+        static const int dil[8] = {1, 2, 5, 9, 1, 2, 5, 9};     // sequence_model.py:47-58
+        const float* cur = static_cast<const float*>(m->fbin.p);
+        float* nxt = static_cast<float*>(m->xa.p);
+        for (int blk = 0; blk < 8; ++blk) {
+            double* st1 = stats + (size_t)(2 * blk) * Z * 2;
+            double* st2 = stats + (size_t)(2 * blk + 1) * Z * 2;
+            auto key = [&](int b, const char* leaf) { return std::string("fb_model") + sfx[b] + ".sequence_model." + std::to_string(blk) + "." + leaf; };
+            ConvLaunch ca{};
+            ca.X = cur; ca.Y = static_cast<float*>(m->y1.p); ca.Z = Z; ca.zper = B; ca.M = 512; ca.K = F; ca.Tp = Tp; ca.P = Pp;
+            ca.pro = PRO_NONE; ca.epi = EPI_PRELU_STATS; ca.stats_out = st1;
+            for (int b = 0; b < 3; ++b) { ca.W[b] = P(m, key(b, "conv1x1.weight")); ca.bias[b] = P(m, key(b, "conv1x1.bias")); ca.prelu[b] = P(m, key(b, "prelu1.weight")); }
+            launch_conv1x1(ca, s); m->launches++;
+
+            DwLaunch da{};
+            da.X = static_cast<const float*>(m->y1.p); da.Y = static_cast<float*>(m->y2.p);
+            da.Z = Z; da.zper = B; da.C = 512; da.Tp = Tp; da.P = Pp; da.dilation = dil[blk];
+            da.stats_in = st1; da.stats_out = st2;
+            for (int b = 0; b < 3; ++b) {
+                da.gamma[b] = P(m, key(b, "norm1.weight")); da.beta[b] = P(m, key(b, "norm1.bias"));
+                da.w[b] = P(m, key(b, "depthwise_conv.weight")); da.b[b] = P(m, key(b, "depthwise_conv.bias"));
+                da.prelu[b] = P(m, key(b, "prelu2.weight"));
+            }
+            launch_dwconv(da, s); m->launches++;
+
+            ConvLaunch cc{};
+            cc.X = static_cast<const float*>(m->y2.p); cc.Y = nxt; cc.Z = Z; cc.zper = B; cc.M = F; cc.K = 512; cc.Tp = Tp; cc.P = Pp;
+            cc.pro = PRO_GLN; cc.epi = EPI_RESIDUAL; cc.stats_in = st2; cc.count_in = (double)512 * Tp; cc.R = cur;
+            for (int b = 0; b < 3; ++b) {
+                cc.W[b] = P(m, key(b, "sconv.weight")); cc.bias[b] = P(m, key(b, "sconv.bias"));
+                cc.gamma[b] = P(m, key(b, "norm2.weight")); cc.beta[b] = P(m, key(b, "norm2.bias"));
+            }
+            launch_conv1x1(cc, s); m->launches++;
+            cur = nxt;
+            nxt = (nxt == static_cast<float*>(m->xa.p)) ? static_cast<float*>(m->xb.p) : static_cast<float*>(m->xa.p);
+        }
+        ConvLaunch cf{};
+        cf.X = cur; cf.Y = static_cast<float*>(m->fbout.p); cf.Z = Z; cf.zper = B; cf.M = F; cf.K = F; cf.Tp = Tp; cf.P = Pp;
+        cf.pro = PRO_RELU; cf.epi = EPI_ACT; cf.act = c.fb_act;
+        for (int b = 0; b < 3; ++b) {
+            cf.W[b] = P(m, std::string("fb_model") + sfx[b] + ".fc_output_layer.weight");
+            cf.bias[b] = P(m, std::string("fb_model") + sfx[b] + ".fc_output_layer.bias");
+        }
+        launch_conv1x1(cf, s); m->launches++;
+
+        sp.win = static_cast<const float*>(m->fbin.p); sp.Pw = Pp;      // post-attention mag branch (fullsubnet_plus.py:182)
+        sp.nfb = 3;
+        for (int b = 0; b < 3; ++b) sp.fb[b] = static_cast<const float*>(m->fbout.p) + (size_t)b * B * F * Pp;
+    } else {
+        TsseLaunch ta{};
+        ta.x[0] = d_mag; ta.nbranch = 1; ta.B = B; ta.F = F; ta.T = T; ta.Tp = Tp; ta.P = Pp; ta.attention = 0;
+        ta.out = static_cast<float*>(m->fbin.p);
+        launch_tsse_norm(ta, s); m->launches++;
+        launch_pad_copy(d_mag, static_cast<float*>(m->magpad.p), B, F, T, Pp, s); m->launches++;
+        const int Ipad = (F + 15) / 16 * 16, rows_pad = (B + 63) / 64 * 64;
+        launch_fb_pack(static_cast<const float*>(m->fbin.p), static_cast<__half*>(m->fbx.p), B, F, Tp, Pp, rows_pad, Ipad, s); m->launches++;
+        LstmMmaLaunch a{};
+        for (int l = 0; l < c.num_layers; ++l) {
+            a.w.wfrag[l] = static_cast<const uint4*>(m->fb_frag[l].p);
+            a.w.bias[l] = static_cast<const float*>(m->fb_bias[l].p);
+        }
+        a.L = c.num_layers; a.H = c.fb_hidden; a.I = F; a.Ipad = Ipad; a.rows = B; a.Tp = Tp;
+        a.xplain = static_cast<const __half*>(m->fbx.p); a.rows_pad = rows_pad;
+        a.cstate = static_cast<float*>(m->cstate.p);
+        lstm_mma_cstate_bytes(c.num_layers, B, c.fb_hidden, &a.rows_alloc);
+        a.hseq = static_cast<float*>(m->hseq.p); a.P = Pp; a.fast = c.fast_math;
+        int e = launch_lstm_mma(a, s);
+        if (e) return fail(FSN_ECUDA, "full-band LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
+        m->launches++;
+        ConvLaunch cf{};
+        cf.X = static_cast<const float*>(m->hseq.p); cf.Y = static_cast<float*>(m->fbout.p);
+        cf.Z = B; cf.zper = B; cf.M = F; cf.K = c.fb_hidden; cf.Tp = Tp; cf.P = Pp;
+        cf.pro = PRO_NONE; cf.epi = EPI_ACT; cf.act = c.fb_act;
+        cf.W[0] = P(m, "fb_model.fc_output_layer.weight"); cf.bias[0] = P(m, "fb_model.fc_output_layer.bias");
+        launch_conv1x1(cf, s); m->launches++;
+
+        sp.win = static_cast<const float*>(m->magpad.p); sp.Pw = Pp;    // raw padded magnitude (fullsubnet.py:94)
+        sp.nfb = 1;
+        sp.fb[0] = static_cast<const float*>(m->fbout.p);
+    }
+    launch_sb_stats(sp, s); m->launches++;
+    launch_sb_pack(sp, s); m->launches++;
+    rc = run_sb_lstm(m, B, T, d_out, s);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return FSN_OK;
+}
+
+extern "C" int fsn_model_forward_host(fsn_model* m, const float* h_mag, const float* h_real, const float* h_imag, int32_t B, int32_t T,
+                                      float* h_out, void* stream) {
+    if (!m || !h_mag || !h_out) return fail(FSN_EINVAL, "null argument");
+    const fsn_config& c = m->cfg;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t in_bytes = (size_t)B * c.num_freqs * T * 4, out_bytes = (size_t)B * c.output_size * c.num_freqs * T * 4;
+    const float* hin[3] = {h_mag, h_real, h_imag};
+    const int nin = (c.model_kind == FSN_KIND_PLUS) ? 3 : 1;
+    for (int i = 0; i < nin; ++i) {
+        if (!hin[i]) return fail(FSN_EINVAL, "missing input %d", i);
+        if (m->stage_in[i].ensure(in_bytes, false)) return fail(FSN_ECUDA, "staging allocation failed");
+        CK(cudaMemcpyAsync(m->stage_in[i].p, hin[i], in_bytes, cudaMemcpyHostToDevice, s));
+    }
+    if (m->stage_out.ensure(out_bytes, false)) return fail(FSN_ECUDA, "staging allocation failed");
+    int rc = fsn_model_forward(m, static_cast<const float*>(m->stage_in[0].p), static_cast<const float*>(m->stage_in[1].p),
+                               static_cast<const float*>(m->stage_in[2].p), B, T, static_cast<float*>(m->stage_out.p), stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_out, m->stage_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return FSN_OK;
+}
+
+extern "C" int fsn_model_get_stage(fsn_model* m, const char* name, float* d_dst, int64_t numel, void* stream) {
+    if (!m || !name || !d_dst) return fail(FSN_EINVAL, "null argument");
+    if (!m->wsB) return fail(FSN_ESTATE, "no forward has run yet");
+    const fsn_config& c = m->cfg;
+    const int F = c.num_freqs, Tp = m->wsT + c.look_ahead, Pp = (Tp + 3) & ~3, B = m->wsB;
+    const int nbr = (c.model_kind == FSN_KIND_PLUS) ? 3 : 1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const std::string n(name);
+    if (n == "fb_in" || n == "fb_out") {
+        if (numel != (int64_t)nbr * B * F * Tp) return fail(FSN_EINVAL, "%s needs %lld elements", name, (long long)nbr * B * F * Tp);
+        const void* src = (n == "fb_in") ? m->fbin.p : m->fbout.p;
+        CK(cudaMemcpy2DAsync(d_dst, (size_t)Tp * 4, src, (size_t)Pp * 4, (size_t)Tp * 4, (size_t)nbr * B * F, cudaMemcpyDeviceToDevice, s));
+        return FSN_OK;
+    }
+    if (n == "sb_mu") {
+        if (numel != B) return fail(FSN_EINVAL, "sb_mu needs %d elements", B);
+        CK(cudaMemcpyAsync(d_dst, m->mu.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
+        return FSN_OK;
+    }
+    return fail(FSN_EINVAL, "unknown stage %s", name);
+}
+
+extern "C" int64_t fsn_model_last_launch_count(const fsn_model* m) { return m ? m->launches : 0; }
+extern "C" int fsn_model_last_lstm_impl(const fsn_model* m) { return m ? m->last_impl : 0; }
+
+extern "C" int fsn_probe_tcgen05(float* h_report, int32_t n) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FSN_ECUDA, "no CUDA device");
+    int rc = run_probe_tcgen05(h_report, n);
+    if (rc < 0) return fail(FSN_ECUDA, "probe failed (rc=%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}

@@ -1,0 +1,126 @@
+// Internal launch prototypes (host side) of the fsnplus_b200 kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fsn {
+
+// ---- k_front.cu ------------------------------------------------------------------------------
+struct TsseParams {            // device pointers, one set per branch
+    const float* conv_w[3];    // [C, k]
+    const float* conv_b[3];    // [C]
+    const float* cat_w;        // [3]
+    const float* cat_b;        // [1]
+    const float* fc1_w;        // [C/2, C]
+    const float* fc1_b;        // [C/2]
+    const float* fc2_w;        // [C, C/2]
+    const float* fc2_b;        // [C]
+};
+struct TsseLaunch {
+    const float* x[3];         // per branch input [B, F, T]
+    TsseParams p[3];
+    int nbranch, B, F, T, Tp, P;   // Tp = T + look_ahead, P = row pitch of the output
+    int ksz[3];
+    int attention;             // 0: norm only (fullsubnet.Model), 1: norm + TSSE
+    float* out;                // [nbranch, B, F, P]
+};
+void launch_tsse_norm(const TsseLaunch& a, cudaStream_t s);
+
+enum { PRO_NONE = 0, PRO_GLN = 1, PRO_RELU = 2 };
+enum { EPI_NONE = 0, EPI_PRELU_STATS = 1, EPI_RESIDUAL = 2, EPI_ACT = 3 };
+struct ConvLaunch {
+    const float* X;      // [Z, K, P]
+    const float* W[3];   // per group [M, K]
+    const float* bias[3];
+    float* Y;            // [Z, M, P]
+    int Z, zper;         // group g = z / zper
+    int M, K, Tp, P;
+    int pro, epi;
+    const double* stats_in;   // [Z, 2] (sum, sumsq) of X          (PRO_GLN)
+    const float* gamma[3];    // [K]
+    const float* beta[3];
+    double* stats_out;        // [Z, 2] accumulated over Y          (EPI_PRELU_STATS)
+    const float* prelu[3];    // [1]
+    const float* R;           // residual [Z, M, P]                 (EPI_RESIDUAL)
+    int act;                  // FSN_ACT_*                          (EPI_ACT)
+    double count_in;          // elements per sample in the GLN statistics (K * Tp)
+};
+void launch_conv1x1(const ConvLaunch& a, cudaStream_t s);
+
+struct DwLaunch {
+    const float* X;  // [Z, C, P] (post-PReLU1)
+    float* Y;        // [Z, C, P] (post-PReLU2)
+    int Z, zper, C, Tp, P, dilation;
+    const double* stats_in;
+    double* stats_out;
+    const float* gamma[3];
+    const float* beta[3];
+    const float* w[3];      // [C, 3]
+    const float* b[3];      // [C]
+    const float* prelu[3];  // [1]
+};
+void launch_dwconv(const DwLaunch& a, cudaStream_t s);
+
+struct SbPackLaunch {
+    const float* win;        // [B, F, Pw] window source (post-attention mag branch, or raw padded mag)
+    int Pw;
+    const float* fb[3];      // [B, F, P] full-band outputs (nfb of them)
+    int nfb, P;
+    int B, F, Tp, Ns, Nf;    // neighbours
+    float* mu;               // [B] utterance mean of the concatenated sub-band input
+    __half* ximg;            // [ntiles, Tp, 128 rows, 64 halves] SWIZZLE_128B images
+    int ntiles;
+};
+void launch_sb_stats(const SbPackLaunch& a, cudaStream_t s);
+void launch_sb_pack(const SbPackLaunch& a, cudaStream_t s);
+// [B, F, T] fp32 (+ zero look-ahead pad) -> zero-padded copy [B, F, P]
+void launch_pad_copy(const float* x, float* y, int B, int F, int T, int P, cudaStream_t s);
+// full-band LSTM input: [B, F, P] fp32 -> [Tp, Bpad, Ipad] fp16 (rows >= B and k >= F zero)
+void launch_fb_pack(const float* x, __half* y, int B, int F, int Tp, int P, int rows_pad, int Ipad, cudaStream_t s);
+
+// ---- k_lstm_mma.cu ---------------------------------------------------------------------------
+struct LstmMmaWeights {       // device, produced by pack (fsn_api.cu)
+    const uint4* wfrag[4];    // per layer: [H/8 groups][K/16][32 lanes][2 x uint4]
+    const float* bias[4];     // per layer [4H] (b_ih + b_hh), original i,f,g,o order
+    const float* fc_w;        // [O, H]
+    const float* fc_b;        // [O]
+};
+struct LstmMmaLaunch {
+    LstmMmaWeights w;
+    int L, H, I, Ipad;        // Ipad: multiple of 16
+    int rows, Tp;
+    // input: either SW128 images (img != null; Ipad == 64) or plain [Tp, rows_pad, Ipad]
+    const __half* img; int ntiles;
+    const __half* xplain; int rows_pad;
+    float* cstate;            // [L, rows_alloc, H] scratch (zeroed by the launcher)
+    int rows_alloc;
+    // output A (fused FC, O <= 8): out[b][o][f][t - la]  (row = b*F + f)
+    float* out; int O, F, la, act;
+    // output B: top-layer h as fp32 [rows, H, P]
+    float* hseq; int P;
+    int fast;
+};
+size_t lstm_mma_cstate_bytes(int L, int rows, int H, int* rows_alloc);
+int launch_lstm_mma(const LstmMmaLaunch& a, cudaStream_t s);   // returns 0 or cudaError
+
+// ---- k_lstm_tc5.cu ---------------------------------------------------------------------------
+struct LstmTc5Launch {
+    const __half* wstream;    // packed weight stream (fsn_tc5_pack_weights)
+    const float* bias;        // [2][4H] permuted to the stream's gate-column order
+    const float* fc_w;        // [O=2][H]
+    const float* fc_b;        // [2]
+    int H, I;
+    int rows, Tp;
+    const __half* img; int ntiles;   // [ntiles, Tp, 16 KB]
+    float* cstate;            // [ntiles][2 layers][H/16 chunks][4][128][4] fp32
+    float* out; int F, la;
+    int fast;
+};
+size_t lstm_tc5_cstate_bytes(int ntiles, int H);
+bool lstm_tc5_supported(int L, int H, int I, int O);
+int launch_lstm_tc5(const LstmTc5Launch& a, cudaStream_t s);
+
+// ---- k_probe.cu ------------------------------------------------------------------------------
+int run_probe_tcgen05(float* h_report, int n);
+
+}  // namespace fsn

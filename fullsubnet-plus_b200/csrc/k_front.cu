@@ -1,0 +1,392 @@
+// Full-band front end of the FullSubNet+/FullSubNet forward on sm_100a:
+//   * utterance Laplace norm + TSSE ("MulCA") channel attention     (K1 + K2 of SURVEY.md 2a)
+//   * TCN blocks as TF32 tensor-core 1x1 convolutions with the PReLU / gLN statistics / residual
+//     fused into their prologue and epilogue, plus the dilated depth-wise convolution            (K3)
+//   * utterance mean of the (never materialised) unfolded sub-band input and the fp16 packing of the
+//     per-step LSTM input tiles                                                                  (K4)
+#include "fsn_common.cuh"
+#include "fsn_kernels.h"
+#include "../../include/fsnplus_b200.h"
+
+namespace fsn {
+
+// =============================================================================================
+// K1 + K2: x / (mean(x) + 1e-5), then the TSSE gate.
+// reference: audio_zen/model/base_model.py:210-225, audio_zen/model/module/attention_model.py:78-98
+// conv(no padding) -> average pool is linear, so each pooled feature is
+//   b_k[c] + sum_j w_k[c,j] * mean_t x[c, j : T'-k+1+j]
+// i.e. 18 windowed means per channel, all derived from the row sum and the first / last 15 samples.
+// One CTA per (sample, branch); two passes over the [F, T] input (second pass hits L2).
+// =============================================================================================
+constexpr int TSSE_KMAX = 16;
+
+__global__ void __launch_bounds__(256) tsse_norm_kernel(TsseLaunch a) {
+    extern __shared__ float sm[];
+    const int b = blockIdx.x, br = blockIdx.y;
+    const int F = a.F, T = a.T, Tp = a.Tp;
+    float* S = sm;                                  // [F] row sums
+    float* Pfx = S + F;                             // [F][KMAX]   Pfx[f][j] = sum_{t<j} x[f][t]
+    float* Sfx = Pfx + F * TSSE_KMAX;               // [F][KMAX]   Sfx[f][m] = sum_{t>=Tp-m} x[f][t]
+    float* sq = Sfx + F * TSSE_KMAX;                // [F]
+    float* gate = sq + F;                           // [F]
+    float* f1 = gate + F;                           // [F/2]
+    __shared__ float s_inv;
+
+    const float* x = a.x[br] + (size_t)b * F * T;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+
+    for (int f = warp; f < F; f += nwarp) {
+        const float* row = x + (size_t)f * T;
+        float acc = 0.f;
+        for (int t = lane; t < T; t += 32) acc += row[t];
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            S[f] = acc;
+            float p = 0.f;
+            for (int j = 0; j < TSSE_KMAX; ++j) { Pfx[f * TSSE_KMAX + j] = p; if (j < T) p += row[j]; }
+            float q = 0.f;
+            for (int m = 0; m < TSSE_KMAX; ++m) {
+                Sfx[f * TSSE_KMAX + m] = q;            // sum of the last m samples of the padded row
+                int t = Tp - 1 - m;
+                if (t >= 0 && t < T) q += row[t];      // t >= T is the zero look-ahead pad
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double tot = 0.0;
+        for (int f = lane; f < F; f += 32) tot += (double)S[f];
+        tot = warp_sum_d(tot);
+        if (lane == 0) s_inv = (float)(1.0 / (tot / ((double)F * (double)Tp) + 1e-5));
+    }
+    __syncthreads();
+    const float inv = s_inv;
+    float* out = a.out + ((size_t)br * a.B + b) * F * a.P;
+
+    if (a.attention) {
+        const TsseParams& p = a.p[br];
+        for (int c = threadIdx.x; c < F; c += blockDim.x) {
+            float s = p.cat_b[0];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int k = a.ksz[i];
+                const float rlen = 1.0f / (float)(Tp - k + 1);
+                float acc = 0.f;
+                for (int j = 0; j < k; ++j) {
+                    float wsum = S[c] - Pfx[c * TSSE_KMAX + j] - Sfx[c * TSSE_KMAX + (k - 1 - j)];
+                    acc = fmaf(p.conv_w[i][c * k + j], wsum, acc);
+                }
+                float feat = fmaxf(fmaf(acc, inv * rlen, p.conv_b[i][c]), 0.f);
+                s = fmaf(p.cat_w[i], feat, s);
+            }
+            sq[c] = s;
+        }
+        __syncthreads();
+        const int Cr = F / 2;
+        for (int o = warp; o < Cr; o += nwarp) {
+            float acc = 0.f;
+            for (int c = lane; c < F; c += 32) acc = fmaf(p.fc1_w[(size_t)o * F + c], sq[c], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) f1[o] = fmaxf(acc + p.fc1_b[o], 0.f);
+        }
+        __syncthreads();
+        for (int o = warp; o < F; o += nwarp) {
+            float acc = 0.f;
+            for (int c = lane; c < Cr; c += 32) acc = fmaf(p.fc2_w[(size_t)o * Cr + c], f1[c], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) gate[o] = 1.0f / (1.0f + __expf(-(acc + p.fc2_b[o])));
+        }
+        __syncthreads();
+    }
+    for (int f = warp; f < F; f += nwarp) {
+        const float g = a.attention ? gate[f] * inv : inv;
+        const float* row = x + (size_t)f * T;
+        float* orow = out + (size_t)f * a.P;
+        for (int t = lane; t < a.P; t += 32) orow[t] = (t < T) ? row[t] * g : 0.f;
+    }
+}
+
+void launch_tsse_norm(const TsseLaunch& a, cudaStream_t s) {
+    size_t smem = sizeof(float) * ((size_t)a.F * (3 + 2 * TSSE_KMAX) + a.F / 2 + 8);
+    cudaFuncSetAttribute(tsse_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tsse_norm_kernel<<<dim3(a.B, a.nbranch), 256, smem, s>>>(a);
+}
+
+// =============================================================================================
+// K3a: 1x1 convolution Y[z] = W[g] * pro(X[z]) + b as a TF32 tensor-core GEMM (mma.sync m16n8k8),
+// 64x64x32 tiles, 4 warps.  Prologue: gLN apply (statistics from the producer's epilogue) or ReLU.
+// Epilogue: PReLU + gLN statistics of the output, residual add, or output activation.
+// reference: causal_conv.py:96-108 (TCNBlock.forward), sequence_model.py:106-112.
+// =============================================================================================
+template <int PRO, int EPI>
+__global__ void __launch_bounds__(128) conv1x1_tf32_kernel(ConvLaunch a) {
+    __shared__ uint32_t Ws[64][36];
+    __shared__ uint32_t Xs[32][72];
+    __shared__ double red[8];
+    const int z = blockIdx.z, g = z / a.zper;
+    const int m0 = blockIdx.y * 64, t0 = blockIdx.x * 64;
+    const int M = a.M, K = a.K, Tp = a.Tp, P = a.P;
+    const float* W = a.W[g];
+    const float* X = a.X + (size_t)z * K * P;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+
+    float mean = 0.f, rstd = 1.f;
+    if (PRO == PRO_GLN) {
+        double su = a.stats_in[2 * z], sq = a.stats_in[2 * z + 1];
+        double mu = su / a.count_in;
+        double var = sq / a.count_in - mu * mu;
+        mean = (float)mu;
+        rstd = (float)(1.0 / sqrt((var > 0 ? var : 0) + 1e-8));
+    }
+    const float* gam = (PRO == PRO_GLN) ? a.gamma[g] : nullptr;
+    const float* bet = (PRO == PRO_GLN) ? a.beta[g] : nullptr;
+
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            int e = tid + 128 * j, r = e >> 5, c = e & 31;
+            float v = (m0 + r < M && k0 + c < K) ? W[(size_t)(m0 + r) * K + k0 + c] : 0.f;
+            Ws[r][c] = f2tf32(v);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            int e = tid + 128 * j, kk = e >> 6, tt = e & 63;
+            float v = 0.f;
+            if (k0 + kk < K && t0 + tt < Tp) {
+                v = X[(size_t)(k0 + kk) * P + t0 + tt];
+                if (PRO == PRO_GLN) v = fmaf((v - mean) * rstd, gam[k0 + kk], bet[k0 + kk]);
+                if (PRO == PRO_RELU) v = fmaxf(v, 0.f);
+            }
+            Xs[kk][tt] = f2tf32(v);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t af[2][4], bf[4][2];
+            const int r = lane >> 2, c = ks * 8 + (lane & 3);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                int rr = wm * 32 + mt * 16 + r;
+                af[mt][0] = Ws[rr][c]; af[mt][1] = Ws[rr + 8][c]; af[mt][2] = Ws[rr][c + 4]; af[mt][3] = Ws[rr + 8][c + 4];
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                int nn = wn * 32 + nt * 8 + (lane >> 2);
+                bf[nt][0] = Xs[ks * 8 + (lane & 3)][nn];
+                bf[nt][1] = Xs[ks * 8 + (lane & 3) + 4][nn];
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) mma_tf32_1688(acc[mt][nt], af[mt], bf[nt][0], bf[nt][1]);
+        }
+        __syncthreads();
+    }
+
+    const float* bias = a.bias[g];
+    float* Y = a.Y + (size_t)z * M * P;
+    const float slope = (EPI == EPI_PRELU_STATS) ? a.prelu[g][0] : 0.f;
+    double lsum = 0.0, lsq = 0.0;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int row = m0 + wm * 32 + mt * 16 + (lane >> 2) + ((q & 2) ? 8 : 0);
+                int col = t0 + wn * 32 + nt * 8 + 2 * (lane & 3) + (q & 1);
+                if (row < M && col < Tp) {
+                    float y = acc[mt][nt][q] + bias[row];
+                    if (EPI == EPI_PRELU_STATS) {
+                        y = (y >= 0.f) ? y : slope * y;
+                        lsum += (double)y; lsq += (double)y * (double)y;
+                    }
+                    if (EPI == EPI_RESIDUAL) y += a.R[(size_t)z * M * P + (size_t)row * P + col];
+                    if (EPI == EPI_ACT) {
+                        if (a.act == FSN_ACT_RELU) y = fmaxf(y, 0.f);
+                        else if (a.act == FSN_ACT_TANH) y = tanhf(y);
+                        else if (a.act == FSN_ACT_RELU6) y = fminf(fmaxf(y, 0.f), 6.f);
+                    }
+                    Y[(size_t)row * P + col] = y;
+                }
+            }
+    if (EPI == EPI_PRELU_STATS) {
+        lsum = warp_sum_d(lsum); lsq = warp_sum_d(lsq);
+        if (lane == 0) { red[warp] = lsum; red[4 + warp] = lsq; }
+        __syncthreads();
+        if (tid == 0) {
+            atomicAdd(&a.stats_out[2 * z], red[0] + red[1] + red[2] + red[3]);
+            atomicAdd(&a.stats_out[2 * z + 1], red[4] + red[5] + red[6] + red[7]);
+        }
+    }
+}
+
+void launch_conv1x1(const ConvLaunch& a, cudaStream_t s) {
+    dim3 grid((a.Tp + 63) / 64, (a.M + 63) / 64, a.Z), block(128);
+#define FSN_CONV_CASE(P_, E_) \
+    if (a.pro == P_ && a.epi == E_) { conv1x1_tf32_kernel<P_, E_><<<grid, block, 0, s>>>(a); return; }
+    FSN_CONV_CASE(PRO_NONE, EPI_PRELU_STATS)
+    FSN_CONV_CASE(PRO_GLN, EPI_RESIDUAL)
+    FSN_CONV_CASE(PRO_RELU, EPI_ACT)
+    FSN_CONV_CASE(PRO_NONE, EPI_ACT)
+    FSN_CONV_CASE(PRO_NONE, EPI_NONE)
+#undef FSN_CONV_CASE
+}
+
+// =============================================================================================
+// K3b: gLN1 apply -> depth-wise conv (k=3, dilation d, zero padding d in the normalised domain)
+//      -> PReLU2, accumulating the gLN2 statistics.  reference: causal_conv.py:100-106.
+// =============================================================================================
+__global__ void __launch_bounds__(256) dwconv_kernel(DwLaunch a) {
+    __shared__ double red[16];
+    const int z = blockIdx.z, g = z / a.zper;
+    const int C = a.C, Tp = a.Tp, P = a.P, d = a.dilation;
+    const double cnt = (double)C * (double)Tp;
+    const double mu = a.stats_in[2 * z] / cnt;
+    const double var = a.stats_in[2 * z + 1] / cnt - mu * mu;
+    const float mean = (float)mu, rstd = (float)(1.0 / sqrt((var > 0 ? var : 0) + 1e-8));
+    const float slope = a.prelu[g][0];
+    const int c0 = blockIdx.x * 8;
+    double lsum = 0.0, lsq = 0.0;
+    for (int e = threadIdx.x; e < 8 * Tp; e += blockDim.x) {
+        const int c = c0 + e / Tp, t = e % Tp;
+        if (c >= C) break;
+        const float* xr = a.X + ((size_t)z * C + c) * P;
+        const float ga = a.gamma[g][c] * rstd, be = a.beta[g][c] - mean * rstd * a.gamma[g][c];
+        float acc = a.b[g][c];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            int tt = t + (j - 1) * d;
+            if (tt >= 0 && tt < Tp) acc = fmaf(a.w[g][c * 3 + j], fmaf(xr[tt], ga, be), acc);
+        }
+        acc = (acc >= 0.f) ? acc : slope * acc;
+        a.Y[((size_t)z * C + c) * P + t] = acc;
+        lsum += (double)acc; lsq += (double)acc * (double)acc;
+    }
+    lsum = warp_sum_d(lsum); lsq = warp_sum_d(lsq);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[warp] = lsum; red[8 + warp] = lsq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s1 = 0, s2 = 0;
+        for (int i = 0; i < 8; ++i) { s1 += red[i]; s2 += red[8 + i]; }
+        atomicAdd(&a.stats_out[2 * z], s1);
+        atomicAdd(&a.stats_out[2 * z + 1], s2);
+    }
+}
+
+void launch_dwconv(const DwLaunch& a, cudaStream_t s) {
+    dwconv_kernel<<<dim3((a.C + 7) / 8, 1, a.Z), 256, 0, s>>>(a);
+}
+
+// =============================================================================================
+// K4: sub-band input.  reference: fullsubnet_plus.py:167-202 / fullsubnet.py:90-111 + base_model.py:15-47.
+// The [B, F, I, T'] unfolded tensor is never materialised in fp32: its utterance mean follows from
+// row sums (each reflected row counted as often as it appears in some window), and the normalised
+// values are written once, in fp16, directly in the per-step 128-row tile images the LSTM kernels
+// stream (K-major, SWIZZLE_128B, 64 halves per row; columns >= I and rows >= B*F are zero).
+// =============================================================================================
+__global__ void __launch_bounds__(256) sb_stats_kernel(SbPackLaunch a) {
+    extern __shared__ float sm[];
+    const int b = blockIdx.x, F = a.F, Tp = a.Tp;
+    float* Sw = sm;                 // [F]
+    float* Sf = Sw + F;             // [nfb][F]
+    __shared__ double red[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int r = warp; r < F * (1 + a.nfb); r += nwarp) {
+        const int which = r / F, f = r % F;
+        const float* row = (which == 0) ? a.win + ((size_t)b * F + f) * a.Pw : a.fb[which - 1] + ((size_t)b * F + f) * a.P;
+        float acc = 0.f;
+        for (int t = lane; t < Tp; t += 32) acc += row[t];
+        acc = warp_sum(acc);
+        if (lane == 0) sm[r] = acc;
+    }
+    __syncthreads();
+    double tot = 0.0;
+    const int nw = 2 * a.Ns + 1, nf = 2 * a.Nf + 1;
+    for (int e = threadIdx.x; e < F * nw; e += blockDim.x) tot += (double)Sw[reflect_idx(e / nw + e % nw - a.Ns, F)];
+    for (int k = 0; k < a.nfb; ++k)
+        for (int e = threadIdx.x; e < F * nf; e += blockDim.x) tot += (double)Sf[k * F + reflect_idx(e / nf + e % nf - a.Nf, F)];
+    tot = warp_sum_d(tot);
+    if (lane == 0) red[warp] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int i = 0; i < nwarp; ++i) s += red[i];
+        a.mu[b] = (float)(s / ((double)F * (double)(nw + a.nfb * nf) * (double)Tp));
+    }
+}
+
+void launch_sb_stats(const SbPackLaunch& a, cudaStream_t s) {
+    sb_stats_kernel<<<a.B, 256, sizeof(float) * a.F * (1 + a.nfb), s>>>(a);
+}
+
+__global__ void __launch_bounds__(128) sb_pack_kernel(SbPackLaunch a) {
+    const int f = blockIdx.x, b = blockIdx.y, F = a.F, Tp = a.Tp;
+    const int row = b * F + f, tile = row >> 7, r = row & 127;
+    const float inv = 1.0f / (a.mu[b] + 1e-5f);
+    const int nw = 2 * a.Ns + 1, nf = 2 * a.Nf + 1;
+    const int I = nw + a.nfb * nf;
+    for (int t = threadIdx.x; t < Tp; t += blockDim.x) {
+        auto val = [&](int k) -> float {          // k-th channel of the concatenated sub-band input
+            float v = 0.f;
+            if (k < nw) v = a.win[((size_t)b * F + reflect_idx(f + k - a.Ns, F)) * a.Pw + t];
+            else if (k < I) {
+                const int kk = k - nw, q = kk / nf, j = kk % nf;
+                const float* src = (q == 0) ? a.fb[0] : (q == 1) ? a.fb[1] : a.fb[2];
+                v = src[((size_t)b * F + reflect_idx(f + j - a.Nf, F)) * a.P + t];
+            }
+            return fminf(fmaxf(v * inv, -65504.f), 65504.f);
+        };
+        char* img = reinterpret_cast<char*>(a.ximg) + ((size_t)tile * Tp + t) * (128 * 128);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint4 u;
+            u.x = pack_half2(val(c * 8 + 0), val(c * 8 + 1));
+            u.y = pack_half2(val(c * 8 + 2), val(c * 8 + 3));
+            u.z = pack_half2(val(c * 8 + 4), val(c * 8 + 5));
+            u.w = pack_half2(val(c * 8 + 6), val(c * 8 + 7));
+            *reinterpret_cast<uint4*>(img + sw128_offset(r, c * 8)) = u;
+        }
+    }
+}
+
+void launch_sb_pack(const SbPackLaunch& a, cudaStream_t s) { sb_pack_kernel<<<dim3(a.F, a.B), 128, 0, s>>>(a); }
+
+__global__ void pad_copy_kernel(const float* x, float* y, int rows, int T, int P) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * P) return;
+    int t = (int)(i % P);
+    size_t r = i / P;
+    y[i] = (t < T) ? x[r * T + t] : 0.f;
+}
+void launch_pad_copy(const float* x, float* y, int B, int F, int T, int P, cudaStream_t s) {
+    size_t n = (size_t)B * F * P;
+    pad_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, B * F, T, P);
+}
+
+__global__ void fb_pack_kernel(const float* x, __half* y, int B, int F, int Tp, int P, int rows_pad, int Ipad) {
+    // y[t][b][k] = x[b][k][t]
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)Tp * rows_pad * Ipad) return;
+    int k = (int)(i % Ipad);
+    int b = (int)((i / Ipad) % rows_pad);
+    int t = (int)(i / ((size_t)Ipad * rows_pad));
+    float v = (b < B && k < F) ? x[((size_t)b * F + k) * P + t] : 0.f;
+    y[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+}
+void launch_fb_pack(const float* x, __half* y, int B, int F, int Tp, int P, int rows_pad, int Ipad, cudaStream_t s) {
+    size_t n = (size_t)Tp * rows_pad * Ipad;
+    fb_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, B, F, Tp, P, rows_pad, Ipad);
+}
+
+}  // namespace fsn

@@ -1,0 +1,333 @@
+// Persistent 2-layer LSTM + Linear for the 257*B independent sub-band sequences (K5 + K6 of SURVEY.md 2a)
+// on the 5th-generation tensor cores (tcgen05) of sm_100a.
+//
+// reference: FullSubNet_Plus.forward -> self.sb_model(sb_input) (fullsubnet_plus.py:205-208), i.e.
+//   SequenceModel.forward LSTM branch (audio_zen/model/module/sequence_model.py:113-122):
+//   nn.LSTM(I, H, 2, batch_first) + nn.Linear(H, 2), output re-laid out to [B, 2, F, T] and the first
+//   look_ahead frames dropped.
+//
+// Design:
+//   * one CTA = 128 sequences (the 128 TMEM lanes) for ALL time steps and BOTH layers;
+//   * the recurrent operands h0/h1 live in TENSOR MEMORY as packed fp16 (192 columns each for H=384)
+//     and are fed to tcgen05.mma as the A operand (A-from-TMEM form) -- they never touch shared or
+//     global memory; the two 64-column fp32 accumulators occupy the remaining 128 TMEM columns;
+//   * the weights (3.6 MB fp16 for H=384) are streamed from L2 every step as pre-swizzled 8 KB
+//     K-major tiles through a ring of shared-memory stages filled by 1-D bulk async copies (TMA engine,
+//     mbarrier complete_tx), in exactly the order the MMA issuer consumes them;
+//   * each layer-step's gate matrix [128, 4H] is produced in chunks of 64 columns (16 hidden units x
+//     i,f,g,o); two epilogue warpgroups alternate on the two accumulators so the cell update of chunk j
+//     overlaps the MMAs of chunk j+1;
+//   * fp32 cell state goes through an L2-resident scratch private to the CTA (coalesced float4);
+//   * new hidden values are parked (thread-private shared memory) until the layer-step's last MMA has
+//     retired, then written back to TMEM with tcgen05.st;
+//   * Linear(H, 2) is accumulated from the fp32 hidden values in the layer-1 epilogue and the mask is
+//     written directly in the reference's [B, 2, F, T] layout.
+#include "fsn_common.cuh"
+#include "fsn_kernels.h"
+#include "../../include/fsnplus_b200.h"
+
+#include <cstring>
+#include <vector>
+
+namespace fsn {
+
+constexpr int TC5_STAGE = 8192;     // 64 gate columns x 64 k x fp16, SWIZZLE_128B
+constexpr int TC5_XIMG = 16384;     // 128 rows x 64 k x fp16, SWIZZLE_128B
+constexpr int TC5_THREADS = 384;    // warp 0 producer, 1 MMA issuer, 2 TMEM alloc, 3 idle, 4-11 epilogue
+constexpr int TC5_MAX_SMEM = 227 * 1024;
+
+struct Tc5Plan { int nstage; size_t fixed, total; };
+static inline Tc5Plan tc5_plan(int H) {
+    Tc5Plan p;
+    p.fixed = 2 * TC5_XIMG + (size_t)128 * H * 2 /*park*/ + (size_t)2 * 4 * H * 4 /*bias*/ + (size_t)2 * H * 4 /*fc*/ +
+              2 * 128 * 2 * 4 /*fcpart*/ + 64 * 8 /*barriers*/ + 64;
+    long avail = TC5_MAX_SMEM - 1024 /*alignment slack*/ - (long)p.fixed;
+    p.nstage = (int)(avail / TC5_STAGE);
+    if (p.nstage > 24) p.nstage = 24;
+    p.total = p.fixed + (size_t)p.nstage * TC5_STAGE + 1024;
+    return p;
+}
+
+bool lstm_tc5_supported(int L, int H, int I, int O) { return L == 2 && H % 64 == 0 && H >= 64 && H <= 384 && I <= 64 && O == 2; }
+
+size_t lstm_tc5_cstate_bytes(int ntiles, int H) { return (size_t)ntiles * 2 * H * 128 * sizeof(float); }
+
+template <bool FAST>
+__global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch a, int nstage) {
+    extern __shared__ uint8_t smem_raw[];
+    const int H = a.H, NCH = H / 16, KBH = H / 64, hcols = H / 2, Tp = a.Tp;
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* stages = smem;
+    uint8_t* ximg = stages + (size_t)nstage * TC5_STAGE;
+    uint8_t* park = ximg + 2 * TC5_XIMG;
+    float* biasp = reinterpret_cast<float*>(park + (size_t)128 * H * 2);
+    float* fcw = biasp + 2 * 4 * H;
+    float* fcpart = fcw + 2 * H;                                   // [2][128][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fcpart + 2 * 128 * 2);
+    uint64_t* full = bars;
+    uint64_t* empty = full + nstage;
+    uint64_t* xfull = empty + nstage;
+    uint64_t* xempty = xfull + 2;
+    uint64_t* accfull = xempty + 2;
+    uint64_t* accempty = accfull + 2;
+    uint64_t* hready = accempty + 2;
+    uint64_t* layerdone = hready + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layerdone + 1);
+
+    if (tid == 0) {
+        for (int i = 0; i < nstage; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1);
+            mbar_init(&accfull[i], 1); mbar_init(&accempty[i], 128);
+        }
+        mbar_init(hready, 256);
+        mbar_init(layerdone, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    for (int i = tid; i < 2 * 4 * H; i += TC5_THREADS) biasp[i] = a.bias[i];
+    for (int i = tid; i < 2 * H; i += TC5_THREADS) fcw[i] = a.fc_w[i];
+    tc5_fence_before();
+    __syncthreads();
+    tc5_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t acc_col = 2 * hcols;
+    const int SPS = NCH * (1 + KBH) + NCH * 2 * KBH;               // weight stages per time step
+
+    if (warp == 0) {
+        // ======================= bulk-copy producer =======================================
+        if (lane == 0) {
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wstream);
+            const uint8_t* xsrc = reinterpret_cast<const uint8_t*>(a.img) + (size_t)tile * Tp * TC5_XIMG;
+            int slot = 0; uint32_t ph = 0;
+            mbar_arrive_expect_tx(&xfull[0], TC5_XIMG);
+            bulk_g2s(ximg, xsrc, TC5_XIMG, &xfull[0]);
+            for (int t = 0; t < Tp; ++t) {
+                if (t + 1 < Tp) {
+                    const int xb = (t + 1) & 1, n = (t + 1) >> 1;
+                    mbar_wait(&xempty[xb], (n & 1) ^ 1);
+                    mbar_arrive_expect_tx(&xfull[xb], TC5_XIMG);
+                    bulk_g2s(ximg + xb * TC5_XIMG, xsrc + (size_t)(t + 1) * TC5_XIMG, TC5_XIMG, &xfull[xb]);
+                }
+                for (int s = 0; s < SPS; ++s) {
+                    mbar_wait(&empty[slot], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[slot], TC5_STAGE);
+                    bulk_g2s(stages + (size_t)slot * TC5_STAGE, wsrc + (size_t)s * TC5_STAGE, TC5_STAGE, &full[slot]);
+                    if (++slot == nstage) { slot = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer (one thread) ==================================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(128, 64);
+            int slot = 0; uint32_t ph = 0, accuse[2] = {0, 0}, ls = 0;
+            for (int t = 0; t < Tp; ++t) {
+                for (int layer = 0; layer < 2; ++layer, ++ls) {
+                    mbar_wait(hready, ls & 1);                     // h operands of this layer-step are in TMEM
+                    uint64_t xdesc = 0;
+                    if (layer == 0) {
+                        mbar_wait(&xfull[t & 1], (t >> 1) & 1);
+                        xdesc = umma_desc_sw128(smem_u32(ximg + (t & 1) * TC5_XIMG));
+                    }
+                    tc5_fence_after();
+                    const int nkb = (layer == 0) ? 1 + KBH : 2 * KBH;
+                    for (int j = 0; j < NCH; ++j) {
+                        const int buf = j & 1;
+                        mbar_wait(&accempty[buf], (accuse[buf] & 1) ^ 1);
+                        ++accuse[buf];
+                        tc5_fence_after();
+                        const uint32_t d = tmem + acc_col + buf * 64;
+                        for (int kb = 0; kb < nkb; ++kb) {
+                            mbar_wait(&full[slot], ph);
+                            tc5_fence_after();
+                            const uint64_t bdesc = umma_desc_sw128(smem_u32(stages + (size_t)slot * TC5_STAGE));
+                            if (layer == 0 && kb == 0) {
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) umma_ss(d, xdesc + 2 * kk, bdesc + 2 * kk, idesc, kk != 0);
+                            } else {
+                                const uint32_t acol = (layer == 0) ? (kb - 1) * 32 : (kb < KBH ? kb * 32 : hcols + (kb - KBH) * 32);
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma_ts(d, tmem + acol + kk * 8, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+                            }
+                            umma_commit(&empty[slot]);             // stage reusable once these MMAs retire
+                            if (++slot == nstage) { slot = 0; ph ^= 1; }
+                        }
+                        umma_commit(&accfull[buf]);
+                    }
+                    if (layer == 0) umma_commit(&xempty[t & 1]);
+                    umma_commit(layerdone);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ======================= epilogue warpgroups ======================================
+        const int wg = (warp - 4) >> 2;
+        const int q = warp & 3;                                    // TMEM lane quarter of this warp
+        const int r = q * 32 + lane;                               // sequence (row) inside the tile
+        const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+        {
+            const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            // each warpgroup zeroes half of the h columns of its lanes
+            for (int c = wg * (NCH / 2); c < (wg + 1) * (NCH / 2); ++c) { tmem_st8(tl + c * 8, z); tmem_st8(tl + hcols + c * 8, z); }
+            tmem_wait_st();
+            tc5_fence_before();
+            mbar_arrive(hready);
+        }
+        uint32_t accn = 0, ls = 0;
+        float* cbase = a.cstate + (size_t)tile * 2 * H * 128;
+        uint8_t* mypark = park + ((size_t)wg * (NCH / 2) * 128 + r) * 32;
+        const int grow = tile * 128 + r;
+        const int ob = grow / a.F, of = grow % a.F;
+        const int Tout = Tp - a.la;
+
+        for (int t = 0; t < Tp; ++t) {
+            for (int layer = 0; layer < 2; ++layer, ++ls) {
+                float fc0 = 0.f, fc1 = 0.f;
+                for (int jj = 0; jj < NCH / 2; ++jj) {
+                    const int j = 2 * jj + wg;
+                    float4* cp = reinterpret_cast<float4*>(cbase + ((size_t)(layer * NCH + j) * 4) * 128 * 4) + r;
+                    float4 c4[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c4[i] = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[i * 128];
+                    mbar_wait(&accfull[wg], accn & 1);
+                    ++accn;
+                    tc5_fence_after();
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) tmem_ld16(tl + acc_col + wg * 64 + g * 16, v[g]);
+                    tmem_wait_ld();
+                    tc5_fence_before();
+                    mbar_arrive(&accempty[wg]);
+
+                    const float* bj = biasp + (size_t)(layer * NCH + j) * 64;
+                    const float* w0 = fcw + j * 16;
+                    const float* w1 = fcw + H + j * 16;
+                    uint32_t hp[8];
+                    float cn[16];
+                    const float cpv[16] = {c4[0].x, c4[0].y, c4[0].z, c4[0].w, c4[1].x, c4[1].y, c4[1].z, c4[1].w,
+                                           c4[2].x, c4[2].y, c4[2].z, c4[2].w, c4[3].x, c4[3].y, c4[3].z, c4[3].w};
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const float gi = __uint_as_float(v[0][u]) + bj[u];
+                        const float gf = __uint_as_float(v[1][u]) + bj[16 + u];
+                        const float gg = __uint_as_float(v[2][u]) + bj[32 + u];
+                        const float go = __uint_as_float(v[3][u]) + bj[48 + u];
+                        const float cprev = cpv[u];
+                        const float c = sigm<FAST>(gf) * cprev + sigm<FAST>(gi) * tanh_<FAST>(gg);
+                        const float h = sigm<FAST>(go) * tanh_<FAST>(c);
+                        cn[u] = c;
+                        if (layer == 1) { fc0 = fmaf(h, w0[u], fc0); fc1 = fmaf(h, w1[u], fc1); }
+                        if (u & 1) hp[u >> 1] = pack_half2(__uint_as_float(hp[u >> 1]), h); else hp[u >> 1] = __float_as_uint(h);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cp[i * 128] = make_float4(cn[4 * i], cn[4 * i + 1], cn[4 * i + 2], cn[4 * i + 3]);
+                    uint4* pk = reinterpret_cast<uint4*>(mypark + (size_t)jj * 128 * 32);
+                    pk[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                    pk[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+                }
+                // every MMA of this layer-step has retired -> h_{t-1} may be overwritten in TMEM
+                mbar_wait(layerdone, ls & 1);
+                tc5_fence_after();
+                for (int jj = 0; jj < NCH / 2; ++jj) {
+                    const int j = 2 * jj + wg;
+                    const uint4* pk = reinterpret_cast<const uint4*>(mypark + (size_t)jj * 128 * 32);
+                    const uint4 p0 = pk[0], p1 = pk[1];
+                    const uint32_t hv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                    tmem_st8(tl + layer * hcols + j * 8, hv);
+                }
+                tmem_wait_st();
+                tc5_fence_before();
+                mbar_arrive(hready);
+
+                if (layer == 1) {
+                    float* part = fcpart + (size_t)(t & 1) * 256;
+                    if (wg == 1) { part[2 * r] = fc0; part[2 * r + 1] = fc1; }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (wg == 0 && t >= a.la && grow < a.rows) {
+                        const float o0 = fc0 + part[2 * r] + a.fc_b[0];
+                        const float o1 = fc1 + part[2 * r + 1] + a.fc_b[1];
+                        a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)] = o0;
+                        a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)] = o1;
+                    }
+                }
+            }
+        }
+    }
+    tc5_fence_before();
+    __syncthreads();
+    tc5_fence_after();
+    if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+int launch_lstm_tc5(const LstmTc5Launch& a, cudaStream_t s) {
+    if (!lstm_tc5_supported(2, a.H, a.I, 2)) return (int)cudaErrorInvalidValue;
+    const Tc5Plan p = tc5_plan(a.H);
+    if (p.nstage < 4) return (int)cudaErrorInvalidValue;
+    cudaError_t e;
+    if (a.fast) {
+        e = cudaFuncSetAttribute(lstm_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);
+        if (e != cudaSuccess) return (int)e;
+        lstm_tc5_kernel<true><<<a.ntiles, TC5_THREADS, p.total, s>>>(a, p.nstage);
+    } else {
+        e = cudaFuncSetAttribute(lstm_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);
+        if (e != cudaSuccess) return (int)e;
+        lstm_tc5_kernel<false><<<a.ntiles, TC5_THREADS, p.total, s>>>(a, p.nstage);
+    }
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side packing of the weight stream (exposed through the C ABI for CPU layout tests).
+// Stream order per time step: layer 0, chunk j = 0..H/16-1: [x block][H/64 hidden blocks];
+//                             layer 1, chunk j:              [H/64 blocks of W_ih1][H/64 blocks of W_hh1].
+// Stage = 64 gate columns (n = q*16 + u  <->  weight row q*H + 16 j + u, q in i,f,g,o) x 64 k, K-major,
+// SWIZZLE_128B.
+// ---------------------------------------------------------------------------------------------
+static inline uint16_t f2h_bits(float f) {
+    __half h = __float2half_rn(f);
+    uint16_t b;
+    std::memcpy(&b, &h, 2);
+    return b;
+}
+
+}  // namespace fsn
+
+extern "C" int64_t fsn_tc5_weight_stream_bytes(int32_t I, int32_t H) {
+    if (H % 64 || I > 64) return -1;
+    const int NCH = H / 16, KBH = H / 64;
+    return (int64_t)(NCH * (1 + KBH) + NCH * 2 * KBH) * fsn::TC5_STAGE;
+}
+
+extern "C" int fsn_tc5_pack_weights(int32_t I, int32_t H, const float* w_ih0, const float* w_hh0, const float* w_ih1,
+                                    const float* w_hh1, uint16_t* dst) {
+    if (H % 64 || I > 64) return FSN_EINVAL;
+    const int NCH = H / 16, KBH = H / 64;
+    size_t s = 0;
+    auto stage = [&](auto&& getw) {
+        uint8_t* img = reinterpret_cast<uint8_t*>(dst) + s * fsn::TC5_STAGE;
+        for (int n = 0; n < 64; ++n)
+            for (int k = 0; k < 64; ++k) {
+                uint16_t b = fsn::f2h_bits(getw(n, k));
+                std::memcpy(img + fsn::sw128_offset(n, k), &b, 2);
+            }
+        ++s;
+    };
+    for (int j = 0; j < NCH; ++j) {
+        auto row = [&](int n) { return (n / 16) * H + 16 * j + (n % 16); };
+        stage([&](int n, int k) { return k < I ? w_ih0[(size_t)row(n) * I + k] : 0.f; });
+        for (int kb = 0; kb < KBH; ++kb) stage([&](int n, int k) { return w_hh0[(size_t)row(n) * H + kb * 64 + k]; });
+    }
+    for (int j = 0; j < NCH; ++j) {
+        auto row = [&](int n) { return (n / 16) * H + 16 * j + (n % 16); };
+        for (int kb = 0; kb < KBH; ++kb) stage([&](int n, int k) { return w_ih1[(size_t)row(n) * H + kb * 64 + k]; });
+        for (int kb = 0; kb < KBH; ++kb) stage([&](int n, int k) { return w_hh1[(size_t)row(n) * H + kb * 64 + k]; });
+    }
+    return FSN_OK;
+}
+
+extern "C" uint32_t fsn_sw128_offset(uint32_t row, uint32_t k) { return fsn::sw128_offset(row, k); }

@@ -1,0 +1,128 @@
+/*
+ * fsnplus_b200 -- C ABI of the B200-native FullSubNet+/FullSubNet inference forward.
+ *
+ * This is the drop-in boundary for ONE path of RookieJunChen/FullSubNet-plus: the model forward
+ *   speech_enhance/fullsubnet_plus/model/fullsubnet_plus.py:122-209  (FullSubNet_Plus.forward)
+ *   speech_enhance/fullsubnet/model/fullsubnet.py:68-118             (Model.forward)
+ * as called by the inferencer at
+ *   speech_enhance/fullsubnet_plus/inferencer/inferencer.py:150 and :123.
+ * The reference has no FFI of its own (it is pure Python/PyTorch); the Python mirror in
+ * fullsubnet-plus_b200/fsnplus_b200/model.py binds these entry points with ctypes and exposes the
+ * reference's nn.Module constructors / forward signatures / state_dict keys.
+ *
+ * Conventions: plain C types only; every pointer named d_* is a CUDA device pointer, h_* a host
+ * pointer; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all entry points
+ * return 0 on success or a negative FSN_E* code, with a message available from fsn_last_error().
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with FSN_ECUDA.
+ */
+#ifndef FSNPLUS_B200_H_
+#define FSNPLUS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSN_OK 0
+#define FSN_EINVAL (-1)  /* bad argument / unsupported configuration (the reference raises/asserts) */
+#define FSN_ECUDA (-2)   /* CUDA runtime error (including "no device")                              */
+#define FSN_ESTATE (-3)  /* call order error (e.g. forward before finalize, missing parameter)      */
+
+/* model_kind */
+#define FSN_KIND_PLUS 0 /* fullsubnet_plus.model.fullsubnet_plus.FullSubNet_Plus (fullsubnet_plus.py:16) */
+#define FSN_KIND_FSN 1  /* fullsubnet.model.fullsubnet.Model                      (fullsubnet.py:12)      */
+
+/* activations: audio_zen/model/module/sequence_model.py:84-93 */
+#define FSN_ACT_NONE 0
+#define FSN_ACT_RELU 1
+#define FSN_ACT_TANH 2
+#define FSN_ACT_RELU6 3
+
+/* norm_type: audio_zen/model/base_model.py:318-330 (norm_wrapper) */
+#define FSN_NORM_OFFLINE_LAPLACE 0
+#define FSN_NORM_CUMULATIVE_LAPLACE 1
+#define FSN_NORM_OFFLINE_GAUSSIAN 2
+#define FSN_NORM_CUMULATIVE_LAYER 3
+
+/* lstm_impl */
+#define FSN_LSTM_AUTO 0
+#define FSN_LSTM_MMA 1     /* generic mma.sync kernel (any hidden size / layer count)               */
+#define FSN_LSTM_TCGEN05 2 /* persistent tcgen05/TMEM kernel (2 layers, hidden <= 384, input <= 64) */
+
+typedef struct fsn_config {
+    int32_t model_kind;
+    int32_t num_freqs;        /* F                                   (config/inference.toml:33) */
+    int32_t look_ahead;       /*                                      (:34)                      */
+    int32_t sb_num_neighbors; /*                                      (:31)                      */
+    int32_t fb_num_neighbors; /*                                      (:32)                      */
+    int32_t fb_hidden;        /* fb_model_hidden_size (LSTM full band; ignored by the TCN)       */
+    int32_t sb_hidden;        /* sb_model_hidden_size                 (:40)                      */
+    int32_t num_layers;       /* 2 in the reference (fullsubnet_plus.py:76,106); additive knob   */
+    int32_t output_size;      /* 2                                    (fullsubnet_plus.py:31)    */
+    int32_t fb_act;           /* fb_output_activate_function          (:36)                      */
+    int32_t sb_act;           /* sb_output_activate_function          (:37)                      */
+    int32_t norm_type;        /*                                      (:42)                      */
+    int32_t kersize[3];       /* TSSE kernel sizes                    (:44)                      */
+    int32_t lstm_impl;        /* FSN_LSTM_*                                                      */
+    int32_t fast_math;        /* 0: ex2/rcp gates (default); 1: tanh.approx gates                */
+} fsn_config;
+
+typedef struct fsn_model fsn_model;
+
+int fsn_version(void);
+const char* fsn_last_error(void);
+
+/* Replaces FullSubNet_Plus.__init__ / Model.__init__ (fullsubnet_plus.py:17-120, fullsubnet.py:13-66):
+ * validates the configuration and creates an empty parameter store on the current CUDA device. */
+int fsn_model_create(const fsn_config* cfg, fsn_model** out);
+void fsn_model_destroy(fsn_model* m);
+
+/* Replaces nn.Module.load_state_dict for this module tree (audio_zen/inferencer/base_inferencer.py:104):
+ * `key` is the reference state_dict key, `h_data` float32 host data in the reference's shape. */
+int fsn_model_set_param(fsn_model* m, const char* key, const float* h_data, int64_t numel);
+/* Number of keys the configuration expects / i-th expected key and its element count. */
+int fsn_model_num_params(const fsn_model* m);
+int fsn_model_param_info(const fsn_model* m, int index, const char** key, int64_t* numel);
+/* Re-orders / converts the parameters into the kernel layouts (fp16 gate-interleaved LSTM images, ...). */
+int fsn_model_finalize(fsn_model* m);
+
+/* Replaces FullSubNet_Plus.forward(noisy_mag, noisy_real, noisy_imag) (fullsubnet_plus.py:122-209) and
+ * Model.forward(noisy_mag) (fullsubnet.py:68-118; pass d_real = d_imag = NULL).
+ * Inputs: [B, 1, F, T] float32, contiguous, device.  Output: [B, output_size, F, T] float32, contiguous,
+ * device, caller-owned.  Every sample is processed independently (the eval semantics of the reference
+ * called with batch 1; the training-only drop_band of fullsubnet_plus.py:192-196 is never applied). */
+int fsn_model_forward(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                      float* d_out, void* stream);
+/* Same call with HOST buffers (pinned or pageable): H2D copies, the forward and the D2H copy of the
+ * mask are all enqueued on `stream` and the call returns after the result is in h_out. */
+int fsn_model_forward_host(fsn_model* m, const float* h_mag, const float* h_real, const float* h_imag, int32_t B, int32_t T,
+                           float* h_out, void* stream);
+
+/* Test hooks: copy an intermediate of the LAST forward to a device buffer.
+ *   "fb_in"  [nbranch, B, F, T+look_ahead]  post-norm (and post-attention) full-band inputs
+ *   "fb_out" [nbranch, B, F, T+look_ahead]  full-band model outputs
+ *   "sb_mu"  [B]                            utterance mean of the (un-normalised) sub-band input */
+int fsn_model_get_stage(fsn_model* m, const char* name, float* d_dst, int64_t numel, void* stream);
+/* Kernels launched by the last forward (bench.py reports it as gpu_launches). */
+int64_t fsn_model_last_launch_count(const fsn_model* m);
+/* Which LSTM implementation the last forward used for the sub-band model (FSN_LSTM_MMA / _TCGEN05). */
+int fsn_model_last_lstm_impl(const fsn_model* m);
+
+/* Host-side packers exposed for CPU tests of the kernel layouts (no GPU needed). */
+/* 128-row x 64-half tile with the SWIZZLE_128B layout: byte offset of element (row, k). */
+uint32_t fsn_sw128_offset(uint32_t row, uint32_t k);
+/* Size in bytes and content of the tcgen05 weight stream for a 2-layer LSTM. */
+int64_t fsn_tc5_weight_stream_bytes(int32_t input_size, int32_t hidden);
+int fsn_tc5_pack_weights(int32_t input_size, int32_t hidden, const float* w_ih0, const float* w_hh0, const float* w_ih1,
+                         const float* w_hh1, uint16_t* h_dst /* fp16 bits */);
+
+/* tcgen05 / TMEM / bulk-copy self-test used by the GPU test-suite (tests/test_gpu_probe.py):
+ * runs tiny single-CTA GEMMs through every instruction form the persistent kernel relies on and
+ * writes max-abs-errors into h_report[0..n).  Returns the number of entries written or < 0. */
+int fsn_probe_tcgen05(float* h_report, int32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSNPLUS_B200_H_ */

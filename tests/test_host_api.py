@@ -1,0 +1,129 @@
+"""CPU: the C-ABI library loads and exports every symbol include/fsnplus_b200.h declares, the host-side
+mirror reproduces the reference's constructor / state_dict contract, the kernel-layout packers are correct,
+and the product path fails loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fsn_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, "include", "fsnplus_b200.h")).read()
+    declared = set(re.findall(r"\b(fsn_[a-z0-9_]+)\s*\(", header))
+    from fsnplus_b200 import _lib
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(built_lib, name) is not None
+    assert built_lib.fsn_version() >= 100
+
+
+def test_state_dict_contract_plus():
+    """Keys and shapes must equal the reference's state_dict (tests/golden/make_golden.py loaded the same
+    dict into the unmodified reference with strict=True)."""
+    from fsnplus_b200.model import FullSubNet_Plus
+    cfg = O.default_plus_config()
+    m = FullSubNet_Plus(**cfg)
+    ref = O.make_params_plus(cfg, seed=0)
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(ref.keys())
+    for k, v in ref.items():
+        assert tuple(sd[k].shape) == v.shape, k
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in ref.items()}, strict=True)
+    assert sum(p.numel() for p in m.parameters()) == 8675102
+    assert m.num_groups_in_drop_band == 2 and m.look_ahead == 2
+
+
+def test_state_dict_contract_fsn():
+    from fsnplus_b200.model import Model
+    cfg = O.default_fsn_config()
+    m = Model(**cfg)
+    ref = O.make_params_fsn(cfg, seed=1)
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(ref.keys())
+    for k, v in ref.items():
+        assert tuple(sd[k].shape) == v.shape, k
+    assert sum(p.numel() for p in m.parameters()) == 5637635
+
+
+def test_constructor_errors_mirror_reference():
+    from fsnplus_b200.model import FullSubNet_Plus, Model
+    cfg = O.default_plus_config()
+    with pytest.raises(AssertionError):
+        FullSubNet_Plus(**{**cfg, "sequence_model": "RNN"})             # fullsubnet_plus.py:45
+    with pytest.raises(NotImplementedError):
+        FullSubNet_Plus(**{**cfg, "channel_attention_model": "XYZ"})    # fullsubnet_plus.py:70
+    with pytest.raises(NotImplementedError):
+        FullSubNet_Plus(**{**cfg, "norm_type": "forgetting_norm"})      # base_model.py:328
+    with pytest.raises(AssertionError):
+        Model(**{**O.default_fsn_config(), "sequence_model": "TCN"})    # fullsubnet.py:37
+
+
+def test_no_cpu_fallback(built_lib):
+    from fsnplus_b200.model import FullSubNet_Plus
+    from fsnplus_b200 import _lib
+    cfg = O.default_plus_config()
+    cfg.update(num_freqs=33, sb_num_neighbors=3, sb_model_hidden_size=32)
+    m = FullSubNet_Plus(**cfg).eval()
+    x = torch.rand(1, 1, 33, 20)
+    with pytest.raises(RuntimeError):
+        m(x, x, x)                                                       # CPU tensors are refused
+    with pytest.raises(AssertionError):
+        m(x[0], x[0], x[0])                                              # dim() == 4 (fullsubnet_plus.py:136)
+    with pytest.raises(NotImplementedError):
+        m.train()(x, x, x)
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        rc = built_lib.fsn_model_create(C.byref(m._cfg), C.byref(h))
+        assert rc == -2 and b"no CPU fallback" in built_lib.fsn_last_error()
+
+
+def test_sw128_offsets(built_lib):
+    seen = set()
+    for r in range(128):
+        for k in range(64):
+            off = built_lib.fsn_sw128_offset(r, k)
+            assert off == r * 128 + ((((k >> 3) ^ (r & 7)) & 7) << 4) + ((k & 7) << 1)
+            seen.add(off)
+    assert len(seen) == 128 * 64 and max(seen) == 128 * 128 - 2
+
+
+def test_tc5_weight_stream_layout(built_lib):
+    """The stream must hold, stage by stage in consumption order, 64 gate columns x 64 k tiles whose un-swizzled
+    content is the (i,f,g,o)-interleaved slice of [W_ih | W_hh] the kernel's MMA schedule expects."""
+    I, H = 34, 128
+    rng = np.random.default_rng(0)
+    w = [rng.standard_normal(s).astype(np.float32) for s in ((4 * H, I), (4 * H, H), (4 * H, H), (4 * H, H))]
+    nbytes = built_lib.fsn_tc5_weight_stream_bytes(I, H)
+    NCH, KBH = H // 16, H // 64
+    assert nbytes == (NCH * (1 + KBH) + NCH * 2 * KBH) * 8192
+    buf = np.zeros(nbytes // 2, np.uint16)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    assert built_lib.fsn_tc5_pack_weights(I, H, vp(w[0]), vp(w[1]), vp(w[2]), vp(w[3]), vp(buf)) == 0
+    st = buf.view(np.float16).reshape(-1, 4096)
+    # un-swizzle index map
+    off = np.array([[built_lib.fsn_sw128_offset(n, k) // 2 for k in range(64)] for n in range(64)])
+    s = 0
+    for layer in range(2):
+        for j in range(NCH):
+            rows = np.array([(n // 16) * H + 16 * j + (n % 16) for n in range(64)])
+            blocks = []
+            if layer == 0:
+                x = np.zeros((64, 64), np.float32); x[:, :I] = w[0][rows]
+                blocks.append(x)
+                blocks += [w[1][rows][:, kb * 64:(kb + 1) * 64] for kb in range(KBH)]
+            else:
+                blocks += [w[2][rows][:, kb * 64:(kb + 1) * 64] for kb in range(KBH)]
+                blocks += [w[3][rows][:, kb * 64:(kb + 1) * 64] for kb in range(KBH)]
+            for blk in blocks:
+                got = st[s][off]
+                assert np.array_equal(got, blk.astype(np.float16)), (layer, j, s)
+                s += 1
+    assert s == st.shape[0]
+    assert built_lib.fsn_tc5_weight_stream_bytes(34, 100) == -1           # unsupported geometry
