@@ -63,6 +63,9 @@ struct fsn_model {
     DevBuf fbin, fbout, xa, xb, y1, y2, stats, mu, ximg, cstate, magpad, fbx, hseq, stage_in[3], stage_out;
     int64_t launches = 0;
     int last_impl = 0;
+    static const int NEV = 32;
+    cudaEvent_t ev0[NEV] = {}, ev1[NEV] = {};
+    int64_t nfwd = 0;                                 // forwards whose LSTM events were recorded
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -207,6 +210,7 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     fsn_model* m = new fsn_model();
     m->cfg = c;
     build_specs(m);
+    for (int i = 0; i < fsn_model::NEV; ++i) { cudaEventCreate(&m->ev0[i]); cudaEventCreate(&m->ev1[i]); }
     if (m->Isb > 64) { delete m; return fail(FSN_EINVAL, "sub-band input size %d > 64 not supported", m->Isb); }
     *out = m;
     return FSN_OK;
@@ -218,6 +222,7 @@ extern "C" void fsn_model_destroy(fsn_model* m) {
                      &m->mu, &m->ximg, &m->cstate, &m->magpad, &m->fbx, &m->hseq, &m->stage_in[0], &m->stage_in[1], &m->stage_in[2],
                      &m->stage_out};
     for (auto* b : all) b->release();
+    for (int i = 0; i < fsn_model::NEV; ++i) { if (m->ev0[i]) cudaEventDestroy(m->ev0[i]); if (m->ev1[i]) cudaEventDestroy(m->ev1[i]); }
     for (int i = 0; i < 4; ++i) { m->sb_frag[i].release(); m->sb_bias[i].release(); m->fb_frag[i].release(); m->fb_bias[i].release(); }
     delete m;
 }
@@ -504,8 +509,12 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
     }
     launch_sb_stats(sp, s); m->launches++;
     launch_sb_pack(sp, s); m->launches++;
+    const int evi = (int)(m->nfwd % fsn_model::NEV);
+    cudaEventRecord(m->ev0[evi], s);
     rc = run_sb_lstm(m, B, T, d_out, s);
+    cudaEventRecord(m->ev1[evi], s);
     if (rc) return rc;
+    m->nfwd++;
     CK(cudaGetLastError());
     return FSN_OK;
 }
@@ -555,6 +564,22 @@ extern "C" int fsn_model_get_stage(fsn_model* m, const char* name, float* d_dst,
 }
 
 extern "C" int64_t fsn_model_last_launch_count(const fsn_model* m) { return m ? m->launches : 0; }
+extern "C" int fsn_model_lstm_ms_history(fsn_model* m, float* h_ms, int32_t n) {
+    if (!m || !h_ms || n < 1) return 0;
+    int64_t avail = m->nfwd < fsn_model::NEV ? m->nfwd : fsn_model::NEV;
+    if (n > avail) n = (int32_t)avail;
+    for (int i = 0; i < n; ++i) {
+        const int evi = (int)((m->nfwd - n + i) % fsn_model::NEV);
+        float ms = -1.f;
+        if (cudaEventSynchronize(m->ev1[evi]) != cudaSuccess || cudaEventElapsedTime(&ms, m->ev0[evi], m->ev1[evi]) != cudaSuccess) ms = -1.f;
+        h_ms[i] = ms;
+    }
+    return n;
+}
+extern "C" float fsn_model_last_lstm_ms(fsn_model* m) {
+    float ms = -1.f;
+    return fsn_model_lstm_ms_history(m, &ms, 1) == 1 ? ms : -1.f;
+}
 extern "C" int fsn_model_last_lstm_impl(const fsn_model* m) { return m ? m->last_impl : 0; }
 
 extern "C" int fsn_probe_tcgen05(float* h_report, int32_t n) {

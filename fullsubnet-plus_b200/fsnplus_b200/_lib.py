@@ -14,7 +14,7 @@ LSTM_IMPL = {"auto": 0, "mma": 1, "tcgen05": 2}
 SYMBOLS = [
     "fsn_version", "fsn_last_error", "fsn_model_create", "fsn_model_destroy", "fsn_model_set_param",
     "fsn_model_num_params", "fsn_model_param_info", "fsn_model_finalize", "fsn_model_forward",
-    "fsn_model_forward_host", "fsn_model_get_stage", "fsn_model_last_launch_count", "fsn_model_last_lstm_impl",
+    "fsn_model_forward_host", "fsn_model_get_stage", "fsn_model_last_launch_count", "fsn_model_last_lstm_impl", "fsn_model_last_lstm_ms", "fsn_model_lstm_ms_history",
     "fsn_sw128_offset", "fsn_tc5_weight_stream_bytes", "fsn_tc5_pack_weights", "fsn_probe_tcgen05",
 ]
 
@@ -60,6 +60,9 @@ def load_library():
     lib.fsn_model_last_launch_count.argtypes = [vp]
     lib.fsn_model_last_launch_count.restype = i64
     lib.fsn_model_last_lstm_impl.argtypes = [vp]
+    lib.fsn_model_last_lstm_ms.argtypes = [vp]
+    lib.fsn_model_last_lstm_ms.restype = C.c_float
+    lib.fsn_model_lstm_ms_history.argtypes = [vp, fp, i32]
     lib.fsn_sw128_offset.argtypes = [C.c_uint32, C.c_uint32]
     lib.fsn_sw128_offset.restype = C.c_uint32
     lib.fsn_tc5_weight_stream_bytes.argtypes = [i32, i32]

@@ -194,6 +194,14 @@ class _B200Model(nn.Module):
     def last_lstm_impl(self):
         return {0: "none", 1: "mma", 2: "tcgen05"}[_lib.load_library().fsn_model_last_lstm_impl(self._handle)] if self._handle else "none"
 
+    def last_lstm_ms(self):
+        return float(_lib.load_library().fsn_model_last_lstm_ms(self._handle)) if self._handle else -1.0
+
+    def lstm_ms_history(self, n=32):
+        buf = (C.c_float * n)()
+        k = _lib.load_library().fsn_model_lstm_ms_history(self._handle, buf, n) if self._handle else 0
+        return [float(buf[i]) for i in range(k)]
+
     def last_launch_count(self):
         return int(_lib.load_library().fsn_model_last_launch_count(self._handle)) if self._handle else 0
 

@@ -106,6 +106,11 @@ int fsn_model_forward_host(fsn_model* m, const float* h_mag, const float* h_real
 int fsn_model_get_stage(fsn_model* m, const char* name, float* d_dst, int64_t numel, void* stream);
 /* Kernels launched by the last forward (bench.py reports it as gpu_launches). */
 int64_t fsn_model_last_launch_count(const fsn_model* m);
+/* Device time (ms, CUDA events on the forward's stream) of the sub-band LSTM kernel of the last forward;
+ * synchronises on the closing event.  < 0 if no forward has run. */
+float fsn_model_last_lstm_ms(fsn_model* m);
+/* Same for the last n forwards (n <= 32, oldest first); returns how many were written.  Synchronises. */
+int fsn_model_lstm_ms_history(fsn_model* m, float* h_ms, int32_t n);
 /* Which LSTM implementation the last forward used for the sub-band model (FSN_LSTM_MMA / _TCGEN05). */
 int fsn_model_last_lstm_impl(const fsn_model* m);
 

@@ -1,0 +1,201 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (via the Python mirror of the reference API),
+against the numpy oracle on the same seeded inputs and against the committed golden vectors generated from the
+unmodified reference.
+
+Tolerances (relative L2 over the whole tensor, truth = float64 reference/oracle):
+  * final cIRM mask ................ 1e-3  (the bar BASELINE.json's north_star states)
+  * full-band stages (TF32 convs) .. 2e-3 on fb_out, 1e-5 on fb_in (fp32 CUDA-core math)
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fsn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+MASK_TOL = 1e-3
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+def build_plus(cfg, params, **kw):
+    from fsnplus_b200.model import FullSubNet_Plus
+    m = FullSubNet_Plus(**cfg, **kw)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    return m.to(DEV).eval()
+
+
+def build_fsn(cfg, params, **kw):
+    from fsnplus_b200.model import Model
+    m = Model(**cfg, **kw)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    return m.to(DEV).eval()
+
+
+def small_cfg(H):
+    c = O.default_plus_config()
+    c.update(num_freqs=33, sb_num_neighbors=3, sb_model_hidden_size=H)
+    return c
+
+
+def small_inputs(B, F, T, seed):
+    rng = np.random.default_rng(seed)
+    real = rng.standard_normal((B, 1, F, T)) * 0.05 + 0.004
+    imag = rng.standard_normal((B, 1, F, T)) * 0.05 - 0.003
+    mag = np.sqrt(real ** 2 + imag ** 2)
+    return mag.astype(np.float32), real.astype(np.float32), imag.astype(np.float32)
+
+
+@pytest.mark.parametrize("impl,H", [("mma", 32), ("mma", 64), ("tcgen05", 64), ("tcgen05", 128)])
+def test_plus_small_vs_oracle(built_lib, impl, H):
+    cfg = small_cfg(H)
+    params = O.make_params_plus(cfg, seed=3)
+    mag, real, imag = small_inputs(3, 33, 20, 7)
+    st = {}
+    ref = O.fullsubnet_plus_forward(params, cfg, mag, real, imag, stages=st)
+    m = build_plus(cfg, params, lstm_impl=impl)
+    with torch.no_grad():
+        out = m(_t(mag), _t(real), _t(imag))
+    assert out.shape == (3, 2, 33, 20) and out.dtype == torch.float32
+    assert m.last_lstm_impl() == impl
+    fb_in = m.get_stage("fb_in", (3, 3, 33, 22), DEV).cpu().numpy()
+    fb_out = m.get_stage("fb_out", (3, 3, 33, 22), DEV).cpu().numpy()
+    assert O.rel_l2(fb_in, st["fb_in"]) < 1e-5
+    assert O.rel_l2(fb_out, st["fb_out"]) < 2e-3
+    assert O.rel_l2(out.cpu().numpy(), ref) < MASK_TOL
+
+
+def test_plus_small_golden_from_reference(built_lib, golden):
+    """Committed reference output (H=32 config of make_golden.py)."""
+    g = golden("plus_small")
+    cfg = small_cfg(32)
+    m = build_plus(cfg, O.make_params_plus(cfg, seed=3))
+    with torch.no_grad():
+        out = m(_t(g["mag"]), _t(g["real"]), _t(g["imag"]))
+    assert O.rel_l2(out.cpu().numpy(), g["out"]) < MASK_TOL
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "mma"])
+@pytest.mark.parametrize("stress", [False, True])
+def test_plus_default_config_golden(built_lib, golden, impl, stress):
+    """BASELINE config #1: default config/inference.toml, one 3 s clip, reference fp64 output as truth."""
+    gi = golden("plus_default")
+    g = golden("plus_default_stress") if stress else gi
+    cfg = O.default_plus_config()
+    m = build_plus(cfg, O.make_params_plus(cfg, seed=0, lstm_scale=3.0 if stress else 1.0), lstm_impl=impl)
+    with torch.no_grad():
+        out = m(_t(gi["mag"]), _t(gi["real"]), _t(gi["imag"]))
+    assert out.shape == (1, 2, 257, 188)
+    err = O.rel_l2(out.cpu().numpy(), g["out"])
+    print(f"\n[{impl} stress={stress}] cIRM rel-L2 vs reference fp64 = {err:.3e}")
+    if not stress:
+        fb_in = m.get_stage("fb_in", (3, 1, 257, 190), DEV).cpu().numpy()
+        fb_out = m.get_stage("fb_out", (3, 1, 257, 190), DEV).cpu().numpy()
+        e_in, e_out = O.rel_l2(fb_in, gi["fb_in"]), O.rel_l2(fb_out, gi["fb_out"])
+        print(f"   stages: fb_in {e_in:.2e}  fb_out {e_out:.2e}")
+        assert e_in < 1e-5 and e_out < 2e-3
+    assert err < MASK_TOL
+
+
+def test_plus_default_enhanced_waveform(built_lib, golden):
+    """End of the inferencer method (inferencer.py:152-158): decompress, complex multiply, iSTFT."""
+    g = golden("plus_default")
+    cfg = O.default_plus_config()
+    m = build_plus(cfg, O.make_params_plus(cfg, seed=0))
+    with torch.no_grad():
+        out = m(_t(g["mag"]), _t(g["real"]), _t(g["imag"])).cpu().numpy().astype(np.float64)
+    X = g["real"][:, 0].astype(np.float64) + 1j * g["imag"][:, 0].astype(np.float64)
+    enh = O.istft(O.enhance(X, out), length=48000)
+    assert O.rel_l2(enh, g["enhanced"]) < 2e-3
+
+
+def test_fsn_default_golden(built_lib, golden):
+    gi, g = golden("plus_default"), golden("fsn_default")
+    cfg = O.default_fsn_config()
+    m = build_fsn(cfg, O.make_params_fsn(cfg, seed=1))
+    with torch.no_grad():
+        out = m(_t(gi["mag"]))
+    fb_out = m.get_stage("fb_out", (1, 1, 257, 190), DEV).cpu().numpy()
+    e_fb, err = O.rel_l2(fb_out[0], g["fb_out"]), O.rel_l2(out.cpu().numpy(), g["out"])
+    print(f"\n[fullsubnet.Model] fb_out {e_fb:.2e}  cIRM {err:.3e}")
+    assert e_fb < 2e-3 and err < MASK_TOL
+
+
+def test_fsn_small_golden(built_lib, golden):
+    g = golden("fsn_small_offline_laplace_norm")
+    c = O.default_fsn_config()
+    c.update(num_freqs=33, sb_num_neighbors=3, sb_model_hidden_size=32, fb_model_hidden_size=48)
+    m = build_fsn(c, O.make_params_fsn(c, seed=4))
+    with torch.no_grad():
+        out = m(_t(g["mag"]))
+    assert O.rel_l2(out.cpu().numpy(), g["out"]) < MASK_TOL
+
+
+def test_three_layer_subband(built_lib):
+    """num_layers=3 (BASELINE config #5's additive knob) runs on the generic kernel."""
+    cfg = small_cfg(48)
+    params = O.make_params_plus(cfg, seed=9, num_layers=3)
+    mag, real, imag = small_inputs(2, 33, 18, 1)
+    ref = O.fullsubnet_plus_forward(params, cfg, mag, real, imag, num_layers=3)
+    m = build_plus(cfg, params, num_layers=3)
+    with torch.no_grad():
+        out = m(_t(mag), _t(real), _t(imag))
+    assert m.last_lstm_impl() == "mma"
+    assert O.rel_l2(out.cpu().numpy(), ref) < MASK_TOL
+
+
+def test_edge_shapes(built_lib):
+    """Ragged / minimal inputs the reference accepts: T just above the largest TSSE kernel, a row count that is
+    not a multiple of the 128-row tile, look_ahead = 0."""
+    for (B, T, la) in ((1, 9, 2), (5, 13, 0), (4, 31, 1)):
+        cfg = small_cfg(64)
+        cfg["look_ahead"] = la
+        params = O.make_params_plus(cfg, seed=2)
+        mag, real, imag = small_inputs(B, 33, T, 3)
+        ref = O.fullsubnet_plus_forward(params, cfg, mag, real, imag)
+        for impl in ("tcgen05", "mma"):
+            m = build_plus(cfg, params, lstm_impl=impl)
+            with torch.no_grad():
+                out = m(_t(mag), _t(real), _t(imag))
+            assert out.shape == (B, 2, 33, T)
+            assert O.rel_l2(out.cpu().numpy(), ref) < MASK_TOL, (B, T, la, impl)
+
+
+def test_batch_invariance_full_size(built_lib, golden):
+    """Size-independent property at BASELINE's full batch (64 clips): every sample is processed independently, so
+    sample i of a batched call must equal the same sample run alone
+    and a permuted batch must give the permuted output."""
+    g = golden("plus_default")
+    cfg = O.default_plus_config()
+    m = build_plus(cfg, O.make_params_plus(cfg, seed=0))
+    B = 64
+    rng = np.random.default_rng(0)
+    scale = rng.uniform(0.3, 3.0, size=(B, 1, 1, 1)).astype(np.float32)
+    shift = rng.integers(0, 188, size=B)
+    mk = lambda x: np.stack([np.roll(x[0], int(s), axis=-1) for s in shift]) * scale
+    mag, real, imag = mk(g["mag"]), mk(g["real"]), mk(g["imag"])
+    with torch.no_grad():
+        full = m(_t(mag), _t(real), _t(imag))
+        assert torch.isfinite(full).all()
+        for i in (0, 17, 63):
+            one = m(_t(mag[i:i + 1]), _t(real[i:i + 1]), _t(imag[i:i + 1]))
+            # identical arithmetic per sequence; only the fp64 atomics of the gLN statistics may reorder
+            assert O.rel_l2(one[0].cpu().numpy(), full[i].cpu().numpy()) < 1e-5, i
+        perm = torch.from_numpy(rng.permutation(B)).to(DEV)
+        fullp = m(_t(mag)[perm], _t(real)[perm], _t(imag)[perm])
+        assert O.rel_l2(fullp.cpu().numpy(), full[perm].cpu().numpy()) < 1e-5
+
+
+def test_host_buffer_entry_point(built_lib):
+    cfg = small_cfg(64)
+    params = O.make_params_plus(cfg, seed=3)
+    mag, real, imag = small_inputs(3, 33, 20, 7)
+    m = build_plus(cfg, params)
+    with torch.no_grad():
+        dev = m(_t(mag), _t(real), _t(imag)).cpu()
+    pin = lambda x: torch.from_numpy(x).pin_memory()
+    host = m.forward_host(pin(mag), pin(real), pin(imag), device=DEV)
+    assert torch.equal(host, dev)

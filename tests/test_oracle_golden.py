@@ -102,3 +102,19 @@ def test_flops_match_survey():
     assert abs(f["subband"] / 1e9 - 177.982) < 0.01
     g = O.flops_fsn(O.default_fsn_config(), 188)
     assert abs(g["total"] / 1e9 - 179.127) < 0.01
+
+
+def test_torch_port_matches_reference(golden):
+    """The torch-CPU port that bench.py times as the CPU baseline reproduces the reference (fp32 noise floor)."""
+    import torch
+    from oracle.torch_port import TorchPort
+    g = golden("plus_default")
+    cfg = O.default_plus_config()
+    port = TorchPort(O.make_params_plus(cfg, seed=0), cfg, "plus")
+    t = lambda k: torch.from_numpy(g[k])
+    out = port.forward(t("mag"), t("real"), t("imag")).numpy()
+    assert O.rel_l2(out, g["out"]) < 1e-4
+    gf = golden("fsn_default")
+    fcfg = O.default_fsn_config()
+    out = TorchPort(O.make_params_fsn(fcfg, seed=1), fcfg, "fsn").forward(t("mag")).numpy()
+    assert O.rel_l2(out, gf["out"]) < 1e-4
