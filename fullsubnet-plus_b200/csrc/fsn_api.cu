@@ -282,10 +282,10 @@ extern "C" int fsn_model_finalize(fsn_model* m) {
         for (int l = 0; l < 2; ++l) {
             const auto& bi = m->host["sb_model.sequence_model.bias_ih_l" + std::to_string(l)];
             const auto& bh = m->host["sb_model.sequence_model.bias_hh_l" + std::to_string(l)];
-            for (int j = 0; j < H / 16; ++j)
-                for (int n = 0; n < 64; ++n) {
-                    const int row = (n / 16) * H + 16 * j + (n % 16);
-                    bp[(size_t)l * 4 * H + j * 64 + n] = bi[row] + bh[row];
+            for (int j = 0; j < H / 32; ++j)
+                for (int n = 0; n < 128; ++n) {
+                    const int row = fsn_tc5_gate_row(H, j, n);
+                    bp[(size_t)l * 4 * H + j * 128 + n] = bi[row] + bh[row];
                 }
         }
         if (upload(m->sb_tc5_bias, bp.data(), bp.size() * 4)) return fail(FSN_ECUDA, "upload failed");

@@ -10,13 +10,14 @@
 //   * one CTA = 128 sequences (the 128 TMEM lanes) for ALL time steps and BOTH layers;
 //   * the recurrent operands h0/h1 live in TENSOR MEMORY as packed fp16 (192 columns each for H=384)
 //     and are fed to tcgen05.mma as the A operand (A-from-TMEM form) -- they never touch shared or
-//     global memory; the two 64-column fp32 accumulators occupy the remaining 128 TMEM columns;
-//   * the weights (3.6 MB fp16 for H=384) are streamed from L2 every step as pre-swizzled 8 KB
+//     global memory; one 128-column fp32 accumulator occupies the remaining TMEM columns;
+//   * the weights (3.6 MB fp16 for H=384) are streamed from L2 every step as pre-swizzled 16 KB
 //     K-major tiles through a ring of shared-memory stages filled by 1-D bulk async copies (TMA engine,
 //     mbarrier complete_tx), in exactly the order the MMA issuer consumes them;
-//   * each layer-step's gate matrix [128, 4H] is produced in chunks of 64 columns (16 hidden units x
-//     i,f,g,o); two epilogue warpgroups alternate on the two accumulators so the cell update of chunk j
-//     overlaps the MMAs of chunk j+1;
+//   * each layer-step's gate matrix [128, 4H] is produced in chunks of 128 columns (32 hidden units x
+//     i,f,g,o; N=128 because a tcgen05.mma of M=128 costs ~93 cycles for every N <= 128, measured by
+//     fsn_probe_tcgen05); BOTH epilogue warpgroups drain the accumulator into registers at once (64 columns
+//     each) and release it, so the cell update of chunk j overlaps the MMAs of chunk j+1;
 //   * fp32 cell state goes through an L2-resident scratch private to the CTA (coalesced float4);
 //   * new hidden values are parked (thread-private shared memory) until the layer-step's last MMA has
 //     retired, then written back to TMEM with tcgen05.st;
@@ -31,7 +32,7 @@
 
 namespace fsn {
 
-constexpr int TC5_STAGE = 8192;     // 64 gate columns x 64 k x fp16, SWIZZLE_128B
+constexpr int TC5_STAGE = 16384;    // 128 gate columns x 64 k x fp16, SWIZZLE_128B
 constexpr int TC5_XIMG = 16384;     // 128 rows x 64 k x fp16, SWIZZLE_128B
 constexpr int TC5_THREADS = 384;    // warp 0 producer, 1 MMA issuer, 2 TMEM alloc, 3 idle, 4-11 epilogue
 constexpr int TC5_MAX_SMEM = 227 * 1024;
@@ -39,11 +40,10 @@ constexpr int TC5_MAX_SMEM = 227 * 1024;
 struct Tc5Plan { int nstage; size_t fixed, total; };
 static inline Tc5Plan tc5_plan(int H) {
     Tc5Plan p;
-    p.fixed = 2 * TC5_XIMG + (size_t)128 * H * 2 /*park*/ + (size_t)2 * 4 * H * 4 /*bias*/ + (size_t)2 * H * 4 /*fc*/ +
-              2 * 128 * 2 * 4 /*fcpart*/ + 64 * 8 /*barriers*/ + 64;
+    p.fixed = TC5_XIMG + (size_t)128 * H * 2 /*park*/ + 128 * 2 * 4 /*fcpart*/ + 32 * 8 /*barriers*/;
     long avail = TC5_MAX_SMEM - 1024 /*alignment slack*/ - (long)p.fixed;
     p.nstage = (int)(avail / TC5_STAGE);
-    if (p.nstage > 24) p.nstage = 24;
+    if (p.nstage > 12) p.nstage = 12;
     p.total = p.fixed + (size_t)p.nstage * TC5_STAGE + 1024;
     return p;
 }
@@ -52,50 +52,64 @@ bool lstm_tc5_supported(int L, int H, int I, int O) { return L == 2 && H % 64 ==
 
 size_t lstm_tc5_cstate_bytes(int ntiles, int H) { return (size_t)ntiles * 2 * H * 128 * sizeof(float); }
 
+// One LSTM cell from the four gate pre-activations.  Accurate path: 5 ex2 + 3 rcp (the i*tanh(g) and
+// o*tanh(c) products share one reciprocal each); fast path: 5 tanh.approx.
+template <bool FAST>
+__device__ __forceinline__ void lstm_cell(float gi, float gf, float gg, float go, float cprev, float& c, float& h) {
+    if (FAST) {
+        c = sigmoid_fast(gf) * cprev + sigmoid_fast(gi) * tanh_approx(gg);
+        h = sigmoid_fast(go) * tanh_approx(c);
+    } else {
+        const float L2E = 1.4426950408889634f;
+        const float ei = ex2f(-L2E * fmaxf(gi, -30.f));
+        const float eg = ex2f(-2.f * L2E * fminf(fmaxf(gg, -15.f), 15.f));
+        const float ef = ex2f(-L2E * gf);
+        const float ig = (1.f - eg) * rcpf((1.f + ei) * (1.f + eg));          // sigmoid(gi) * tanh(gg)
+        c = fmaf(rcpf(1.f + ef), cprev, ig);
+        const float eo = ex2f(-L2E * fmaxf(go, -30.f));
+        const float ec = ex2f(-2.f * L2E * fminf(fmaxf(c, -15.f), 15.f));
+        h = (1.f - ec) * rcpf((1.f + eo) * (1.f + ec));                       // sigmoid(go) * tanh(c)
+    }
+}
+
 template <bool FAST>
 __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch a, int nstage) {
     extern __shared__ uint8_t smem_raw[];
-    const int H = a.H, NCH = H / 16, KBH = H / 64, hcols = H / 2, Tp = a.Tp;
+    const int H = a.H, NCH = H / 32, KBH = H / 64, hcols = H / 2, Tp = a.Tp;
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stages = smem;
     uint8_t* ximg = stages + (size_t)nstage * TC5_STAGE;
-    uint8_t* park = ximg + 2 * TC5_XIMG;
-    float* biasp = reinterpret_cast<float*>(park + (size_t)128 * H * 2);
-    float* fcw = biasp + 2 * 4 * H;
-    float* fcpart = fcw + 2 * H;                                   // [2][128][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(fcpart + 2 * 128 * 2);
+    uint8_t* park = ximg + TC5_XIMG;
+    float* fcpart = reinterpret_cast<float*>(park + (size_t)128 * H * 2);   // [128][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fcpart + 128 * 2);
     uint64_t* full = bars;
     uint64_t* empty = full + nstage;
     uint64_t* xfull = empty + nstage;
-    uint64_t* xempty = xfull + 2;
-    uint64_t* accfull = xempty + 2;
-    uint64_t* accempty = accfull + 2;
-    uint64_t* hready = accempty + 2;
+    uint64_t* xempty = xfull + 1;
+    uint64_t* accfull = xempty + 1;
+    uint64_t* accempty = accfull + 1;
+    uint64_t* hready = accempty + 1;
     uint64_t* layerdone = hready + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layerdone + 1);
 
     if (tid == 0) {
         for (int i = 0; i < nstage; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1);
-            mbar_init(&accfull[i], 1); mbar_init(&accempty[i], 128);
-        }
+        mbar_init(xfull, 1); mbar_init(xempty, 1);
+        mbar_init(accfull, 1); mbar_init(accempty, 256);
         mbar_init(hready, 256);
         mbar_init(layerdone, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
-    for (int i = tid; i < 2 * 4 * H; i += TC5_THREADS) biasp[i] = a.bias[i];
-    for (int i = tid; i < 2 * H; i += TC5_THREADS) fcw[i] = a.fc_w[i];
     tc5_fence_before();
     __syncthreads();
     tc5_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t acc_col = 2 * hcols;
-    const int SPS = NCH * (1 + KBH) + NCH * 2 * KBH;               // weight stages per time step
+    const int SPS0 = NCH * (1 + KBH), SPS1 = NCH * 2 * KBH;       // weight stages per layer-step
 
     if (warp == 0) {
         // ======================= bulk-copy producer =======================================
@@ -103,16 +117,16 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wstream);
             const uint8_t* xsrc = reinterpret_cast<const uint8_t*>(a.img) + (size_t)tile * Tp * TC5_XIMG;
             int slot = 0; uint32_t ph = 0;
-            mbar_arrive_expect_tx(&xfull[0], TC5_XIMG);
-            bulk_g2s(ximg, xsrc, TC5_XIMG, &xfull[0]);
+            mbar_arrive_expect_tx(xfull, TC5_XIMG);
+            bulk_g2s(ximg, xsrc, TC5_XIMG, xfull);
+            const int xpoint = SPS0 + SPS1 / 2;                   // x_{t+1} is fetched half way through layer 1 of step t
             for (int t = 0; t < Tp; ++t) {
-                if (t + 1 < Tp) {
-                    const int xb = (t + 1) & 1, n = (t + 1) >> 1;
-                    mbar_wait(&xempty[xb], (n & 1) ^ 1);
-                    mbar_arrive_expect_tx(&xfull[xb], TC5_XIMG);
-                    bulk_g2s(ximg + xb * TC5_XIMG, xsrc + (size_t)(t + 1) * TC5_XIMG, TC5_XIMG, &xfull[xb]);
-                }
-                for (int s = 0; s < SPS; ++s) {
+                for (int s = 0; s < SPS0 + SPS1; ++s) {
+                    if (s == xpoint && t + 1 < Tp) {
+                        mbar_wait(xempty, t & 1);                 // layer 0 of step t has consumed the single x buffer
+                        mbar_arrive_expect_tx(xfull, TC5_XIMG);
+                        bulk_g2s(ximg, xsrc + (size_t)(t + 1) * TC5_XIMG, TC5_XIMG, xfull);
+                    }
                     mbar_wait(&empty[slot], ph ^ 1);
                     mbar_arrive_expect_tx(&full[slot], TC5_STAGE);
                     bulk_g2s(stages + (size_t)slot * TC5_STAGE, wsrc + (size_t)s * TC5_STAGE, TC5_STAGE, &full[slot]);
@@ -123,24 +137,23 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
     } else if (warp == 1) {
         // ======================= MMA issuer (one thread) ==================================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(128, 64);
-            int slot = 0; uint32_t ph = 0, accuse[2] = {0, 0}, ls = 0;
+            const uint32_t idesc = umma_idesc_f16(128, 128);
+            const uint32_t d = tmem + acc_col;
+            int slot = 0; uint32_t ph = 0, accuse = 0, ls = 0;
             for (int t = 0; t < Tp; ++t) {
                 for (int layer = 0; layer < 2; ++layer, ++ls) {
                     mbar_wait(hready, ls & 1);                     // h operands of this layer-step are in TMEM
                     uint64_t xdesc = 0;
                     if (layer == 0) {
-                        mbar_wait(&xfull[t & 1], (t >> 1) & 1);
-                        xdesc = umma_desc_sw128(smem_u32(ximg + (t & 1) * TC5_XIMG));
+                        mbar_wait(xfull, t & 1);
+                        xdesc = umma_desc_sw128(smem_u32(ximg));
                     }
                     tc5_fence_after();
                     const int nkb = (layer == 0) ? 1 + KBH : 2 * KBH;
                     for (int j = 0; j < NCH; ++j) {
-                        const int buf = j & 1;
-                        mbar_wait(&accempty[buf], (accuse[buf] & 1) ^ 1);
-                        ++accuse[buf];
+                        mbar_wait(accempty, (accuse & 1) ^ 1);     // both warpgroups have drained the accumulator
+                        ++accuse;
                         tc5_fence_after();
-                        const uint32_t d = tmem + acc_col + buf * 64;
                         for (int kb = 0; kb < nkb; ++kb) {
                             mbar_wait(&full[slot], ph);
                             tc5_fence_after();
@@ -157,44 +170,46 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
                             umma_commit(&empty[slot]);             // stage reusable once these MMAs retire
                             if (++slot == nstage) { slot = 0; ph ^= 1; }
                         }
-                        umma_commit(&accfull[buf]);
+                        umma_commit(accfull);
                     }
-                    if (layer == 0) umma_commit(&xempty[t & 1]);
+                    if (layer == 0) umma_commit(xempty);
                     umma_commit(layerdone);
                 }
             }
         }
     } else if (warp >= 4) {
         // ======================= epilogue warpgroups ======================================
+        // Both warpgroups work on every chunk: warpgroup wg owns accumulator columns [64 wg, 64 wg + 64)
+        // = gates i,f,g,o of hidden units 32 j + 16 wg + [0, 16).
         const int wg = (warp - 4) >> 2;
         const int q = warp & 3;                                    // TMEM lane quarter of this warp
         const int r = q * 32 + lane;                               // sequence (row) inside the tile
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
         {
             const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            // each warpgroup zeroes half of the h columns of its lanes
-            for (int c = wg * (NCH / 2); c < (wg + 1) * (NCH / 2); ++c) { tmem_st8(tl + c * 8, z); tmem_st8(tl + hcols + c * 8, z); }
+            for (int c = wg * NCH; c < (wg + 1) * NCH; ++c) { tmem_st8(tl + c * 8, z); tmem_st8(tl + hcols + c * 8, z); }
             tmem_wait_st();
             tc5_fence_before();
             mbar_arrive(hready);
         }
         uint32_t accn = 0, ls = 0;
         float* cbase = a.cstate + (size_t)tile * 2 * H * 128;
-        uint8_t* mypark = park + ((size_t)wg * (NCH / 2) * 128 + r) * 32;
+        uint8_t* mypark = park + ((size_t)wg * NCH * 128 + r) * 32;
         const int grow = tile * 128 + r;
         const int ob = grow / a.F, of = grow % a.F;
         const int Tout = Tp - a.la;
+        const float fcb0 = __ldg(a.fc_b), fcb1 = __ldg(a.fc_b + 1);
 
         for (int t = 0; t < Tp; ++t) {
             for (int layer = 0; layer < 2; ++layer, ++ls) {
                 float fc0 = 0.f, fc1 = 0.f;
-                for (int jj = 0; jj < NCH / 2; ++jj) {
-                    const int j = 2 * jj + wg;
-                    float4* cp = reinterpret_cast<float4*>(cbase + ((size_t)(layer * NCH + j) * 4) * 128 * 4) + r;
+                for (int j = 0; j < NCH; ++j) {
+                    float4* cp = reinterpret_cast<float4*>(cbase + ((size_t)((layer * NCH + j) * 2 + wg) * 4) * 128 * 4) + r;
                     float4 c4[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) c4[i] = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[i * 128];
-                    mbar_wait(&accfull[wg], accn & 1);
+                    const float4* bj = reinterpret_cast<const float4*>(a.bias + (size_t)(layer * NCH + j) * 128 + wg * 64);
+                    mbar_wait(accfull, accn & 1);
                     ++accn;
                     tc5_fence_after();
                     uint32_t v[4][16];
@@ -202,58 +217,62 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
                     for (int g = 0; g < 4; ++g) tmem_ld16(tl + acc_col + wg * 64 + g * 16, v[g]);
                     tmem_wait_ld();
                     tc5_fence_before();
-                    mbar_arrive(&accempty[wg]);
+                    mbar_arrive(accempty);
 
-                    const float* bj = biasp + (size_t)(layer * NCH + j) * 64;
-                    const float* w0 = fcw + j * 16;
-                    const float* w1 = fcw + H + j * 16;
+                    const float4* w0 = reinterpret_cast<const float4*>(a.fc_w + j * 32 + wg * 16);
+                    const float4* w1 = reinterpret_cast<const float4*>(a.fc_w + H + j * 32 + wg * 16);
                     uint32_t hp[8];
                     float cn[16];
-                    const float cpv[16] = {c4[0].x, c4[0].y, c4[0].z, c4[0].w, c4[1].x, c4[1].y, c4[1].z, c4[1].w,
-                                           c4[2].x, c4[2].y, c4[2].z, c4[2].w, c4[3].x, c4[3].y, c4[3].z, c4[3].w};
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        const float gi = __uint_as_float(v[0][u]) + bj[u];
-                        const float gf = __uint_as_float(v[1][u]) + bj[16 + u];
-                        const float gg = __uint_as_float(v[2][u]) + bj[32 + u];
-                        const float go = __uint_as_float(v[3][u]) + bj[48 + u];
-                        const float cprev = cpv[u];
-                        const float c = sigm<FAST>(gf) * cprev + sigm<FAST>(gi) * tanh_<FAST>(gg);
-                        const float h = sigm<FAST>(go) * tanh_<FAST>(c);
-                        cn[u] = c;
-                        if (layer == 1) { fc0 = fmaf(h, w0[u], fc0); fc1 = fmaf(h, w1[u], fc1); }
-                        if (u & 1) hp[u >> 1] = pack_half2(__uint_as_float(hp[u >> 1]), h); else hp[u >> 1] = __float_as_uint(h);
+                    for (int u4 = 0; u4 < 4; ++u4) {
+                        const float4 bi = __ldg(bj + u4), bf = __ldg(bj + 4 + u4), bg = __ldg(bj + 8 + u4), bo = __ldg(bj + 12 + u4);
+                        const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, bfa[4] = {bf.x, bf.y, bf.z, bf.w};
+                        const float bga[4] = {bg.x, bg.y, bg.z, bg.w}, boa[4] = {bo.x, bo.y, bo.z, bo.w};
+                        const float cpv[4] = {c4[u4].x, c4[u4].y, c4[u4].z, c4[u4].w};
+                        float hv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int u = u4 * 4 + e;
+                            lstm_cell<FAST>(__uint_as_float(v[0][u]) + bia[e], __uint_as_float(v[1][u]) + bfa[e],
+                                            __uint_as_float(v[2][u]) + bga[e], __uint_as_float(v[3][u]) + boa[e], cpv[e], cn[u], hv[e]);
+                        }
+                        if (layer == 1) {
+                            const float4 wa = __ldg(w0 + u4), wb = __ldg(w1 + u4);
+                            fc0 = fmaf(hv[0], wa.x, fmaf(hv[1], wa.y, fmaf(hv[2], wa.z, fmaf(hv[3], wa.w, fc0))));
+                            fc1 = fmaf(hv[0], wb.x, fmaf(hv[1], wb.y, fmaf(hv[2], wb.z, fmaf(hv[3], wb.w, fc1))));
+                        }
+                        hp[2 * u4] = pack_half2(hv[0], hv[1]);
+                        hp[2 * u4 + 1] = pack_half2(hv[2], hv[3]);
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) cp[i * 128] = make_float4(cn[4 * i], cn[4 * i + 1], cn[4 * i + 2], cn[4 * i + 3]);
-                    uint4* pk = reinterpret_cast<uint4*>(mypark + (size_t)jj * 128 * 32);
+                    uint4* pk = reinterpret_cast<uint4*>(mypark + (size_t)j * 128 * 32);
                     pk[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                     pk[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
                 }
                 // every MMA of this layer-step has retired -> h_{t-1} may be overwritten in TMEM
                 mbar_wait(layerdone, ls & 1);
                 tc5_fence_after();
-                for (int jj = 0; jj < NCH / 2; ++jj) {
-                    const int j = 2 * jj + wg;
-                    const uint4* pk = reinterpret_cast<const uint4*>(mypark + (size_t)jj * 128 * 32);
+                for (int j = 0; j < NCH; ++j) {
+                    const uint4* pk = reinterpret_cast<const uint4*>(mypark + (size_t)j * 128 * 32);
                     const uint4 p0 = pk[0], p1 = pk[1];
                     const uint32_t hv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-                    tmem_st8(tl + layer * hcols + j * 8, hv);
+                    tmem_st8(tl + layer * hcols + j * 16 + wg * 8, hv);
                 }
                 tmem_wait_st();
                 tc5_fence_before();
                 mbar_arrive(hready);
 
                 if (layer == 1) {
-                    float* part = fcpart + (size_t)(t & 1) * 256;
-                    if (wg == 1) { part[2 * r] = fc0; part[2 * r + 1] = fc1; }
+                    if (wg == 1) { fcpart[2 * r] = fc0; fcpart[2 * r + 1] = fc1; }
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                     if (wg == 0 && t >= a.la && grow < a.rows) {
-                        const float o0 = fc0 + part[2 * r] + a.fc_b[0];
-                        const float o1 = fc1 + part[2 * r + 1] + a.fc_b[1];
+                        const float o0 = fc0 + fcpart[2 * r] + fcb0;
+                        const float o1 = fc1 + fcpart[2 * r + 1] + fcb1;
                         a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)] = o0;
                         a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)] = o1;
                     }
+                    asm volatile("bar.sync 2, 256;" ::: "memory");    // fcpart is single-buffered
                 }
             }
         }
@@ -267,7 +286,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
 int launch_lstm_tc5(const LstmTc5Launch& a, cudaStream_t s) {
     if (!lstm_tc5_supported(2, a.H, a.I, 2)) return (int)cudaErrorInvalidValue;
     const Tc5Plan p = tc5_plan(a.H);
-    if (p.nstage < 4) return (int)cudaErrorInvalidValue;
+    if (p.nstage < 3) return (int)cudaErrorInvalidValue;
     cudaError_t e;
     if (a.fast) {
         e = cudaFuncSetAttribute(lstm_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);
@@ -283,9 +302,9 @@ int launch_lstm_tc5(const LstmTc5Launch& a, cudaStream_t s) {
 
 // ---------------------------------------------------------------------------------------------
 // Host-side packing of the weight stream (exposed through the C ABI for CPU layout tests).
-// Stream order per time step: layer 0, chunk j = 0..H/16-1: [x block][H/64 hidden blocks];
+// Stream order per time step: layer 0, chunk j = 0..H/32-1: [x block][H/64 hidden blocks];
 //                             layer 1, chunk j:              [H/64 blocks of W_ih1][H/64 blocks of W_hh1].
-// Stage = 64 gate columns (n = q*16 + u  <->  weight row q*H + 16 j + u, q in i,f,g,o) x 64 k, K-major,
+// Stage = 128 gate columns (fsn_tc5_gate_row) x 64 k, K-major,
 // SWIZZLE_128B.
 // ---------------------------------------------------------------------------------------------
 static inline uint16_t f2h_bits(float f) {
@@ -299,18 +318,21 @@ static inline uint16_t f2h_bits(float f) {
 
 extern "C" int64_t fsn_tc5_weight_stream_bytes(int32_t I, int32_t H) {
     if (H % 64 || I > 64) return -1;
-    const int NCH = H / 16, KBH = H / 64;
+    const int NCH = H / 32, KBH = H / 64;
     return (int64_t)(NCH * (1 + KBH) + NCH * 2 * KBH) * fsn::TC5_STAGE;
 }
+
+// Gate column n (0..127) of chunk j <-> weight row: n = wg*64 + q*16 + u, q in (i,f,g,o), hidden unit 32 j + 16 wg + u.
+extern "C" int32_t fsn_tc5_gate_row(int32_t H, int32_t j, int32_t n) { return ((n % 64) / 16) * H + 32 * j + 16 * (n / 64) + (n % 16); }
 
 extern "C" int fsn_tc5_pack_weights(int32_t I, int32_t H, const float* w_ih0, const float* w_hh0, const float* w_ih1,
                                     const float* w_hh1, uint16_t* dst) {
     if (H % 64 || I > 64) return FSN_EINVAL;
-    const int NCH = H / 16, KBH = H / 64;
+    const int NCH = H / 32, KBH = H / 64;
     size_t s = 0;
     auto stage = [&](auto&& getw) {
         uint8_t* img = reinterpret_cast<uint8_t*>(dst) + s * fsn::TC5_STAGE;
-        for (int n = 0; n < 64; ++n)
+        for (int n = 0; n < 128; ++n)
             for (int k = 0; k < 64; ++k) {
                 uint16_t b = fsn::f2h_bits(getw(n, k));
                 std::memcpy(img + fsn::sw128_offset(n, k), &b, 2);
@@ -318,12 +340,12 @@ extern "C" int fsn_tc5_pack_weights(int32_t I, int32_t H, const float* w_ih0, co
         ++s;
     };
     for (int j = 0; j < NCH; ++j) {
-        auto row = [&](int n) { return (n / 16) * H + 16 * j + (n % 16); };
+        auto row = [&](int n) { return fsn_tc5_gate_row(H, j, n); };
         stage([&](int n, int k) { return k < I ? w_ih0[(size_t)row(n) * I + k] : 0.f; });
         for (int kb = 0; kb < KBH; ++kb) stage([&](int n, int k) { return w_hh0[(size_t)row(n) * H + kb * 64 + k]; });
     }
     for (int j = 0; j < NCH; ++j) {
-        auto row = [&](int n) { return (n / 16) * H + 16 * j + (n % 16); };
+        auto row = [&](int n) { return fsn_tc5_gate_row(H, j, n); };
         for (int kb = 0; kb < KBH; ++kb) stage([&](int n, int k) { return w_ih1[(size_t)row(n) * H + kb * 64 + k]; });
         for (int kb = 0; kb < KBH; ++kb) stage([&](int n, int k) { return w_hh1[(size_t)row(n) * H + kb * 64 + k]; });
     }

@@ -23,6 +23,7 @@ struct ProbeArgs {
     int N;                   // 64 or 256
     int ts;                  // timing: 1 = TS, 0 = SS
     int reps;
+    int nacc;                // timing: number of accumulators cycled through (1 = dependent chain)
 };
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
@@ -77,10 +78,12 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
             for (int kk = 0; kk < 4; ++kk) umma_ss(tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, kk != 0);
             for (int kk = 0; kk < 4; ++kk) umma_ts(tmem, tmem + a_col + kk * 8, bdesc + 2 * kk, idesc, 1);
         } else {
+            // accumulators at columns 0 and (nacc == 2 ? N : 0); the TMEM A operand sits at a_col (>= 2N for N <= 128)
             for (int rpt = 0; rpt < p.reps; ++rpt)
                 for (int kk = 0; kk < 4; ++kk) {
-                    if (p.ts) umma_ts(tmem, tmem + a_col + kk * 8, bdesc + 2 * kk, idesc, (rpt | kk) != 0);
-                    else umma_ss(tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (rpt | kk) != 0);
+                    const uint32_t d = tmem + ((p.nacc == 2 && (kk & 1)) ? (uint32_t)N : 0u);
+                    if (p.ts) umma_ts(d, tmem + a_col + kk * 8, bdesc + 2 * kk, idesc, rpt != 0 || kk > 1);
+                    else umma_ss(d, adesc + 2 * kk, bdesc + 2 * kk, idesc, rpt != 0 || kk > 1);
                 }
         }
         umma_commit(&bars[1]);
@@ -109,7 +112,7 @@ static float h_val(uint16_t b) { __half h; std::memcpy(&h, &b, 2); return __half
 #define PROBE_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = -(int)e_ - 1000; goto done; } } while (0)
 
 int run_probe_tcgen05(float* report, int n) {
-    if (n < 8) return -1;
+    if (n < 16) return -1;
     int rc = 0;
     std::vector<uint16_t> A(128 * 64), B(256 * 64);
     std::vector<uint8_t> aimg(16384), bimg(32768);
@@ -138,7 +141,7 @@ int run_probe_tcgen05(float* report, int n) {
     PROBE_CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.a_img = da; p.b_img = db; p.a_plain = dp; p.d = dd; p.cycles = dc;
     for (int mode = 0; mode < 3; ++mode) {
-        p.mode = mode; p.N = 64; p.reps = 1; p.ts = 0;
+        p.mode = mode; p.N = 64; p.reps = 1; p.ts = 0; p.nacc = 1;
         PROBE_CK(cudaMemset(dd, 0, 128 * 256 * 4));
         probe_kernel<<<1, 128, smem>>>(p);
         PROBE_CK(cudaGetLastError());
@@ -156,17 +159,21 @@ int run_probe_tcgen05(float* report, int n) {
     }
     {
         int idx = 3;
-        for (int N : {64, 256})
-            for (int ts : {1, 0}) {
-                p.mode = 3; p.N = N; p.ts = ts; p.reps = 256;
-                probe_kernel<<<1, 128, smem>>>(p);
-                PROBE_CK(cudaGetLastError());
-                PROBE_CK(cudaDeviceSynchronize());
-                long long cyc = 0;
-                PROBE_CK(cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost));
-                report[idx++] = (float)cyc / (256.0f * 4.0f);      // cycles per MMA instruction (M=128, K=16)
-            }
-        rc = idx;    // report: [err_ss, err_ts, err_mix, cyc_ts64, cyc_ss64, cyc_ts256, cyc_ss256]
+        // cycles per tcgen05.mma (M=128, K=16) for N in {64,128,192,256} x {TS,SS} x {1,2 accumulators}
+        for (int N : {64, 128, 192, 256})
+            for (int ts : {1, 0})
+                for (int nacc : {1, 2}) {
+                    if (nacc == 2 && N > 128) continue;           // two accumulators + A region must fit 512 columns
+                    if (idx >= n) break;
+                    p.mode = 3; p.N = N; p.ts = ts; p.reps = 256; p.nacc = nacc;
+                    probe_kernel<<<1, 128, smem>>>(p);
+                    PROBE_CK(cudaGetLastError());
+                    PROBE_CK(cudaDeviceSynchronize());
+                    long long cyc = 0;
+                    PROBE_CK(cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost));
+                    report[idx++] = (float)cyc / (256.0f * 4.0f);
+                }
+        rc = idx;
     }
 done:
     cudaFree(da); cudaFree(db); cudaFree(dp); cudaFree(dd); cudaFree(dc);

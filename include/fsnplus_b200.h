@@ -119,6 +119,8 @@ int fsn_model_last_lstm_impl(const fsn_model* m);
 uint32_t fsn_sw128_offset(uint32_t row, uint32_t k);
 /* Size in bytes and content of the tcgen05 weight stream for a 2-layer LSTM. */
 int64_t fsn_tc5_weight_stream_bytes(int32_t input_size, int32_t hidden);
+/* weight row (in [W_i; W_f; W_g; W_o] order) that gate column n (0..127) of 32-unit chunk j maps to */
+int32_t fsn_tc5_gate_row(int32_t hidden, int32_t chunk, int32_t n);
 int fsn_tc5_pack_weights(int32_t input_size, int32_t hidden, const float* w_ih0, const float* w_hh0, const float* w_ih1,
                          const float* w_hh1, uint16_t* h_dst /* fp16 bits */);
 

@@ -95,35 +95,35 @@ def test_sw128_offsets(built_lib):
 
 
 def test_tc5_weight_stream_layout(built_lib):
-    """The stream must hold, stage by stage in consumption order, 64 gate columns x 64 k tiles whose un-swizzled
-    content is the (i,f,g,o)-interleaved slice of [W_ih | W_hh] the kernel's MMA schedule expects."""
+    """The stream must hold, stage by stage in consumption order, 128 gate columns x 64 k tiles whose un-swizzled
+    content is the slice of [W_ih | W_hh] the kernel's MMA schedule expects (gate column n of 32-unit chunk j =
+    gates i,f,g,o of units 32 j + 16 (n // 64) + n % 16)."""
     I, H = 34, 128
     rng = np.random.default_rng(0)
     w = [rng.standard_normal(s).astype(np.float32) for s in ((4 * H, I), (4 * H, H), (4 * H, H), (4 * H, H))]
     nbytes = built_lib.fsn_tc5_weight_stream_bytes(I, H)
-    NCH, KBH = H // 16, H // 64
-    assert nbytes == (NCH * (1 + KBH) + NCH * 2 * KBH) * 8192
+    NCH, KBH = H // 32, H // 64
+    assert nbytes == (NCH * (1 + KBH) + NCH * 2 * KBH) * 16384
     buf = np.zeros(nbytes // 2, np.uint16)
     vp = lambda a: C.c_void_p(a.ctypes.data)
     assert built_lib.fsn_tc5_pack_weights(I, H, vp(w[0]), vp(w[1]), vp(w[2]), vp(w[3]), vp(buf)) == 0
-    st = buf.view(np.float16).reshape(-1, 4096)
-    # un-swizzle index map
-    off = np.array([[built_lib.fsn_sw128_offset(n, k) // 2 for k in range(64)] for n in range(64)])
+    st = buf.view(np.float16).reshape(-1, 8192)
+    off = np.array([[built_lib.fsn_sw128_offset(n, k) // 2 for k in range(64)] for n in range(128)])
     s = 0
     for layer in range(2):
         for j in range(NCH):
-            rows = np.array([(n // 16) * H + 16 * j + (n % 16) for n in range(64)])
+            rows = np.array([built_lib.fsn_tc5_gate_row(H, j, n) for n in range(128)])
+            assert list(rows[:3]) == [32 * j, 32 * j + 1, 32 * j + 2] and rows[16] == H + 32 * j and rows[64] == 32 * j + 16
             blocks = []
             if layer == 0:
-                x = np.zeros((64, 64), np.float32); x[:, :I] = w[0][rows]
+                x = np.zeros((128, 64), np.float32); x[:, :I] = w[0][rows]
                 blocks.append(x)
                 blocks += [w[1][rows][:, kb * 64:(kb + 1) * 64] for kb in range(KBH)]
             else:
                 blocks += [w[2][rows][:, kb * 64:(kb + 1) * 64] for kb in range(KBH)]
                 blocks += [w[3][rows][:, kb * 64:(kb + 1) * 64] for kb in range(KBH)]
             for blk in blocks:
-                got = st[s][off]
-                assert np.array_equal(got, blk.astype(np.float16)), (layer, j, s)
+                assert np.array_equal(st[s][off], blk.astype(np.float16)), (layer, j, s)
                 s += 1
     assert s == st.shape[0]
     assert built_lib.fsn_tc5_weight_stream_bytes(34, 100) == -1           # unsupported geometry
