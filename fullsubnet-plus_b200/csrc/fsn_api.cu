@@ -285,7 +285,9 @@ extern "C" int fsn_model_finalize(fsn_model* m) {
             for (int j = 0; j < H / 32; ++j)
                 for (int n = 0; n < 128; ++n) {
                     const int row = fsn_tc5_gate_row(H, j, n);
-                    bp[(size_t)l * 4 * H + j * 128 + n] = bi[row] + bh[row];
+                    // stored pre-scaled: the kernel evaluates exp2(-log2e * (acc + b)) as one FMA (tanh gate: -2 log2e)
+                    const float sc = ((n % 32) / 8 == 2) ? -2.8853900817779268f : -1.4426950408889634f;
+                    bp[(size_t)l * 4 * H + j * 128 + n] = sc * (bi[row] + bh[row]);
                 }
         }
         if (upload(m->sb_tc5_bias, bp.data(), bp.size() * 4)) return fail(FSN_ECUDA, "upload failed");

@@ -16,8 +16,8 @@
 //     mbarrier complete_tx), in exactly the order the MMA issuer consumes them;
 //   * each layer-step's gate matrix [128, 4H] is produced in chunks of 128 columns (32 hidden units x
 //     i,f,g,o; N=128 because a tcgen05.mma of M=128 costs ~93 cycles for every N <= 128, measured by
-//     fsn_probe_tcgen05); BOTH epilogue warpgroups drain the accumulator into registers at once (64 columns
-//     each) and release it, so the cell update of chunk j overlaps the MMAs of chunk j+1;
+//     fsn_probe_tcgen05); all 16 epilogue warps drain the accumulator into registers at once (32 lanes x 32
+//     columns each) and release it, so the cell update of chunk j overlaps the MMAs of chunk j+1;
 //   * fp32 cell state goes through an L2-resident scratch private to the CTA (coalesced float4);
 //   * new hidden values are parked (thread-private shared memory) until the layer-step's last MMA has
 //     retired, then written back to TMEM with tcgen05.st;
@@ -34,13 +34,14 @@ namespace fsn {
 
 constexpr int TC5_STAGE = 16384;    // 128 gate columns x 64 k x fp16, SWIZZLE_128B
 constexpr int TC5_XIMG = 16384;     // 128 rows x 64 k x fp16, SWIZZLE_128B
-constexpr int TC5_THREADS = 384;    // warp 0 producer, 1 MMA issuer, 2 TMEM alloc, 3 idle, 4-11 epilogue
+constexpr int TC5_EPI_WARPS = 16;   // warps 0-15: epilogue (TMEM lane quarter = warp % 4, column group = warp / 4)
+constexpr int TC5_THREADS = (TC5_EPI_WARPS + 2) * 32;   // warp 16: bulk-copy producer, warp 17: MMA issuer + TMEM alloc
 constexpr int TC5_MAX_SMEM = 227 * 1024;
 
 struct Tc5Plan { int nstage; size_t fixed, total; };
 static inline Tc5Plan tc5_plan(int H) {
     Tc5Plan p;
-    p.fixed = TC5_XIMG + (size_t)128 * H * 2 /*park*/ + 128 * 2 * 4 /*fcpart*/ + 32 * 8 /*barriers*/;
+    p.fixed = TC5_XIMG + (size_t)128 * H * 2 /*park*/ + 4 * 128 * 2 * 4 /*fcpart*/ + 32 * 8 /*barriers*/;
     long avail = TC5_MAX_SMEM - 1024 /*alignment slack*/ - (long)p.fixed;
     p.nstage = (int)(avail / TC5_STAGE);
     if (p.nstage > 12) p.nstage = 12;
@@ -52,24 +53,30 @@ bool lstm_tc5_supported(int L, int H, int I, int O) { return L == 2 && H % 64 ==
 
 size_t lstm_tc5_cstate_bytes(int ntiles, int H) { return (size_t)ntiles * 2 * H * 128 * sizeof(float); }
 
-// One LSTM cell from the four gate pre-activations.  Accurate path: 5 ex2 + 3 rcp (the i*tanh(g) and
-// o*tanh(c) products share one reciprocal each); fast path: 5 tanh.approx.
+// One LSTM cell.  ai/af/ao = -log2(e) * (gate pre-activation), ag = -2 log2(e) * (g pre-activation): the scale and
+// the bias are folded into one FMA on the accumulator (biases are stored pre-scaled).
+// Accurate path: 5 ex2 + 3 rcp (i*tanh(g) and o*tanh(c) share one reciprocal each); fast path: 5 tanh.approx.
 template <bool FAST>
-__device__ __forceinline__ void lstm_cell(float gi, float gf, float gg, float go, float cprev, float& c, float& h) {
+__device__ __forceinline__ void lstm_cell(float ai, float af, float ag, float ao, float cprev, float& c, float& h) {
     if (FAST) {
-        c = sigmoid_fast(gf) * cprev + sigmoid_fast(gi) * tanh_approx(gg);
-        h = sigmoid_fast(go) * tanh_approx(c);
+        const float K = -0.34657359027997264f;                                // -0.5 / log2(e)
+        const float si = fmaf(0.5f, tanh_approx(ai * K), 0.5f), sf = fmaf(0.5f, tanh_approx(af * K), 0.5f);
+        c = fmaf(sf, cprev, si * tanh_approx(ag * K));
+        h = fmaf(0.5f, tanh_approx(ao * K), 0.5f) * tanh_approx(c);
     } else {
-        const float L2E = 1.4426950408889634f;
-        const float ei = ex2f(-L2E * fmaxf(gi, -30.f));
-        const float eg = ex2f(-2.f * L2E * fminf(fmaxf(gg, -15.f), 15.f));
-        const float ef = ex2f(-L2E * gf);
-        const float ig = (1.f - eg) * rcpf((1.f + ei) * (1.f + eg));          // sigmoid(gi) * tanh(gg)
+        const float ei = ex2f(ai), ef = ex2f(af);
+        const float eg = ex2f(fminf(fmaxf(ag, -43.f), 43.f));                  // tanh saturates: |g| <= 15
+        const float ig = (1.f - eg) * rcpf((1.f + ei) * (1.f + eg));          // sigmoid(i) * tanh(g)
         c = fmaf(rcpf(1.f + ef), cprev, ig);
-        const float eo = ex2f(-L2E * fmaxf(go, -30.f));
-        const float ec = ex2f(-2.f * L2E * fminf(fmaxf(c, -15.f), 15.f));
-        h = (1.f - ec) * rcpf((1.f + eo) * (1.f + ec));                       // sigmoid(go) * tanh(c)
+        const float eo = ex2f(ao);
+        const float ec = ex2f(fminf(fmaxf(c * -2.8853900817779268f, -43.f), 43.f));
+        h = (1.f - ec) * rcpf((1.f + eo) * (1.f + ec));                       // sigmoid(o) * tanh(c)
     }
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+                 : "memory");
 }
 
 template <bool FAST>
@@ -83,8 +90,8 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
     uint8_t* stages = smem;
     uint8_t* ximg = stages + (size_t)nstage * TC5_STAGE;
     uint8_t* park = ximg + TC5_XIMG;
-    float* fcpart = reinterpret_cast<float*>(park + (size_t)128 * H * 2);   // [128][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(fcpart + 128 * 2);
+    float* fcpart = reinterpret_cast<float*>(park + (size_t)128 * H * 2);   // [4][128][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fcpart + 4 * 128 * 2);
     uint64_t* full = bars;
     uint64_t* empty = full + nstage;
     uint64_t* xfull = empty + nstage;
@@ -98,12 +105,12 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
     if (tid == 0) {
         for (int i = 0; i < nstage; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(xfull, 1); mbar_init(xempty, 1);
-        mbar_init(accfull, 1); mbar_init(accempty, 256);
-        mbar_init(hready, 256);
+        mbar_init(accfull, 1); mbar_init(accempty, TC5_EPI_WARPS * 32);
+        mbar_init(hready, TC5_EPI_WARPS * 32);
         mbar_init(layerdone, 1);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    if (warp == TC5_EPI_WARPS + 1) tmem_alloc<512>(tmem_slot);
     tc5_fence_before();
     __syncthreads();
     tc5_fence_after();
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
     const uint32_t acc_col = 2 * hcols;
     const int SPS0 = NCH * (1 + KBH), SPS1 = NCH * 2 * KBH;       // weight stages per layer-step
 
-    if (warp == 0) {
+    if (warp == TC5_EPI_WARPS) {
         // ======================= bulk-copy producer =======================================
         if (lane == 0) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wstream);
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == TC5_EPI_WARPS + 1) {
         // ======================= MMA issuer (one thread) ==================================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_f16(128, 128);
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
                     tc5_fence_after();
                     const int nkb = (layer == 0) ? 1 + KBH : 2 * KBH;
                     for (int j = 0; j < NCH; ++j) {
-                        mbar_wait(accempty, (accuse & 1) ^ 1);     // both warpgroups have drained the accumulator
+                        mbar_wait(accempty, (accuse & 1) ^ 1);     // every epilogue warp has drained the accumulator
                         ++accuse;
                         tc5_fence_after();
                         for (int kb = 0; kb < nkb; ++kb) {
@@ -177,24 +184,24 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
                 }
             }
         }
-    } else if (warp >= 4) {
-        // ======================= epilogue warpgroups ======================================
-        // Both warpgroups work on every chunk: warpgroup wg owns accumulator columns [64 wg, 64 wg + 64)
-        // = gates i,f,g,o of hidden units 32 j + 16 wg + [0, 16).
-        const int wg = (warp - 4) >> 2;
-        const int q = warp & 3;                                    // TMEM lane quarter of this warp
+    } else {
+        // ======================= epilogue warps ===========================================
+        // Every warp works on every chunk: warp (quarter q, column group cg) owns TMEM lanes [32 q, 32 q + 32) and
+        // accumulator columns [32 cg, 32 cg + 32) = gates i,f,g,o of hidden units 32 j + 8 cg + [0, 8).
+        const int cg = warp >> 2;
+        const int q = warp & 3;
         const int r = q * 32 + lane;                               // sequence (row) inside the tile
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
         {
             const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int c = wg * NCH; c < (wg + 1) * NCH; ++c) { tmem_st8(tl + c * 8, z); tmem_st8(tl + hcols + c * 8, z); }
+            for (int c = cg; c < 2 * NCH * 2; c += 4) tmem_st8(tl + c * 8, z);   // 2 layers x hcols columns = 4 NCH groups of 8
             tmem_wait_st();
             tc5_fence_before();
             mbar_arrive(hready);
         }
         uint32_t accn = 0, ls = 0;
         float* cbase = a.cstate + (size_t)tile * 2 * H * 128;
-        uint8_t* mypark = park + ((size_t)wg * NCH * 128 + r) * 32;
+        uint8_t* mypark = park + ((size_t)cg * NCH * 128 + r) * 16;
         const int grow = tile * 128 + r;
         const int ob = grow / a.F, of = grow % a.F;
         const int Tout = Tp - a.la;
@@ -204,28 +211,27 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
             for (int layer = 0; layer < 2; ++layer, ++ls) {
                 float fc0 = 0.f, fc1 = 0.f;
                 for (int j = 0; j < NCH; ++j) {
-                    float4* cp = reinterpret_cast<float4*>(cbase + ((size_t)((layer * NCH + j) * 2 + wg) * 4) * 128 * 4) + r;
-                    float4 c4[4];
+                    float4* cp = reinterpret_cast<float4*>(cbase + ((size_t)((layer * NCH + j) * 4 + cg) * 2) * 128 * 4) + r;
+                    float4 c4[2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) c4[i] = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[i * 128];
-                    const float4* bj = reinterpret_cast<const float4*>(a.bias + (size_t)(layer * NCH + j) * 128 + wg * 64);
+                    for (int i = 0; i < 2; ++i) c4[i] = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[i * 128];
+                    const float4* bj = reinterpret_cast<const float4*>(a.bias + (size_t)(layer * NCH + j) * 128 + cg * 32);
                     mbar_wait(accfull, accn & 1);
                     ++accn;
                     tc5_fence_after();
-                    uint32_t v[4][16];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) tmem_ld16(tl + acc_col + wg * 64 + g * 16, v[g]);
+                    uint32_t v[2][16];
+                    tmem_ld16(tl + acc_col + cg * 32, v[0]);               // i(8) f(8)
+                    tmem_ld16(tl + acc_col + cg * 32 + 16, v[1]);          // g(8) o(8)
                     tmem_wait_ld();
                     tc5_fence_before();
                     mbar_arrive(accempty);
 
-                    const float4* w0 = reinterpret_cast<const float4*>(a.fc_w + j * 32 + wg * 16);
-                    const float4* w1 = reinterpret_cast<const float4*>(a.fc_w + H + j * 32 + wg * 16);
-                    uint32_t hp[8];
-                    float cn[16];
+                    const float L2E = 1.4426950408889634f;
+                    uint32_t hp[4];
+                    float cn[8];
 #pragma unroll
-                    for (int u4 = 0; u4 < 4; ++u4) {
-                        const float4 bi = __ldg(bj + u4), bf = __ldg(bj + 4 + u4), bg = __ldg(bj + 8 + u4), bo = __ldg(bj + 12 + u4);
+                    for (int u4 = 0; u4 < 2; ++u4) {
+                        const float4 bi = __ldg(bj + u4), bf = __ldg(bj + 2 + u4), bg = __ldg(bj + 4 + u4), bo = __ldg(bj + 6 + u4);
                         const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, bfa[4] = {bf.x, bf.y, bf.z, bf.w};
                         const float bga[4] = {bg.x, bg.y, bg.z, bg.w}, boa[4] = {bo.x, bo.y, bo.z, bo.w};
                         const float cpv[4] = {c4[u4].x, c4[u4].y, c4[u4].z, c4[u4].w};
@@ -233,46 +239,45 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int u = u4 * 4 + e;
-                            lstm_cell<FAST>(__uint_as_float(v[0][u]) + bia[e], __uint_as_float(v[1][u]) + bfa[e],
-                                            __uint_as_float(v[2][u]) + bga[e], __uint_as_float(v[3][u]) + boa[e], cpv[e], cn[u], hv[e]);
+                            lstm_cell<FAST>(fmaf(__uint_as_float(v[0][u]), -L2E, bia[e]), fmaf(__uint_as_float(v[0][8 + u]), -L2E, bfa[e]),
+                                            fmaf(__uint_as_float(v[1][u]), -2.f * L2E, bga[e]), fmaf(__uint_as_float(v[1][8 + u]), -L2E, boa[e]),
+                                            cpv[e], cn[u], hv[e]);
                         }
                         if (layer == 1) {
-                            const float4 wa = __ldg(w0 + u4), wb = __ldg(w1 + u4);
+                            const float4 wa = __ldg(reinterpret_cast<const float4*>(a.fc_w + j * 32 + cg * 8) + u4);
+                            const float4 wb = __ldg(reinterpret_cast<const float4*>(a.fc_w + H + j * 32 + cg * 8) + u4);
                             fc0 = fmaf(hv[0], wa.x, fmaf(hv[1], wa.y, fmaf(hv[2], wa.z, fmaf(hv[3], wa.w, fc0))));
                             fc1 = fmaf(hv[0], wb.x, fmaf(hv[1], wb.y, fmaf(hv[2], wb.z, fmaf(hv[3], wb.w, fc1))));
                         }
                         hp[2 * u4] = pack_half2(hv[0], hv[1]);
                         hp[2 * u4 + 1] = pack_half2(hv[2], hv[3]);
                     }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) cp[i * 128] = make_float4(cn[4 * i], cn[4 * i + 1], cn[4 * i + 2], cn[4 * i + 3]);
-                    uint4* pk = reinterpret_cast<uint4*>(mypark + (size_t)j * 128 * 32);
-                    pk[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-                    pk[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+                    cp[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                    cp[128] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                    *reinterpret_cast<uint4*>(mypark + (size_t)j * 128 * 16) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                 }
                 // every MMA of this layer-step has retired -> h_{t-1} may be overwritten in TMEM
                 mbar_wait(layerdone, ls & 1);
                 tc5_fence_after();
                 for (int j = 0; j < NCH; ++j) {
-                    const uint4* pk = reinterpret_cast<const uint4*>(mypark + (size_t)j * 128 * 32);
-                    const uint4 p0 = pk[0], p1 = pk[1];
-                    const uint32_t hv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-                    tmem_st8(tl + layer * hcols + j * 16 + wg * 8, hv);
+                    const uint4 p0 = *reinterpret_cast<const uint4*>(mypark + (size_t)j * 128 * 16);
+                    const uint32_t hv[4] = {p0.x, p0.y, p0.z, p0.w};
+                    tmem_st4(tl + layer * hcols + j * 16 + cg * 4, hv);
                 }
                 tmem_wait_st();
                 tc5_fence_before();
                 mbar_arrive(hready);
 
                 if (layer == 1) {
-                    if (wg == 1) { fcpart[2 * r] = fc0; fcpart[2 * r + 1] = fc1; }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    if (wg == 0 && t >= a.la && grow < a.rows) {
-                        const float o0 = fc0 + fcpart[2 * r] + fcb0;
-                        const float o1 = fc1 + fcpart[2 * r + 1] + fcb1;
+                    if (cg != 0) { fcpart[(cg * 128 + r) * 2] = fc0; fcpart[(cg * 128 + r) * 2 + 1] = fc1; }
+                    asm volatile("bar.sync 1, 512;" ::: "memory");
+                    if (cg == 0 && t >= a.la && grow < a.rows) {
+                        const float o0 = fc0 + fcpart[(128 + r) * 2] + fcpart[(256 + r) * 2] + fcpart[(384 + r) * 2] + fcb0;
+                        const float o1 = fc1 + fcpart[(128 + r) * 2 + 1] + fcpart[(256 + r) * 2 + 1] + fcpart[(384 + r) * 2 + 1] + fcb1;
                         a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)] = o0;
                         a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)] = o1;
                     }
-                    asm volatile("bar.sync 2, 256;" ::: "memory");    // fcpart is single-buffered
+                    asm volatile("bar.sync 2, 512;" ::: "memory");    // fcpart is single-buffered
                 }
             }
         }
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
     tc5_fence_before();
     __syncthreads();
     tc5_fence_after();
-    if (warp == 2) tmem_dealloc<512>(tmem);
+    if (warp == TC5_EPI_WARPS + 1) tmem_dealloc<512>(tmem);
 }
 
 int launch_lstm_tc5(const LstmTc5Launch& a, cudaStream_t s) {
@@ -322,8 +327,8 @@ extern "C" int64_t fsn_tc5_weight_stream_bytes(int32_t I, int32_t H) {
     return (int64_t)(NCH * (1 + KBH) + NCH * 2 * KBH) * fsn::TC5_STAGE;
 }
 
-// Gate column n (0..127) of chunk j <-> weight row: n = wg*64 + q*16 + u, q in (i,f,g,o), hidden unit 32 j + 16 wg + u.
-extern "C" int32_t fsn_tc5_gate_row(int32_t H, int32_t j, int32_t n) { return ((n % 64) / 16) * H + 32 * j + 16 * (n / 64) + (n % 16); }
+// Gate column n (0..127) of chunk j <-> weight row: n = cg*32 + q*8 + u, q in (i,f,g,o), hidden unit 32 j + 8 cg + u.
+extern "C" int32_t fsn_tc5_gate_row(int32_t H, int32_t j, int32_t n) { return ((n % 32) / 8) * H + 32 * j + 8 * (n / 32) + (n % 8); }
 
 extern "C" int fsn_tc5_pack_weights(int32_t I, int32_t H, const float* w_ih0, const float* w_hh0, const float* w_ih1,
                                     const float* w_hh1, uint16_t* dst) {

@@ -97,7 +97,7 @@ def test_sw128_offsets(built_lib):
 def test_tc5_weight_stream_layout(built_lib):
     """The stream must hold, stage by stage in consumption order, 128 gate columns x 64 k tiles whose un-swizzled
     content is the slice of [W_ih | W_hh] the kernel's MMA schedule expects (gate column n of 32-unit chunk j =
-    gates i,f,g,o of units 32 j + 16 (n // 64) + n % 16)."""
+    gates i,f,g,o of units 32 j + 8 (n // 32) + n % 8)."""
     I, H = 34, 128
     rng = np.random.default_rng(0)
     w = [rng.standard_normal(s).astype(np.float32) for s in ((4 * H, I), (4 * H, H), (4 * H, H), (4 * H, H))]
@@ -113,7 +113,7 @@ def test_tc5_weight_stream_layout(built_lib):
     for layer in range(2):
         for j in range(NCH):
             rows = np.array([built_lib.fsn_tc5_gate_row(H, j, n) for n in range(128)])
-            assert list(rows[:3]) == [32 * j, 32 * j + 1, 32 * j + 2] and rows[16] == H + 32 * j and rows[64] == 32 * j + 16
+            assert list(rows[:3]) == [32 * j, 32 * j + 1, 32 * j + 2] and rows[8] == H + 32 * j and rows[32] == 32 * j + 8
             blocks = []
             if layer == 0:
                 x = np.zeros((128, 64), np.float32); x[:, :I] = w[0][rows]
