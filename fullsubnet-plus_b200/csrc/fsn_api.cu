@@ -61,6 +61,13 @@ struct fsn_model {
     // workspaces (grow-only, keyed by the last (B, T))
     int wsB = 0, wsT = 0;
     DevBuf fbin, fbout, xa, xb, y1, y2, stats, mu, ximg, cstate, magpad, fbx, hseq, stage_in[3], stage_out;
+    // tcgen05 TCN (FullSubNet+): folded / padded weights, per-block tensor maps, time-major activations
+    bool tcn5 = false;
+    int Cp = 0, tcnNT = 0, tcnNtiles = 0, num_sms = 148;
+    DevBuf tW1, tW2, tWfc, tS1, tS2b, tBfc;            // [8][3][512][Cp], [8][3][Cp][512], [3][Cp][Cp], [8][3][Cp] x2, [3][Cp]
+    DevBuf x0, xr;                                     // time-major fb input / relu'd last residual
+    alignas(64) unsigned char mapW1[8][128], mapW2[8][128], mapWfc[128];
+    alignas(64) unsigned char mapX0[128], mapXa[128], mapXb[128], mapXr[128], mapY2[128];
     int64_t launches = 0;
     int last_impl = 0;
     static const int NEV = 32;
@@ -184,6 +191,80 @@ static int pack_lstm(fsn_model* m, const std::string& pre, int I, int Ipad, int 
     return 0;
 }
 
+
+// tf32 rounding (round-to-nearest on the 13 dropped mantissa bits) so the tensor core's truncation is exact
+static float to_tf32(float x) {
+    uint32_t u; std::memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u += 0x00000fffu + ((u >> 13) & 1u);
+    u &= 0xffffe000u;
+    float y; std::memcpy(&y, &u, 4);
+    return y;
+}
+
+// FullSubNet+ TCN weights for the tcgen05 GEMMs (k_gemm_tc5.cu): channel dim padded to Cp (multiple of 32),
+// the three branches stacked, gLN2 folded into the second 1x1 convolution:
+//   conv(W2, gLN(y)) = rstd * (W2 diag(gamma2)) y - mean * rstd * s1 + s2,  s1[n] = sum_c W2'[n,c],  s2[n] = sum_c W2[n,c] beta2[c]
+static int pack_tcn5(fsn_model* m) {
+    const fsn_config& c = m->cfg;
+    const int F = c.num_freqs, Cp = (F + 31) / 32 * 32, Hd = 512;
+    m->Cp = Cp;
+    int nt = 1;
+    for (; nt <= 64; ++nt) if (Cp % nt == 0 && (Cp / nt) % 16 == 0 && Cp / nt <= 256) break;
+    if (nt > 64) { m->tcn5 = false; return FSN_OK; }
+    m->tcnNtiles = nt; m->tcnNT = Cp / nt;
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) m->num_sms = prop.multiProcessorCount;
+    const char* sfx[3] = {"", "_real", "_imag"};
+    std::vector<float> W1((size_t)8 * 3 * Hd * Cp, 0.f), W2((size_t)8 * 3 * Cp * Hd, 0.f), Wfc((size_t)3 * Cp * Cp, 0.f);
+    std::vector<float> S1((size_t)8 * 3 * Cp, 0.f), S2b((size_t)8 * 3 * Cp, 0.f), Bfc((size_t)3 * Cp, 0.f);
+    for (int blk = 0; blk < 8; ++blk)
+        for (int b = 0; b < 3; ++b) {
+            const std::string q = std::string("fb_model") + sfx[b] + ".sequence_model." + std::to_string(blk) + ".";
+            const auto& w1 = m->host[q + "conv1x1.weight"];
+            const auto& w2 = m->host[q + "sconv.weight"];
+            const auto& b2 = m->host[q + "sconv.bias"];
+            const auto& g2 = m->host[q + "norm2.weight"];
+            const auto& be2 = m->host[q + "norm2.bias"];
+            float* d1 = &W1[((size_t)blk * 3 + b) * Hd * Cp];
+            for (int o = 0; o < Hd; ++o)
+                for (int k = 0; k < F; ++k) d1[(size_t)o * Cp + k] = to_tf32(w1[(size_t)o * F + k]);
+            float* d2 = &W2[((size_t)blk * 3 + b) * Cp * Hd];
+            for (int n = 0; n < F; ++n) {
+                double s1 = 0, s2 = 0;
+                for (int k = 0; k < Hd; ++k) {
+                    const float wf = to_tf32(w2[(size_t)n * Hd + k] * g2[k]);
+                    d2[(size_t)n * Hd + k] = wf;
+                    s1 += (double)wf;
+                    s2 += (double)w2[(size_t)n * Hd + k] * (double)be2[k];
+                }
+                S1[((size_t)blk * 3 + b) * Cp + n] = (float)s1;
+                S2b[((size_t)blk * 3 + b) * Cp + n] = (float)(s2 + (double)b2[n]);
+            }
+        }
+    for (int b = 0; b < 3; ++b) {
+        const auto& w = m->host[std::string("fb_model") + sfx[b] + ".fc_output_layer.weight"];
+        const auto& bb = m->host[std::string("fb_model") + sfx[b] + ".fc_output_layer.bias"];
+        for (int n = 0; n < F; ++n) {
+            for (int k = 0; k < F; ++k) Wfc[((size_t)b * Cp + n) * Cp + k] = to_tf32(w[(size_t)n * F + k]);
+            Bfc[(size_t)b * Cp + n] = bb[n];
+        }
+    }
+    if (upload(m->tW1, W1.data(), W1.size() * 4) || upload(m->tW2, W2.data(), W2.size() * 4) || upload(m->tWfc, Wfc.data(), Wfc.size() * 4) ||
+        upload(m->tS1, S1.data(), S1.size() * 4) || upload(m->tS2b, S2b.data(), S2b.size() * 4) || upload(m->tBfc, Bfc.data(), Bfc.size() * 4))
+        return fail(FSN_ECUDA, "upload of the TCN weights failed");
+    for (int blk = 0; blk < 8; ++blk) {
+        if (make_tmap_f32_2d(m->mapW1[blk], static_cast<float*>(m->tW1.p) + (size_t)blk * 3 * Hd * Cp, 3 * Hd, Cp, 256) ||
+            make_tmap_f32_2d(m->mapW2[blk], static_cast<float*>(m->tW2.p) + (size_t)blk * 3 * Cp * Hd, 3 * Cp, Hd, m->tcnNT))
+            return fail(FSN_ECUDA, "cuTensorMapEncodeTiled failed for the TCN weights");
+    }
+    if (make_tmap_f32_2d(m->mapWfc, m->tWfc.p, 3 * Cp, Cp, m->tcnNT)) return fail(FSN_ECUDA, "cuTensorMapEncodeTiled failed (fc)");
+    m->tcn5 = true;
+    return FSN_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
@@ -220,7 +301,7 @@ extern "C" void fsn_model_destroy(fsn_model* m) {
     if (!m) return;
     DevBuf* all[] = {&m->arena, &m->sb_tc5_stream, &m->sb_tc5_bias, &m->fbin, &m->fbout, &m->xa, &m->xb, &m->y1, &m->y2, &m->stats,
                      &m->mu, &m->ximg, &m->cstate, &m->magpad, &m->fbx, &m->hseq, &m->stage_in[0], &m->stage_in[1], &m->stage_in[2],
-                     &m->stage_out};
+                     &m->stage_out, &m->tW1, &m->tW2, &m->tWfc, &m->tS1, &m->tS2b, &m->tBfc, &m->x0, &m->xr};
     for (auto* b : all) b->release();
     for (int i = 0; i < fsn_model::NEV; ++i) { if (m->ev0[i]) cudaEventDestroy(m->ev0[i]); if (m->ev1[i]) cudaEventDestroy(m->ev1[i]); }
     for (int i = 0; i < 4; ++i) { m->sb_frag[i].release(); m->sb_bias[i].release(); m->fb_frag[i].release(); m->fb_bias[i].release(); }
@@ -292,6 +373,10 @@ extern "C" int fsn_model_finalize(fsn_model* m) {
         }
         if (upload(m->sb_tc5_bias, bp.data(), bp.size() * 4)) return fail(FSN_ECUDA, "upload failed");
     }
+    if (c.model_kind == FSN_KIND_PLUS) {
+        int rc = pack_tcn5(m);
+        if (rc) return rc;
+    }
     m->finalized = true;
     return FSN_OK;
 }
@@ -316,7 +401,24 @@ static int ensure_ws(fsn_model* m, int B, int T) {
     size_t cs = lstm_mma_cstate_bytes(c.num_layers, rows, c.sb_hidden, &ra);
     size_t cs5 = lstm_tc5_cstate_bytes(ntiles, c.sb_hidden);
     e |= m->cstate.ensure(cs > cs5 ? cs : cs5, true);
-    if (c.model_kind == FSN_KIND_PLUS) {
+    if (c.model_kind == FSN_KIND_PLUS && m->tcn5) {
+        const size_t rows = (size_t)3 * B * Tp;
+        const bool regeo = (m->wsB != B || m->wsT != T);
+        if (regeo) { m->x0.release(); m->xa.release(); m->xb.release(); m->xr.release(); m->y1.release(); m->y2.release(); }
+        e |= m->x0.ensure(rows * m->Cp * 4, true);
+        e |= m->xa.ensure(rows * m->Cp * 4, true);
+        e |= m->xb.ensure(rows * m->Cp * 4, true);
+        e |= m->xr.ensure(rows * m->Cp * 4, true);
+        e |= m->y1.ensure(rows * 512 * 4, true);
+        e |= m->y2.ensure(rows * 512 * 4, true);
+        e |= m->stats.ensure((size_t)8 * 2 * 3 * B * 2 * sizeof(double), true);
+        if (!e && regeo) {
+            if (make_tmap_f32_2d(m->mapX0, m->x0.p, rows, m->Cp, 128) || make_tmap_f32_2d(m->mapXa, m->xa.p, rows, m->Cp, 128) ||
+                make_tmap_f32_2d(m->mapXb, m->xb.p, rows, m->Cp, 128) || make_tmap_f32_2d(m->mapXr, m->xr.p, rows, m->Cp, 128) ||
+                make_tmap_f32_2d(m->mapY2, m->y2.p, rows, 512, 128))
+                return fail(FSN_ECUDA, "cuTensorMapEncodeTiled failed for the activations");
+        }
+    } else if (c.model_kind == FSN_KIND_PLUS) {
         e |= m->xa.ensure(act, true);
         e |= m->xb.ensure(act, true);
         const size_t hid = (size_t)3 * B * 512 * Pp * 4;
@@ -361,6 +463,9 @@ static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s)
         a.img = static_cast<const __half*>(m->ximg.p); a.ntiles = ntiles;
         a.cstate = static_cast<float*>(m->cstate.p);
         a.out = d_out; a.F = F; a.la = c.look_ahead; a.fast = c.fast_math;
+        { const char* ev = getenv("FSN_TC5_ELECT"); a.elect = ev ? atoi(ev) : 0; }
+        { const char* ev = getenv("FSN_TC5_NSTAGE"); a.nstage_cap = ev ? atoi(ev) : 0; }
+        { const char* ev = getenv("FSN_TC5_DEBUG"); a.debug = ev ? atoi(ev) : 0; }
         int e = launch_lstm_tc5(a, s);
         if (e) return fail(FSN_ECUDA, "tcgen05 LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
     } else {
@@ -425,12 +530,65 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
             ta.p[b].fc2_w = P(m, p + ".fc2.weight"); ta.p[b].fc2_b = P(m, p + ".fc2.bias");
         }
         ta.out = static_cast<float*>(m->fbin.p);
+        if (m->tcn5) { ta.out_tm = static_cast<float*>(m->x0.p); ta.Cp = m->Cp; }
         launch_tsse_norm(ta, s); m->launches++;
 
         const int Z = 3 * B;
         double* stats = static_cast<double*>(m->stats.p);
         CK(cudaMemsetAsync(stats, 0, (size_t)8 * 2 * Z * 2 * sizeof(double), s));
         static const int dil[8] = {1, 2, 5, 9, 1, 2, 5, 9};     // sequence_model.py:47-58
+        if (m->tcn5) {
+            const int Cp = m->Cp;
+            GemmTc5Launch g{};
+            g.rows_per_branch = B * Tp; g.tiles_m = (B * Tp + 127) / 128; g.nbranch = 3; g.Tp = Tp; g.B = B;
+            const float* curp = static_cast<const float*>(m->x0.p);
+            const unsigned char* curmap = m->mapX0;
+            for (int blk = 0; blk < 8; ++blk) {
+                double* st1 = stats + (size_t)(2 * blk) * Z * 2;
+                double* st2 = stats + (size_t)(2 * blk + 1) * Z * 2;
+                auto key = [&](int b, const char* leaf) { return std::string("fb_model") + sfx[b] + ".sequence_model." + std::to_string(blk) + "." + leaf; };
+                GemmTc5Launch g1 = g;
+                g1.epi = EPI5_PRELU_STATS; g1.Kp = Cp; g1.NT = 256; g1.ntiles_n = 2; g1.Npad = 512;
+                for (int b = 0; b < 3; ++b) { g1.bias[b] = P(m, key(b, "conv1x1.bias")); g1.prelu[b] = P(m, key(b, "prelu1.weight")); }
+                g1.stats_out = st1; g1.Y = static_cast<float*>(m->y1.p); g1.ldY = 512;
+                int e = launch_gemm_tc5(curmap, m->mapW1[blk], g1, m->num_sms, s);
+                if (e) return fail(FSN_ECUDA, "TCN GEMM1 launch failed: %s", cudaGetErrorString((cudaError_t)e));
+                m->launches++;
+
+                DwTmLaunch dw{};
+                dw.X = static_cast<const float*>(m->y1.p); dw.Y = static_cast<float*>(m->y2.p);
+                dw.Z = Z; dw.B = B; dw.C = 512; dw.Tp = Tp; dw.dilation = dil[blk]; dw.tchunk = 48;
+                dw.stats_in = st1; dw.stats_out = st2;
+                for (int b = 0; b < 3; ++b) {
+                    dw.gamma[b] = P(m, key(b, "norm1.weight")); dw.beta[b] = P(m, key(b, "norm1.bias"));
+                    dw.w[b] = P(m, key(b, "depthwise_conv.weight")); dw.b[b] = P(m, key(b, "depthwise_conv.bias"));
+                    dw.prelu[b] = P(m, key(b, "prelu2.weight"));
+                }
+                launch_dwconv_tm(dw, s); m->launches++;
+
+                float* nxtp = (blk & 1) ? static_cast<float*>(m->xb.p) : static_cast<float*>(m->xa.p);
+                GemmTc5Launch g2 = g;
+                g2.epi = EPI5_GLN_RES; g2.Kp = 512; g2.NT = m->tcnNT; g2.ntiles_n = m->tcnNtiles; g2.Npad = Cp;
+                for (int b = 0; b < 3; ++b) {
+                    g2.bias[b] = static_cast<const float*>(m->tS2b.p) + ((size_t)blk * 3 + b) * Cp;
+                    g2.s1[b] = static_cast<const float*>(m->tS1.p) + ((size_t)blk * 3 + b) * Cp;
+                }
+                g2.stats_in = st2; g2.count_in = (double)512 * Tp;
+                g2.Xold = curp; g2.Y = nxtp; g2.ldY = Cp; g2.Xrelu = (blk == 7) ? static_cast<float*>(m->xr.p) : nullptr;
+                e = launch_gemm_tc5(m->mapY2, m->mapW2[blk], g2, m->num_sms, s);
+                if (e) return fail(FSN_ECUDA, "TCN GEMM2 launch failed: %s", cudaGetErrorString((cudaError_t)e));
+                m->launches++;
+                curp = nxtp;
+                curmap = (blk & 1) ? m->mapXb : m->mapXa;
+            }
+            GemmTc5Launch g3 = g;
+            g3.epi = EPI5_OUT; g3.Kp = Cp; g3.NT = m->tcnNT; g3.ntiles_n = m->tcnNtiles; g3.Npad = Cp;
+            for (int b = 0; b < 3; ++b) g3.bias[b] = static_cast<const float*>(m->tBfc.p) + (size_t)b * Cp;
+            g3.out = static_cast<float*>(m->fbout.p); g3.F = F; g3.P = Pp; g3.act = c.fb_act;
+            int e = launch_gemm_tc5(m->mapXr, m->mapWfc, g3, m->num_sms, s);
+            if (e) return fail(FSN_ECUDA, "TCN output GEMM launch failed: %s", cudaGetErrorString((cudaError_t)e));
+            m->launches++;
+        } else {
         const float* cur = static_cast<const float*>(m->fbin.p);
         float* nxt = static_cast<float*>(m->xa.p);
         for (int blk = 0; blk < 8; ++blk) {
@@ -473,6 +631,7 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
             cf.bias[b] = P(m, std::string("fb_model") + sfx[b] + ".fc_output_layer.bias");
         }
         launch_conv1x1(cf, s); m->launches++;
+        }
 
         sp.win = static_cast<const float*>(m->fbin.p); sp.Pw = Pp;      // post-attention mag branch (fullsubnet_plus.py:182)
         sp.nfb = 3;

@@ -111,6 +111,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
+// One lane of a fully converged warp (elect.sync).  The tcgen05 issue loops must stay warp-uniform and predicate only
+// the instruction on this: an `if (lane == 0)` region forces every UTCHMMA operand through R2UR moves and serialises the
+// mbarrier polls with the issue -- measured 109 vs 64 cycles per M=128,N=128 MMA (fsn_probe_tcgen05, "probe4").
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------
 __device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -23,6 +23,7 @@ struct TsseLaunch {
     int ksz[3];
     int attention;             // 0: norm only (fullsubnet.Model), 1: norm + TSSE
     float* out;                // [nbranch, B, F, P]
+    float* out_tm; int Cp;     // optional time-major copy [(branch, b, t), Cp] for the tcgen05 TCN (pad columns stay zero)
 };
 void launch_tsse_norm(const TsseLaunch& a, cudaStream_t s);
 
@@ -115,10 +116,38 @@ struct LstmTc5Launch {
     float* cstate;            // [ntiles][2 layers][H/16 chunks][4][128][4] fp32
     float* out; int F, la;
     int fast;
+    int elect;                // tuning knob: 1 = one elected mbarrier arrive per epilogue warp, 0 = every thread arrives
+    int nstage_cap;           // tuning knob: cap on the weight ring depth (0 = as many as fit)
+    int debug;                // timing experiments only (results invalid): 1 = skip the cell update, 2 = MMA issuer ignores accempty
 };
 size_t lstm_tc5_cstate_bytes(int ntiles, int H);
 bool lstm_tc5_supported(int L, int H, int I, int O);
 int launch_lstm_tc5(const LstmTc5Launch& a, cudaStream_t s);
+
+// ---- k_gemm_tc5.cu (TCN on tcgen05, time-major activations) ----------------------------------
+enum { EPI5_PRELU_STATS = 1, EPI5_GLN_RES = 2, EPI5_OUT = 3 };
+struct GemmTc5Launch {
+    int Kp, NT, nstage, ntiles_n, Npad;        // K (multiple of 32), N tile, ring depth, N tiles and padded N per branch
+    int rows_per_branch, tiles_m, nbranch, Tp, B;
+    int epi;
+    const float* bias[3];                      // PRELU_STATS / OUT: conv bias; GLN_RES: s2 + conv bias
+    const float* prelu[3];
+    const float* s1[3];                        // GLN_RES: sum_c W'[n, c]
+    double* stats_out;                         // [Z, 2]
+    const double* stats_in; double count_in;
+    float* Y; int ldY;                         // PRELU_STATS: output; GLN_RES: new residual stream
+    const float* Xold; float* Xrelu;           // GLN_RES: residual input, optional relu'd copy
+    float* out; int F, P, act;                 // OUT: [Z, F, P]
+};
+int make_tmap_f32_2d(void* out_map /*128 B, 64 B aligned*/, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+int launch_gemm_tc5(const void* mapA, const void* mapB, GemmTc5Launch a, int num_sms, cudaStream_t s);
+struct DwTmLaunch {
+    const float* X; float* Y;                  // [Z * Tp, C]
+    int Z, B, C, Tp, dilation, tchunk;
+    const double* stats_in; double* stats_out;
+    const float* gamma[3]; const float* beta[3]; const float* w[3]; const float* b[3]; const float* prelu[3];
+};
+void launch_dwconv_tm(const DwTmLaunch& a, cudaStream_t s);
 
 // ---- k_probe.cu ------------------------------------------------------------------------------
 int run_probe_tcgen05(float* h_report, int n);

@@ -98,11 +98,28 @@ __global__ void __launch_bounds__(256) tsse_norm_kernel(TsseLaunch a) {
         }
         __syncthreads();
     }
-    for (int f = warp; f < F; f += nwarp) {
-        const float g = a.attention ? gate[f] * inv : inv;
-        const float* row = x + (size_t)f * T;
-        float* orow = out + (size_t)f * a.P;
-        for (int t = lane; t < a.P; t += 32) orow[t] = (t < T) ? row[t] * g : 0.f;
+    __shared__ float tr[32][33];
+    float* otm = a.out_tm ? a.out_tm + ((size_t)br * a.B + b) * (size_t)Tp * a.Cp : nullptr;
+    for (int f0 = 0; f0 < F; f0 += 32) {
+        for (int t0 = 0; t0 < a.P; t0 += 32) {
+            for (int rr = warp; rr < 32; rr += nwarp) {
+                const int f = f0 + rr, t = t0 + lane;
+                float v = 0.f;
+                if (f < F && t < a.P) {
+                    const float g = a.attention ? gate[f] * inv : inv;
+                    v = (t < T) ? x[(size_t)f * T + t] * g : 0.f;
+                    out[(size_t)f * a.P + t] = v;
+                }
+                tr[rr][lane] = v;
+            }
+            __syncthreads();
+            if (otm)
+                for (int rr = warp; rr < 32; rr += nwarp) {
+                    const int t = t0 + rr, f = f0 + lane;
+                    if (t < Tp && f < F) otm[(size_t)t * a.Cp + f] = tr[lane][rr];
+                }
+            __syncthreads();
+        }
     }
 }
 

@@ -105,8 +105,9 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
     if (tid == 0) {
         for (int i = 0; i < nstage; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(xfull, 1); mbar_init(xempty, 1);
-        mbar_init(accfull, 1); mbar_init(accempty, TC5_EPI_WARPS * 32);
-        mbar_init(hready, TC5_EPI_WARPS * 32);
+        const uint32_t narr = a.elect ? TC5_EPI_WARPS : TC5_EPI_WARPS * 32;   // one elected arrive per epilogue warp, or every thread
+        mbar_init(accfull, 1); mbar_init(accempty, narr);
+        mbar_init(hready, narr);
         mbar_init(layerdone, 1);
         fence_barrier_init();
     }
@@ -142,8 +143,10 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
             }
         }
     } else if (warp == TC5_EPI_WARPS + 1) {
-        // ======================= MMA issuer (one thread) ==================================
-        if (lane == 0) {
+        // ======================= MMA issuer ================================================
+        // The whole warp runs the loop (uniform control flow, operands stay in uniform registers); only the
+        // tcgen05 instructions are predicated on one elected lane.
+        {
             const uint32_t idesc = umma_idesc_f16(128, 128);
             const uint32_t d = tmem + acc_col;
             int slot = 0; uint32_t ph = 0, accuse = 0, ls = 0;
@@ -158,29 +161,37 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
                     tc5_fence_after();
                     const int nkb = (layer == 0) ? 1 + KBH : 2 * KBH;
                     for (int j = 0; j < NCH; ++j) {
-                        mbar_wait(accempty, (accuse & 1) ^ 1);     // every epilogue warp has drained the accumulator
+                        if (!(a.debug & 2)) mbar_wait(accempty, (accuse & 1) ^ 1);   // every epilogue warp has drained the accumulator
                         ++accuse;
                         tc5_fence_after();
                         for (int kb = 0; kb < nkb; ++kb) {
                             mbar_wait(&full[slot], ph);
                             tc5_fence_after();
                             const uint64_t bdesc = umma_desc_sw128(smem_u32(stages + (size_t)slot * TC5_STAGE));
-                            if (layer == 0 && kb == 0) {
+                            const bool xblock = (layer == 0 && kb == 0);
+                            const uint32_t acol = (layer == 0) ? (kb - 1) * 32 : (kb < KBH ? kb * 32 : hcols + (kb - KBH) * 32);
+                            if (elect_one()) {
+                                if (xblock) {
 #pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) umma_ss(d, xdesc + 2 * kk, bdesc + 2 * kk, idesc, kk != 0);
-                            } else {
-                                const uint32_t acol = (layer == 0) ? (kb - 1) * 32 : (kb < KBH ? kb * 32 : hcols + (kb - KBH) * 32);
+                                    for (int kk = 0; kk < 4; ++kk) umma_ss(d, xdesc + 2 * kk, bdesc + 2 * kk, idesc, kk != 0);
+                                } else {
 #pragma unroll
-                                for (int kk = 0; kk < 4; ++kk)
-                                    umma_ts(d, tmem + acol + kk * 8, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        umma_ts(d, tmem + acol + kk * 8, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+                                }
+                                umma_commit(&empty[slot]);         // stage reusable once these MMAs retire
+                                if (kb == nkb - 1) {
+                                    umma_commit(accfull);
+                                    if (j == NCH - 1) {
+                                        if (layer == 0) umma_commit(xempty);
+                                        umma_commit(layerdone);
+                                    }
+                                }
                             }
-                            umma_commit(&empty[slot]);             // stage reusable once these MMAs retire
+                            __syncwarp();
                             if (++slot == nstage) { slot = 0; ph ^= 1; }
                         }
-                        umma_commit(accfull);
                     }
-                    if (layer == 0) umma_commit(xempty);
-                    umma_commit(layerdone);
                 }
             }
         }
@@ -197,7 +208,8 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
             for (int c = cg; c < 2 * NCH * 2; c += 4) tmem_st8(tl + c * 8, z);   // 2 layers x hcols columns = 4 NCH groups of 8
             tmem_wait_st();
             tc5_fence_before();
-            mbar_arrive(hready);
+            if (a.elect) __syncwarp();
+            if (!a.elect || lane == 0) mbar_arrive(hready);
         }
         uint32_t accn = 0, ls = 0;
         float* cbase = a.cstate + (size_t)tile * 2 * H * 128;
@@ -224,8 +236,10 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
                     tmem_ld16(tl + acc_col + cg * 32 + 16, v[1]);          // g(8) o(8)
                     tmem_wait_ld();
                     tc5_fence_before();
-                    mbar_arrive(accempty);
+                    if (a.elect) __syncwarp();
+                    if (!a.elect || lane == 0) mbar_arrive(accempty);
 
+                    if (a.debug & 1) continue;                     // timing experiment: drain only, no cell update
                     const float L2E = 1.4426950408889634f;
                     uint32_t hp[4];
                     float cn[8];
@@ -266,7 +280,8 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
                 }
                 tmem_wait_st();
                 tc5_fence_before();
-                mbar_arrive(hready);
+                if (a.elect) __syncwarp();
+                if (!a.elect || lane == 0) mbar_arrive(hready);
 
                 if (layer == 1) {
                     if (cg != 0) { fcpart[(cg * 128 + r) * 2] = fc0; fcpart[(cg * 128 + r) * 2 + 1] = fc1; }
@@ -290,8 +305,9 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
 
 int launch_lstm_tc5(const LstmTc5Launch& a, cudaStream_t s) {
     if (!lstm_tc5_supported(2, a.H, a.I, 2)) return (int)cudaErrorInvalidValue;
-    const Tc5Plan p = tc5_plan(a.H);
-    if (p.nstage < 3) return (int)cudaErrorInvalidValue;
+    Tc5Plan p = tc5_plan(a.H);
+    if (a.nstage_cap > 0 && a.nstage_cap < p.nstage) { p.total -= (size_t)(p.nstage - a.nstage_cap) * TC5_STAGE; p.nstage = a.nstage_cap; }
+    if (p.nstage < 2) return (int)cudaErrorInvalidValue;
     cudaError_t e;
     if (a.fast) {
         e = cudaFuncSetAttribute(lstm_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);

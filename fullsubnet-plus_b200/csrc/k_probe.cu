@@ -106,13 +106,144 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+
+// ---- timing probe 2: accumulator drain (16 warps x 32 lanes x 32 columns) and M=64 MMAs -------------------
+struct Probe2Args { long long* cycles; const uint8_t* b_img; int mode; int reps; int commit_every; int wait_every; };   // mode 0: drain, 1: M=64 TS N=128, 2: M=64 SS N=128
+
+__global__ void __launch_bounds__(576, 1) probe2_kernel(Probe2Args p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sa = smem;                 // 16 KB (content irrelevant)
+    uint8_t* sb = smem + 16384;         // 16 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_barrier_init(); }
+    if (warp == 17) tmem_alloc<512>(tslot);
+    for (int i = tid; i < 8192; i += 576) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // fp16 1.0
+    fence_proxy_async();
+    tc5_fence_before();
+    __syncthreads();
+    tc5_fence_after();
+    const uint32_t tmem = *tslot;
+    if (p.mode == 0) {
+        if (warp < 16) {
+            const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 384 + (warp >> 2) * 32;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            long long t0 = clock64();
+            uint32_t acc = 0;
+            for (int r = 0; r < p.reps; ++r) {
+                uint32_t v0[16], v1[16];
+                tmem_ld16(tl, v0); tmem_ld16(tl + 16, v1);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc += v0[i] ^ v1[i];
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            long long t1 = clock64();
+            if (tid == 0) p.cycles[0] = t1 - t0;
+            if (acc == 0x12345678u) p.cycles[1] = acc;
+        }
+    } else if (tid == 0) {
+        const uint32_t idesc = umma_idesc_f16(p.mode >= 3 ? 128 : 64, 128);
+        const uint64_t adesc = umma_desc_sw128(smem_u32(sa)), bdesc = umma_desc_sw128(smem_u32(sb));
+        long long t0 = clock64();
+        for (int r = 0; r < p.reps; ++r) {
+            // mode 3: M=128 N=128 TS with a tcgen05.commit every `commit_every` groups of 4 MMAs (0 = never) and an
+            // already-complete mbarrier try_wait every `wait_every` groups -- the in-kernel issue pattern
+            if (p.mode == 3 && p.wait_every && r % p.wait_every == 0) mbar_wait(&bars[0], 1);
+            for (int kk = 0; kk < 4; ++kk) {
+                if (p.mode == 1 || p.mode == 3) umma_ts(tmem + 384, tmem + ((r * 32 + kk * 8) % 384), bdesc + 2 * kk, idesc, 1);
+                else umma_ss(tmem + 384, adesc + 2 * kk, bdesc + 2 * kk, idesc, 1);
+            }
+            if (p.mode == 3 && p.commit_every && r % p.commit_every == 0) umma_commit(&bars[2]);
+        }
+        umma_commit(&bars[1]);
+        mbar_wait(&bars[1], 0);
+        p.cycles[0] = clock64() - t0;
+    }
+    tc5_fence_before();
+    __syncthreads();
+    tc5_fence_after();
+    if (warp == 17) tmem_dealloc<512>(tmem);
+}
+
+// ---- timing probe 4: the MMA issue loop itself -----------------------------------------------------------------
+// VARIANT bit 0: warp-uniform loop, instruction predicated by elect.sync (CUTLASS style) instead of an `if (lane == 0)` region
+//         bit 1: an (already complete) mbarrier try_wait before every group of 4 MMAs
+//         bit 2: a tcgen05.commit after every group of 4 MMAs
+//         bit 3: A operand walks over TMEM columns instead of re-reading the same 32
+
+template <int VARIANT, int N>
+__global__ void __launch_bounds__(128, 1) probe_issue_kernel(long long* cycles, int reps) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sb = smem;                 // N x 64 fp16 tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_barrier_init(); }
+    if (warp == 1) tmem_alloc<512>(tslot);
+    for (int i = tid; i < 8192; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    fence_proxy_async();
+    tc5_fence_before();
+    __syncthreads();
+    tc5_fence_after();
+    const uint32_t tmem = *tslot;
+    if (warp == 0) {
+        constexpr bool UNI = VARIANT & 1, WAIT = VARIANT & 2, COMMIT = VARIANT & 4, WALK = VARIANT & 8;
+        const uint32_t idesc = umma_idesc_f16(128, N);
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(sb));
+        const uint32_t d = tmem + 256;
+        if (UNI || lane == 0) {
+            long long t0 = clock64();
+            uint32_t acol = 0;
+            for (int r = 0; r < reps; ++r) {
+                if (WAIT) mbar_wait(&bars[0], 1);
+                if (UNI) {
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) umma_ts(d, tmem + acol + kk * 8, bdesc + 2 * kk, idesc, 1);
+                        if (COMMIT) umma_commit(&bars[2]);
+                    }
+                    __syncwarp();
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) umma_ts(d, tmem + acol + kk * 8, bdesc + 2 * kk, idesc, 1);
+                    if (COMMIT) umma_commit(&bars[2]);
+                }
+                if (WALK) acol = (acol + 32) & 127;
+            }
+            if (UNI) { if (elect_one()) umma_commit(&bars[1]); __syncwarp(); }
+            else umma_commit(&bars[1]);
+            mbar_wait(&bars[1], 0);
+            if (lane == 0) cycles[0] = clock64() - t0;
+        }
+    }
+    tc5_fence_before();
+    __syncthreads();
+    tc5_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+template <int VARIANT, int N>
+static float run_issue(long long* dc) {
+    const size_t smem = 32768 + 1024 + 64;
+    cudaFuncSetAttribute(probe_issue_kernel<VARIANT, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    probe_issue_kernel<VARIANT, N><<<1, 128, smem>>>(dc, 512);
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1.f;
+    long long cyc = 0;
+    cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost);
+    return (float)cyc / (512.0f * 4.0f);
+}
+
 static uint16_t h_bits(float f) { __half h = __float2half_rn(f); uint16_t b; std::memcpy(&b, &h, 2); return b; }
 static float h_val(uint16_t b) { __half h; std::memcpy(&h, &b, 2); return __half2float(h); }
 
 #define PROBE_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = -(int)e_ - 1000; goto done; } } while (0)
 
 int run_probe_tcgen05(float* report, int n) {
-    if (n < 16) return -1;
+    if (n < 40) return -1;
     int rc = 0;
     std::vector<uint16_t> A(128 * 64), B(256 * 64);
     std::vector<uint8_t> aimg(16384), bimg(32768);
@@ -134,7 +265,7 @@ int run_probe_tcgen05(float* report, int n) {
     const size_t smem = 16384 + 32768 + 64 + 1024;
     ProbeArgs p{};
     PROBE_CK(cudaMalloc(&da, 16384)); PROBE_CK(cudaMalloc(&db, 32768)); PROBE_CK(cudaMalloc(&dp, 128 * 32 * 4));
-    PROBE_CK(cudaMalloc(&dd, 128 * 256 * 4)); PROBE_CK(cudaMalloc(&dc, 8));
+    PROBE_CK(cudaMalloc(&dd, 128 * 256 * 4)); PROBE_CK(cudaMalloc(&dc, 16));
     PROBE_CK(cudaMemcpy(da, aimg.data(), 16384, cudaMemcpyHostToDevice));
     PROBE_CK(cudaMemcpy(db, bimg.data(), 32768, cudaMemcpyHostToDevice));
     PROBE_CK(cudaMemcpy(dp, aplain.data(), 128 * 32 * 4, cudaMemcpyHostToDevice));
@@ -173,6 +304,29 @@ int run_probe_tcgen05(float* report, int n) {
                     PROBE_CK(cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost));
                     report[idx++] = (float)cyc / (256.0f * 4.0f);
                 }
+        // drain of a 128x128 fp32 accumulator by 16 warps (cycles per drain), M=64 N=128 MMAs (cycles per instruction)
+        Probe2Args q{}; q.cycles = dc; q.b_img = db;
+        PROBE_CK(cudaFuncSetAttribute(probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 1024 + 64));
+        for (int mode = 0; mode < 3 && idx < n; ++mode) {
+            q.mode = mode; q.reps = 256;
+            probe2_kernel<<<1, 576, 32768 + 1024 + 64>>>(q);
+            PROBE_CK(cudaGetLastError());
+            PROBE_CK(cudaDeviceSynchronize());
+            long long cyc = 0;
+            PROBE_CK(cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost));
+            report[idx++] = (float)cyc / (mode == 0 ? 256.0f : 256.0f * 4.0f);
+        }
+        // issue-loop variants (see probe_issue_kernel): N=128 and N=64
+        if (idx + 16 <= n) {
+            report[idx++] = run_issue<0, 128>(dc);  report[idx++] = run_issue<1, 128>(dc);
+            report[idx++] = run_issue<2, 128>(dc);  report[idx++] = run_issue<3, 128>(dc);
+            report[idx++] = run_issue<4, 128>(dc);  report[idx++] = run_issue<5, 128>(dc);
+            report[idx++] = run_issue<6, 128>(dc);  report[idx++] = run_issue<7, 128>(dc);
+            report[idx++] = run_issue<8, 128>(dc);  report[idx++] = run_issue<15, 128>(dc);
+            report[idx++] = run_issue<0, 64>(dc);   report[idx++] = run_issue<1, 64>(dc);
+            report[idx++] = run_issue<7, 64>(dc);   report[idx++] = run_issue<1, 256>(dc);
+            report[idx++] = run_issue<7, 256>(dc);  report[idx++] = run_issue<15, 256>(dc);
+        }
         rc = idx;
     }
 done:
