@@ -66,6 +66,7 @@ struct fsn_model {
     int Cp = 0, tcnNT = 0, tcnNtiles = 0, num_sms = 148;
     DevBuf tW1, tW2, tWfc, tS1, tS2b, tBfc;            // [8][3][512][Cp], [8][3][Cp][512], [3][Cp][Cp], [8][3][Cp] x2, [3][Cp]
     DevBuf x0, xr;                                     // time-major fb input / relu'd last residual
+    DevBuf xn, sigma;                                  // pre-normalised inputs / sub-band std for the non-default norm types
     alignas(64) unsigned char mapW1[8][128], mapW2[8][128], mapWfc[128];
     alignas(64) unsigned char mapX0[128], mapXa[128], mapXb[128], mapXr[128], mapY2[128];
     int64_t launches = 0;
@@ -281,8 +282,7 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     if (c.sb_hidden % 16 || c.sb_hidden < 16) return fail(FSN_EINVAL, "sb_model_hidden_size must be a multiple of 16");
     if (c.model_kind == FSN_KIND_FSN && (c.fb_hidden % 16 || c.fb_hidden < 16)) return fail(FSN_EINVAL, "fb_model_hidden_size must be a multiple of 16");
     if (c.output_size < 1 || c.output_size > 8) return fail(FSN_EINVAL, "output_size must be 1..8");
-    if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE)
-        return fail(FSN_EINVAL, "norm_type %d not implemented on the GPU path yet (offline_laplace_norm only)", c.norm_type);
+    if (c.norm_type < FSN_NORM_OFFLINE_LAPLACE || c.norm_type > FSN_NORM_CUMULATIVE_LAYER) return fail(FSN_EINVAL, "unknown norm_type %d", c.norm_type);
     if (c.model_kind == FSN_KIND_PLUS)
         for (int i = 0; i < 3; ++i)
             if (c.kersize[i] < 1 || c.kersize[i] > 16) return fail(FSN_EINVAL, "kersize must be in 1..16");
@@ -301,7 +301,7 @@ extern "C" void fsn_model_destroy(fsn_model* m) {
     if (!m) return;
     DevBuf* all[] = {&m->arena, &m->sb_tc5_stream, &m->sb_tc5_bias, &m->fbin, &m->fbout, &m->xa, &m->xb, &m->y1, &m->y2, &m->stats,
                      &m->mu, &m->ximg, &m->cstate, &m->magpad, &m->fbx, &m->hseq, &m->stage_in[0], &m->stage_in[1], &m->stage_in[2],
-                     &m->stage_out, &m->tW1, &m->tW2, &m->tWfc, &m->tS1, &m->tS2b, &m->tBfc, &m->x0, &m->xr};
+                     &m->stage_out, &m->tW1, &m->tW2, &m->tWfc, &m->tS1, &m->tS2b, &m->tBfc, &m->x0, &m->xr, &m->xn, &m->sigma};
     for (auto* b : all) b->release();
     for (int i = 0; i < fsn_model::NEV; ++i) { if (m->ev0[i]) cudaEventDestroy(m->ev0[i]); if (m->ev1[i]) cudaEventDestroy(m->ev1[i]); }
     for (int i = 0; i < 4; ++i) { m->sb_frag[i].release(); m->sb_bias[i].release(); m->fb_frag[i].release(); m->fb_bias[i].release(); }
@@ -393,6 +393,8 @@ static int ensure_ws(fsn_model* m, int B, int T) {
     e |= m->fbin.ensure(act, true);
     e |= m->fbout.ensure(act, true);
     e |= m->mu.ensure((size_t)B * 4, true);
+    e |= m->sigma.ensure((size_t)B * 4, true);
+    if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE) e |= m->xn.ensure((size_t)nbr * B * F * Tp * 4, true);
     // images are re-zeroed whenever the geometry changes (rows beyond B*F and k >= I must stay zero)
     const size_t img_bytes = (size_t)ntiles * Tp * 16384;
     if (m->wsB != B || m->wsT != T) { m->ximg.release(); }
@@ -509,6 +511,8 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
     SbPackLaunch sp{};
     sp.B = B; sp.F = F; sp.Tp = Tp; sp.Ns = c.sb_num_neighbors; sp.Nf = c.fb_num_neighbors; sp.P = Pp;
     sp.mu = static_cast<float*>(m->mu.p);
+    sp.sigma = static_cast<float*>(m->sigma.p);
+    sp.norm_type = c.norm_type;
     sp.ximg = static_cast<__half*>(m->ximg.p);
     sp.ntiles = (B * F + 127) / 128;
 
@@ -531,6 +535,14 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
         }
         ta.out = static_cast<float*>(m->fbin.p);
         if (m->tcn5) { ta.out_tm = static_cast<float*>(m->x0.p); ta.Cp = m->Cp; }
+        if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE) {
+            NormLaunch na{};
+            na.x[0] = d_mag; na.x[1] = d_real; na.x[2] = d_imag; na.y = static_cast<float*>(m->xn.p);
+            na.nbranch = 3; na.B = B; na.F = F; na.T = T; na.Tp = Tp; na.type = c.norm_type;
+            launch_input_norm(na, s); m->launches++;
+            for (int b = 0; b < 3; ++b) ta.x[b] = static_cast<const float*>(m->xn.p) + (size_t)b * B * F * Tp;
+            ta.T = Tp; ta.prenorm = 1;                                  // padded frames are part of the normalised signal
+        }
         launch_tsse_norm(ta, s); m->launches++;
 
         const int Z = 3 * B;
@@ -640,6 +652,13 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
         TsseLaunch ta{};
         ta.x[0] = d_mag; ta.nbranch = 1; ta.B = B; ta.F = F; ta.T = T; ta.Tp = Tp; ta.P = Pp; ta.attention = 0;
         ta.out = static_cast<float*>(m->fbin.p);
+        if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE) {
+            NormLaunch na{};
+            na.x[0] = d_mag; na.y = static_cast<float*>(m->xn.p);
+            na.nbranch = 1; na.B = B; na.F = F; na.T = T; na.Tp = Tp; na.type = c.norm_type;
+            launch_input_norm(na, s); m->launches++;
+            ta.x[0] = static_cast<const float*>(m->xn.p); ta.T = Tp; ta.prenorm = 1;
+        }
         launch_tsse_norm(ta, s); m->launches++;
         launch_pad_copy(d_mag, static_cast<float*>(m->magpad.p), B, F, T, Pp, s); m->launches++;
         const int Ipad = (F + 15) / 16 * 16, rows_pad = (B + 63) / 64 * 64;

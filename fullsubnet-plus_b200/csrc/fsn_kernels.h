@@ -23,9 +23,13 @@ struct TsseLaunch {
     int ksz[3];
     int attention;             // 0: norm only (fullsubnet.Model), 1: norm + TSSE
     float* out;                // [nbranch, B, F, P]
+    int prenorm;               // 1: input is already normalised (input_norm_kernel), skip the utterance-mean division
     float* out_tm; int Cp;     // optional time-major copy [(branch, b, t), Cp] for the tcgen05 TCN (pad columns stay zero)
 };
 void launch_tsse_norm(const TsseLaunch& a, cudaStream_t s);
+// norm types other than offline_laplace_norm (reference base_model.py:227-316): y[nbranch, B, F, Tp] = norm(pad(x))
+struct NormLaunch { const float* x[3]; float* y; int nbranch, B, F, T, Tp, type; };
+void launch_input_norm(const NormLaunch& a, cudaStream_t s);
 
 enum { PRO_NONE = 0, PRO_GLN = 1, PRO_RELU = 2 };
 enum { EPI_NONE = 0, EPI_PRELU_STATS = 1, EPI_RESIDUAL = 2, EPI_ACT = 3 };
@@ -69,6 +73,8 @@ struct SbPackLaunch {
     int nfb, P;
     int B, F, Tp, Ns, Nf;    // neighbours
     float* mu;               // [B] utterance mean of the concatenated sub-band input
+    float* sigma;            // [B] unbiased std (offline_gaussian_norm only)
+    int norm_type;           // FSN_NORM_*
     __half* ximg;            // [ntiles, Tp, 128 rows, 64 halves] SWIZZLE_128B images
     int ntiles;
 };

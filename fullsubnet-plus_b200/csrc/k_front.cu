@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) tsse_norm_kernel(TsseLaunch a) {
         double tot = 0.0;
         for (int f = lane; f < F; f += 32) tot += (double)S[f];
         tot = warp_sum_d(tot);
-        if (lane == 0) s_inv = (float)(1.0 / (tot / ((double)F * (double)Tp) + 1e-5));
+        if (lane == 0) s_inv = a.prenorm ? 1.0f : (float)(1.0 / (tot / ((double)F * (double)Tp) + 1e-5));
     }
     __syncthreads();
     const float inv = s_inv;
@@ -127,6 +127,66 @@ void launch_tsse_norm(const TsseLaunch& a, cudaStream_t s) {
     size_t smem = sizeof(float) * ((size_t)a.F * (3 + 2 * TSSE_KMAX) + a.F / 2 + 8);
     cudaFuncSetAttribute(tsse_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     tsse_norm_kernel<<<dim3(a.B, a.nbranch), 256, smem, s>>>(a);
+}
+
+
+// =============================================================================================
+// Input normalisations other than offline_laplace_norm.  reference: base_model.py:227-258 (cumulative_laplace_norm),
+// :260-275 (offline_gaussian_norm), :277-316 (cumulative_layer_norm); all applied AFTER the look-ahead zero padding
+// (fullsubnet_plus.py:137-144), so the padded frames take part and come out non-zero for the centred norms.
+// One CTA per (sample, branch): per-frame sums over F, a serial fp64 scan over the frames, y = x * a[t] + b[t].
+// =============================================================================================
+__global__ void __launch_bounds__(256) input_norm_kernel(NormLaunch a) {
+    extern __shared__ float sm[];
+    const int b = blockIdx.x, br = blockIdx.y, F = a.F, T = a.T, Tp = a.Tp;
+    float* cs = sm;             // [Tp] column sums
+    float* cq = cs + Tp;        // [Tp] column sums of squares
+    float* sa = cq + Tp;        // [Tp] scale
+    float* sb = sa + Tp;        // [Tp] shift
+    const float* x = a.x[br] + (size_t)b * F * T;
+    for (int t = threadIdx.x; t < Tp; t += blockDim.x) {
+        float s = 0.f, q = 0.f;
+        if (t < T)
+            for (int f = 0; f < F; ++f) { const float v = x[(size_t)f * T + t]; s += v; q = fmaf(v, v, q); }
+        cs[t] = s; cq[t] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double EPS = 1.1920928955078125e-07;            // np.finfo(np.float32).eps (audio_zen/constant.py:8)
+        if (a.type == FSN_NORM_OFFLINE_GAUSSIAN) {
+            double s = 0, q = 0;
+            for (int t = 0; t < Tp; ++t) { s += cs[t]; q += cq[t]; }
+            const double n = (double)F * Tp, mu = s / n;
+            const double var = (q - n * mu * mu) / (n - 1.0);  // torch.std: unbiased
+            const double inv = 1.0 / (sqrt(var > 0 ? var : 0) + 1e-5);
+            for (int t = 0; t < Tp; ++t) { sa[t] = (float)inv; sb[t] = (float)(-mu * inv); }
+        } else {
+            double s = 0, q = 0;
+            for (int t = 0; t < Tp; ++t) {
+                s += cs[t]; q += cq[t];
+                const double cnt = (double)F * (t + 1), cm = s / cnt;
+                if (a.type == FSN_NORM_CUMULATIVE_LAPLACE) { sa[t] = (float)(1.0 / (cm + EPS)); sb[t] = 0.f; }
+                else {
+                    const double cv = (q - 2.0 * cm * s) / cnt + cm * cm;
+                    const double inv = 1.0 / sqrt(cv + EPS);
+                    sa[t] = (float)inv; sb[t] = (float)(-cm * inv);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    float* y = a.y + ((size_t)br * a.B + b) * F * Tp;
+    for (int e = threadIdx.x; e < F * Tp; e += blockDim.x) {
+        const int f = e / Tp, t = e % Tp;
+        const float v = (t < T) ? x[(size_t)f * T + t] : 0.f;
+        y[e] = fmaf(v, sa[t], sb[t]);
+    }
+}
+
+void launch_input_norm(const NormLaunch& a, cudaStream_t s) {
+    const size_t smem = sizeof(float) * 4 * a.Tp;
+    cudaFuncSetAttribute(input_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    input_norm_kernel<<<dim3(a.B, a.nbranch), 256, smem, s>>>(a);
 }
 
 // =============================================================================================
@@ -315,42 +375,53 @@ void launch_dwconv(const DwLaunch& a, cudaStream_t s) {
 __global__ void __launch_bounds__(256) sb_stats_kernel(SbPackLaunch a) {
     extern __shared__ float sm[];
     const int b = blockIdx.x, F = a.F, Tp = a.Tp;
-    float* Sw = sm;                 // [F]
-    float* Sf = Sw + F;             // [nfb][F]
-    __shared__ double red[8];
+    const int nrow = F * (1 + a.nfb);
+    float* S1 = sm;                 // [1 + nfb][F] row sums
+    float* S2 = sm + nrow;          // [1 + nfb][F] row sums of squares
+    __shared__ double red[16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    for (int r = warp; r < F * (1 + a.nfb); r += nwarp) {
+    for (int r = warp; r < nrow; r += nwarp) {
         const int which = r / F, f = r % F;
         const float* row = (which == 0) ? a.win + ((size_t)b * F + f) * a.Pw : a.fb[which - 1] + ((size_t)b * F + f) * a.P;
-        float acc = 0.f;
-        for (int t = lane; t < Tp; t += 32) acc += row[t];
-        acc = warp_sum(acc);
-        if (lane == 0) sm[r] = acc;
+        float acc = 0.f, acq = 0.f;
+        for (int t = lane; t < Tp; t += 32) { const float v = row[t]; acc += v; acq = fmaf(v, v, acq); }
+        acc = warp_sum(acc); acq = warp_sum(acq);
+        if (lane == 0) { S1[r] = acc; S2[r] = acq; }
     }
     __syncthreads();
-    double tot = 0.0;
+    double tot = 0.0, tq = 0.0;
     const int nw = 2 * a.Ns + 1, nf = 2 * a.Nf + 1;
-    for (int e = threadIdx.x; e < F * nw; e += blockDim.x) tot += (double)Sw[reflect_idx(e / nw + e % nw - a.Ns, F)];
+    for (int e = threadIdx.x; e < F * nw; e += blockDim.x) {
+        const int i = reflect_idx(e / nw + e % nw - a.Ns, F);
+        tot += (double)S1[i]; tq += (double)S2[i];
+    }
     for (int k = 0; k < a.nfb; ++k)
-        for (int e = threadIdx.x; e < F * nf; e += blockDim.x) tot += (double)Sf[k * F + reflect_idx(e / nf + e % nf - a.Nf, F)];
-    tot = warp_sum_d(tot);
-    if (lane == 0) red[warp] = tot;
+        for (int e = threadIdx.x; e < F * nf; e += blockDim.x) {
+            const int i = (k + 1) * F + reflect_idx(e / nf + e % nf - a.Nf, F);
+            tot += (double)S1[i]; tq += (double)S2[i];
+        }
+    tot = warp_sum_d(tot); tq = warp_sum_d(tq);
+    if (lane == 0) { red[warp] = tot; red[8 + warp] = tq; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double s = 0;
-        for (int i = 0; i < nwarp; ++i) s += red[i];
-        a.mu[b] = (float)(s / ((double)F * (double)(nw + a.nfb * nf) * (double)Tp));
+        double s = 0, q = 0;
+        for (int i = 0; i < nwarp; ++i) { s += red[i]; q += red[8 + i]; }
+        const double n = (double)F * (double)(nw + a.nfb * nf) * (double)Tp, mu = s / n;
+        a.mu[b] = (float)mu;
+        if (a.sigma) { const double var = (q - n * mu * mu) / (n - 1.0); a.sigma[b] = (float)sqrt(var > 0 ? var : 0); }
     }
 }
 
 void launch_sb_stats(const SbPackLaunch& a, cudaStream_t s) {
-    sb_stats_kernel<<<a.B, 256, sizeof(float) * a.F * (1 + a.nfb), s>>>(a);
+    sb_stats_kernel<<<a.B, 256, sizeof(float) * 2 * a.F * (1 + a.nfb), s>>>(a);
 }
 
 __global__ void __launch_bounds__(128) sb_pack_kernel(SbPackLaunch a) {
     const int f = blockIdx.x, b = blockIdx.y, F = a.F, Tp = a.Tp;
     const int row = b * F + f, tile = row >> 7, r = row & 127;
-    const float inv = 1.0f / (a.mu[b] + 1e-5f);
+    const bool gauss = (a.norm_type == FSN_NORM_OFFLINE_GAUSSIAN);
+    const float inv = gauss ? 1.0f / (a.sigma[b] + 1e-5f) : 1.0f / (a.mu[b] + 1e-5f);
+    const float sub = gauss ? a.mu[b] : 0.f;                  // (v - mu) / (sigma + 1e-5)  (base_model.py:260-275)
     const int nw = 2 * a.Ns + 1, nf = 2 * a.Nf + 1;
     const int I = nw + a.nfb * nf;
     for (int t = threadIdx.x; t < Tp; t += blockDim.x) {
@@ -362,7 +433,7 @@ __global__ void __launch_bounds__(128) sb_pack_kernel(SbPackLaunch a) {
                 const float* src = (q == 0) ? a.fb[0] : (q == 1) ? a.fb[1] : a.fb[2];
                 v = src[((size_t)b * F + reflect_idx(f + j - a.Nf, F)) * a.P + t];
             }
-            return fminf(fmaxf(v * inv, -65504.f), 65504.f);
+            return (k < I) ? fminf(fmaxf((v - sub) * inv, -65504.f), 65504.f) : 0.f;
         };
         char* img = reinterpret_cast<char*>(a.ximg) + ((size_t)tile * Tp + t) * (128 * 128);
 #pragma unroll
@@ -377,7 +448,68 @@ __global__ void __launch_bounds__(128) sb_pack_kernel(SbPackLaunch a) {
     }
 }
 
-void launch_sb_pack(const SbPackLaunch& a, cudaStream_t s) { sb_pack_kernel<<<dim3(a.F, a.B), 128, 0, s>>>(a); }
+
+// Cumulative norms of the 4-D sub-band input (base_model.py:227-258 / :277-316 with dim 1 = F folded into the batch): every
+// sequence (b, f) is normalised by the running mean (and std) over its I channels.  One warp per sequence, lanes over
+// frames, warp scan with carry.
+__global__ void __launch_bounds__(128) sb_pack_cum_kernel(SbPackLaunch a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 4 + warp, F = a.F, Tp = a.Tp;
+    if (row >= a.B * F) return;
+    const int b = row / F, f = row % F, tile = row >> 7, r = row & 127;
+    const int nw = 2 * a.Ns + 1, nf = 2 * a.Nf + 1, I = nw + a.nfb * nf;
+    const double EPS = 1.1920928955078125e-07;
+    double cs = 0.0, cq = 0.0;                                   // running sums carried across 32-frame chunks
+    for (int t0 = 0; t0 < Tp; t0 += 32) {
+        const int t = t0 + lane;
+        float v[64];
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            float x = 0.f;
+            if (t < Tp && k < I) {
+                if (k < nw) x = a.win[((size_t)b * F + reflect_idx(f + k - a.Ns, F)) * a.Pw + t];
+                else {
+                    const int kk = k - nw, qq = kk / nf, j = kk % nf;
+                    const float* src = (qq == 0) ? a.fb[0] : (qq == 1) ? a.fb[1] : a.fb[2];
+                    x = src[((size_t)b * F + reflect_idx(f + j - a.Nf, F)) * a.P + t];
+                }
+            }
+            v[k] = x; s += x; q = fmaf(x, x, q);
+        }
+        double ds = s, dq = q;                                   // inclusive scan over the 32 frames of this chunk
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double us = __shfl_up_sync(0xffffffffu, ds, o), uq = __shfl_up_sync(0xffffffffu, dq, o);
+            if (lane >= o) { ds += us; dq += uq; }
+        }
+        ds += cs; dq += cq;
+        const double cnt = (double)I * (t + 1), cm = ds / cnt;
+        float sc, sh;
+        if (a.norm_type == FSN_NORM_CUMULATIVE_LAPLACE) { sc = (float)(1.0 / (cm + EPS)); sh = 0.f; }
+        else { const double cv = (dq - 2.0 * cm * ds) / cnt + cm * cm; const double inv = 1.0 / sqrt(cv + EPS); sc = (float)inv; sh = (float)(-cm * inv); }
+        cs = __shfl_sync(0xffffffffu, ds, 31); cq = __shfl_sync(0xffffffffu, dq, 31);
+        if (t < Tp) {
+            char* img = reinterpret_cast<char*>(a.ximg) + ((size_t)tile * Tp + t) * (128 * 128);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = (c * 8 + i < I) ? fminf(fmaxf(fmaf(v[c * 8 + i], sc, sh), -65504.f), 65504.f) : 0.f;
+                *reinterpret_cast<uint4*>(img + sw128_offset(r, c * 8)) =
+                    make_uint4(pack_half2(w[0], w[1]), pack_half2(w[2], w[3]), pack_half2(w[4], w[5]), pack_half2(w[6], w[7]));
+            }
+        }
+    }
+}
+
+void launch_sb_pack(const SbPackLaunch& a, cudaStream_t s) {
+    if (a.norm_type == FSN_NORM_CUMULATIVE_LAPLACE || a.norm_type == FSN_NORM_CUMULATIVE_LAYER)
+        sb_pack_cum_kernel<<<(a.B * a.F + 3) / 4, 128, 0, s>>>(a);
+    else
+        sb_pack_kernel<<<dim3(a.F, a.B), 128, 0, s>>>(a);
+}
+
 
 __global__ void pad_copy_kernel(const float* x, float* y, int rows, int T, int P) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -199,3 +199,36 @@ def test_host_buffer_entry_point(built_lib):
     pin = lambda x: torch.from_numpy(x).pin_memory()
     host = m.forward_host(pin(mag), pin(real), pin(imag), device=DEV)
     assert torch.equal(host, dev)
+
+
+@pytest.mark.parametrize("norm", ["offline_laplace_norm", "cumulative_laplace_norm", "offline_gaussian_norm", "cumulative_layer_norm"])
+def test_fsn_small_all_norm_types_golden(built_lib, golden, norm):
+    """Every norm_type the reference's norm_wrapper accepts (base_model.py:318-330), against reference outputs."""
+    g = golden(f"fsn_small_{norm}")
+    c = O.default_fsn_config()
+    c.update(num_freqs=33, sb_num_neighbors=3, sb_model_hidden_size=32, fb_model_hidden_size=48, norm_type=norm)
+    m = build_fsn(c, O.make_params_fsn(c, seed=4))
+    with torch.no_grad():
+        out = m(_t(g["mag"]))
+    fb_out = m.get_stage("fb_out", (1, 3, 33, 22), DEV).cpu().numpy()
+    e_fb, err = O.rel_l2(fb_out[0], g["fb_out"]), O.rel_l2(out.cpu().numpy(), g["out"])
+    print(f"\n[fullsubnet.Model {norm}] fb_out {e_fb:.2e} cIRM {err:.3e}")
+    assert err < MASK_TOL
+
+
+@pytest.mark.parametrize("norm", ["offline_gaussian_norm", "cumulative_layer_norm"])
+@pytest.mark.parametrize("impl", ["tcgen05", "mma"])
+def test_plus_small_centred_norms_vs_oracle(built_lib, norm, impl):
+    """FullSubNet+ with the centred norms (the Laplace norms divide the real/imag branches by a near-zero running
+    mean and are ill-conditioned in the reference itself, SURVEY.md 7.2 -- covered on fullsubnet.Model above)."""
+    cfg = small_cfg(64)
+    cfg["norm_type"] = norm
+    params = O.make_params_plus(cfg, seed=6)
+    mag, real, imag = small_inputs(2, 33, 21, 5)
+    ref = O.fullsubnet_plus_forward(params, cfg, mag, real, imag)
+    m = build_plus(cfg, params, lstm_impl=impl)
+    with torch.no_grad():
+        out = m(_t(mag), _t(real), _t(imag))
+    err = O.rel_l2(out.cpu().numpy(), ref)
+    print(f"\n[FullSubNet+ {norm} {impl}] cIRM {err:.3e}")
+    assert err < MASK_TOL
