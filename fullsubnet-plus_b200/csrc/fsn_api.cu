@@ -388,7 +388,7 @@ static int ensure_ws(fsn_model* m, int B, int T) {
     const int F = c.num_freqs, Tp = T + c.look_ahead, Pp = (Tp + 3) & ~3;
     const int nbr = (c.model_kind == FSN_KIND_PLUS) ? 3 : 1;
     const size_t act = (size_t)nbr * B * F * Pp * 4;
-    const int rows = B * F, ntiles = (rows + 127) / 128;
+    const int rows = B * F, ntiles = ((rows + 127) / 128 + 1) / 2 * 2;      // whole CTA pairs (k_lstm_tc5p.cu)
     int e = 0;
     e |= m->fbin.ensure(act, true);
     e |= m->fbout.ensure(act, true);
@@ -468,7 +468,9 @@ static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s)
         { const char* ev = getenv("FSN_TC5_ELECT"); a.elect = ev ? atoi(ev) : 0; }
         { const char* ev = getenv("FSN_TC5_NSTAGE"); a.nstage_cap = ev ? atoi(ev) : 0; }
         { const char* ev = getenv("FSN_TC5_DEBUG"); a.debug = ev ? atoi(ev) : 0; }
-        int e = launch_lstm_tc5(a, s);
+        int pair = 1;
+        { const char* ev = getenv("FSN_TC5_PAIR"); if (ev) pair = atoi(ev); }
+        int e = pair ? launch_lstm_tc5_pair(a, s) : launch_lstm_tc5(a, s);
         if (e) return fail(FSN_ECUDA, "tcgen05 LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
     } else {
         LstmMmaLaunch a{};

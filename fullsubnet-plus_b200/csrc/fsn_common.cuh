@@ -194,6 +194,78 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                  : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): one tcgen05.mma drives both SMs of a 2-CTA cluster; each CTA holds half of B ---------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address valid in every CTA) inside CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank)); return r;
+}
+// Remote arrive.  Relaxed on purpose: a cluster-scope RELEASE costs ~1K cycles per arrive (measured: 26 ms vs 12 ms
+// kernel), and nothing but the barrier state has to be published -- the payload it guards was written by the async
+// proxy (bulk copy -> shared memory) or lives in tensor memory (ordered by tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <uint32_t NCOLS> __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t NCOLS> __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void umma2_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all prior cta_group::2 MMAs -> arrive on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+
+// One LSTM cell.  ai/af/ao = -log2(e) * (gate pre-activation), ag = -2 log2(e) * (g pre-activation): the scale and
+// the bias are folded into one FMA on the accumulator (biases are stored pre-scaled).
+// Accurate path: 5 ex2 + 3 rcp (i*tanh(g) and o*tanh(c) share one reciprocal each); fast path: 5 tanh.approx.
+template <bool FAST>
+__device__ __forceinline__ void lstm_cell(float ai, float af, float ag, float ao, float cprev, float& c, float& h) {
+    if (FAST) {
+        const float K = -0.34657359027997264f;                                // -0.5 / log2(e)
+        const float si = fmaf(0.5f, tanh_approx(ai * K), 0.5f), sf = fmaf(0.5f, tanh_approx(af * K), 0.5f);
+        c = fmaf(sf, cprev, si * tanh_approx(ag * K));
+        h = fmaf(0.5f, tanh_approx(ao * K), 0.5f) * tanh_approx(c);
+    } else {
+        const float ei = ex2f(ai), ef = ex2f(af);
+        const float eg = ex2f(fminf(fmaxf(ag, -43.f), 43.f));                  // tanh saturates: |g| <= 15
+        const float ig = (1.f - eg) * rcpf((1.f + ei) * (1.f + eg));          // sigmoid(i) * tanh(g)
+        c = fmaf(rcpf(1.f + ef), cprev, ig);
+        const float eo = ex2f(ao);
+        const float ec = ex2f(fminf(fmaxf(c * -2.8853900817779268f, -43.f), 43.f));
+        h = (1.f - ec) * rcpf((1.f + eo) * (1.f + ec));                       // sigmoid(o) * tanh(c)
+    }
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+                 : "memory");
+}
+
+
 // ---- legacy tensor path (mma.sync) used by the generic kernels ------------------------------
 __device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(

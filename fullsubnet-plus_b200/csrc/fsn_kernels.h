@@ -129,6 +129,7 @@ struct LstmTc5Launch {
 size_t lstm_tc5_cstate_bytes(int ntiles, int H);
 bool lstm_tc5_supported(int L, int H, int I, int O);
 int launch_lstm_tc5(const LstmTc5Launch& a, cudaStream_t s);
+int launch_lstm_tc5_pair(const LstmTc5Launch& a, cudaStream_t s);   // k_lstm_tc5p.cu: cta_group::2 version (2-CTA clusters)
 
 // ---- k_gemm_tc5.cu (TCN on tcgen05, time-major activations) ----------------------------------
 enum { EPI5_PRELU_STATS = 1, EPI5_GLN_RES = 2, EPI5_OUT = 3 };

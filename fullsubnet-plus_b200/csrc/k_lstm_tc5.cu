@@ -53,32 +53,6 @@ bool lstm_tc5_supported(int L, int H, int I, int O) { return L == 2 && H % 64 ==
 
 size_t lstm_tc5_cstate_bytes(int ntiles, int H) { return (size_t)ntiles * 2 * H * 128 * sizeof(float); }
 
-// One LSTM cell.  ai/af/ao = -log2(e) * (gate pre-activation), ag = -2 log2(e) * (g pre-activation): the scale and
-// the bias are folded into one FMA on the accumulator (biases are stored pre-scaled).
-// Accurate path: 5 ex2 + 3 rcp (i*tanh(g) and o*tanh(c) share one reciprocal each); fast path: 5 tanh.approx.
-template <bool FAST>
-__device__ __forceinline__ void lstm_cell(float ai, float af, float ag, float ao, float cprev, float& c, float& h) {
-    if (FAST) {
-        const float K = -0.34657359027997264f;                                // -0.5 / log2(e)
-        const float si = fmaf(0.5f, tanh_approx(ai * K), 0.5f), sf = fmaf(0.5f, tanh_approx(af * K), 0.5f);
-        c = fmaf(sf, cprev, si * tanh_approx(ag * K));
-        h = fmaf(0.5f, tanh_approx(ao * K), 0.5f) * tanh_approx(c);
-    } else {
-        const float ei = ex2f(ai), ef = ex2f(af);
-        const float eg = ex2f(fminf(fmaxf(ag, -43.f), 43.f));                  // tanh saturates: |g| <= 15
-        const float ig = (1.f - eg) * rcpf((1.f + ei) * (1.f + eg));          // sigmoid(i) * tanh(g)
-        c = fmaf(rcpf(1.f + ef), cprev, ig);
-        const float eo = ex2f(ao);
-        const float ec = ex2f(fminf(fmaxf(c * -2.8853900817779268f, -43.f), 43.f));
-        h = (1.f - ec) * rcpf((1.f + eo) * (1.f + ec));                       // sigmoid(o) * tanh(c)
-    }
-}
-
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
-                 : "memory");
-}
-
 template <bool FAST>
 __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch a, int nstage) {
     extern __shared__ uint8_t smem_raw[];
@@ -212,6 +186,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
             if (!a.elect || lane == 0) mbar_arrive(hready);
         }
         uint32_t accn = 0, ls = 0;
+        float4 cnext[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};   // t = 0: zero cell state
         float* cbase = a.cstate + (size_t)tile * 2 * H * 128;
         uint8_t* mypark = park + ((size_t)cg * NCH * 128 + r) * 16;
         const int grow = tile * 128 + r;
@@ -224,9 +199,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
                 float fc0 = 0.f, fc1 = 0.f;
                 for (int j = 0; j < NCH; ++j) {
                     float4* cp = reinterpret_cast<float4*>(cbase + ((size_t)((layer * NCH + j) * 4 + cg) * 2) * 128 * 4) + r;
-                    float4 c4[2];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) c4[i] = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[i * 128];
+                    const float4 c4[2] = {cnext[0], cnext[1]};     // prefetched during the previous chunk
                     const float4* bj = reinterpret_cast<const float4*>(a.bias + (size_t)(layer * NCH + j) * 128 + cg * 32);
                     mbar_wait(accfull, accn & 1);
                     ++accn;
@@ -238,6 +211,14 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) lstm_tc5_kernel(LstmTc5Launch 
                     tc5_fence_before();
                     if (a.elect) __syncwarp();
                     if (!a.elect || lane == 0) mbar_arrive(accempty);
+                    {   // cell state of the NEXT chunk in program order: (layer, j+1), else chunk 0 of the other layer (next step after layer 1)
+                        const int nj = (j + 1 < NCH) ? j + 1 : 0;
+                        const int nl = (j + 1 < NCH) ? layer : (layer ^ 1);
+                        const int nt = (j + 1 < NCH || layer == 0) ? t : t + 1;
+                        const float4* np = reinterpret_cast<const float4*>(cbase + ((size_t)((nl * NCH + nj) * 4 + cg) * 2) * 128 * 4) + r;
+                        if (nt == 0 || nt >= Tp) { cnext[0] = make_float4(0.f, 0.f, 0.f, 0.f); cnext[1] = cnext[0]; }
+                        else { cnext[0] = np[0]; cnext[1] = np[128]; }
+                    }
 
                     if (a.debug & 1) continue;                     // timing experiment: drain only, no cell update
                     const float L2E = 1.4426950408889634f;

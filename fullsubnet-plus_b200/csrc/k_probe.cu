@@ -237,6 +237,83 @@ static float run_issue(long long* dc) {
     return (float)cyc / (512.0f * 4.0f);
 }
 
+// ---- probe 5: CTA pair (cta_group::2).  D[256 x 128] = A[256 x 64] * B[128 x 64]^T: each CTA holds its own 128 rows of A and
+// 64 rows of B (CTA rank r: B rows [64 r, 64 r + 64)); the leader issues the MMAs for both SMs; commit multicasts to both.
+struct Probe5Args { const uint8_t* a_img; const uint8_t* b_img; const uint32_t* a_plain; float* d; long long* cycles; int mode; int reps; };
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe_pair_kernel(Probe5Args p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sa = smem;                 // 16 KB: my 128 rows of A
+    uint8_t* sb = smem + 16384;         // 8 KB: my 64 rows of B
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 8192);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t rank = cluster_ctarank();
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc_pair<512>(tslot);
+    tc5_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc5_fence_after();
+    const uint32_t tmem = *tslot;
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bars[0], 16384 + 8192);
+        bulk_g2s(sa, p.a_img + (size_t)rank * 16384, 16384, &bars[0]);
+        bulk_g2s(sb, p.b_img + (size_t)rank * 8192, 8192, &bars[0]);
+    }
+    {   // A operand into TMEM columns [256, 288): my row
+        const uint32_t* src = p.a_plain + ((size_t)rank * 128 + tid) * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = src[c * 8 + i];
+            tmem_st8(tl + 256 + c * 8, v);
+        }
+        tmem_wait_st();
+    }
+    mbar_wait(&bars[0], 0);
+    tc5_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // both CTAs' operands are in place
+    tc5_fence_after();
+    if (rank == 0 && warp == 0) {
+        const uint32_t idesc = umma_idesc_f16(256, 128);
+        const uint64_t adesc = umma_desc_sw128(smem_u32(sa)), bdesc = umma_desc_sw128(smem_u32(sb));
+        long long t0 = clock64();
+        for (int r = 0; r < p.reps; ++r) {
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    if (p.mode == 0) umma2_ss(tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (r | kk) != 0);
+                    else umma2_ts(tmem, tmem + 256 + kk * 8, bdesc + 2 * kk, idesc, (r | kk) != 0);
+                }
+            }
+            __syncwarp();
+        }
+        if (elect_one()) umma2_commit_mc(&bars[1], 3);
+        __syncwarp();
+        mbar_wait(&bars[1], 0);
+        if (tid == 0) p.cycles[0] = clock64() - t0;
+    }
+    mbar_wait(&bars[1], 0);
+    tc5_fence_after();
+    for (int c = 0; c < 8; ++c) {
+        uint32_t v[16];
+        tmem_ld16(tl + c * 16, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) p.d[((size_t)rank * 128 + tid) * 128 + c * 16 + i] = __uint_as_float(v[i]);
+    }
+    tc5_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc5_fence_after();
+    if (warp == 0) tmem_dealloc_pair<512>(tmem);
+}
+
 static uint16_t h_bits(float f) { __half h = __float2half_rn(f); uint16_t b; std::memcpy(&b, &h, 2); return b; }
 static float h_val(uint16_t b) { __half h; std::memcpy(&h, &b, 2); return __half2float(h); }
 
@@ -328,6 +405,56 @@ int run_probe_tcgen05(float* report, int n) {
             report[idx++] = run_issue<7, 256>(dc);  report[idx++] = run_issue<15, 256>(dc);
         }
         rc = idx;
+    }
+    if (rc > 0 && rc + 4 <= n) {
+        // CTA pair: A[256 x 64], B[128 x 64] -> errors of the SS and TS forms, cycles per cta_group::2 MMA (M=256, N=128)
+        std::vector<uint16_t> A2(256 * 64), B2(128 * 64);
+        std::vector<uint8_t> a2img(2 * 16384), b2img(2 * 8192);
+        std::vector<uint32_t> a2plain(256 * 32);
+        std::vector<float> D2(256 * 128);
+        for (auto& v : A2) v = h_bits(rnd());
+        for (auto& v : B2) v = h_bits(rnd());
+        for (int r = 0; r < 256; ++r)
+            for (int k = 0; k < 64; ++k) {
+                std::memcpy(&a2img[(size_t)(r / 128) * 16384 + sw128_offset(r % 128, k)], &A2[r * 64 + k], 2);
+                if (k % 2 == 0) a2plain[r * 32 + k / 2] = (uint32_t)A2[r * 64 + k] | ((uint32_t)A2[r * 64 + k + 1] << 16);
+            }
+        for (int r = 0; r < 128; ++r)
+            for (int k = 0; k < 64; ++k) std::memcpy(&b2img[(size_t)(r / 64) * 8192 + sw128_offset(r % 64, k)], &B2[r * 64 + k], 2);
+        uint8_t *da2 = nullptr, *db2 = nullptr; uint32_t* dp2 = nullptr; float* dd2 = nullptr;
+        cudaMalloc(&da2, a2img.size()); cudaMalloc(&db2, b2img.size()); cudaMalloc(&dp2, a2plain.size() * 4); cudaMalloc(&dd2, D2.size() * 4);
+        cudaMemcpy(da2, a2img.data(), a2img.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(db2, b2img.data(), b2img.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(dp2, a2plain.data(), a2plain.size() * 4, cudaMemcpyHostToDevice);
+        const size_t smem5 = 16384 + 8192 + 64 + 1024;
+        cudaFuncSetAttribute(probe_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
+        Probe5Args q5{da2, db2, dp2, dd2, dc, 0, 1};
+        bool ok5 = true;
+        for (int mode = 0; mode < 2 && ok5; ++mode) {
+            q5.mode = mode; q5.reps = 1;
+            cudaMemset(dd2, 0, D2.size() * 4);
+            probe_pair_kernel<<<2, 128, smem5>>>(q5);
+            if (cudaDeviceSynchronize() != cudaSuccess) { ok5 = false; break; }
+            cudaMemcpy(D2.data(), dd2, D2.size() * 4, cudaMemcpyDeviceToHost);
+            double maxerr = 0;
+            for (int r = 0; r < 256; ++r)
+                for (int c = 0; c < 128; ++c) {
+                    double ref = 0;
+                    for (int k = 0; k < 64; ++k) ref += (double)h_val(A2[r * 64 + k]) * (double)h_val(B2[c * 64 + k]);
+                    maxerr = std::fmax(maxerr, std::fabs(ref - (double)D2[r * 128 + c]));
+                }
+            report[rc++] = (float)maxerr;
+        }
+        for (int mode = 0; mode < 2 && ok5; ++mode) {
+            q5.mode = mode; q5.reps = 512;
+            probe_pair_kernel<<<2, 128, smem5>>>(q5);
+            if (cudaDeviceSynchronize() != cudaSuccess) { ok5 = false; break; }
+            long long cyc = 0;
+            cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost);
+            report[rc++] = (float)cyc / (512.0f * 4.0f);
+        }
+        cudaFree(da2); cudaFree(db2); cudaFree(dp2); cudaFree(dd2);
+        if (!ok5) rc = -2000 - (int)cudaGetLastError();
     }
 done:
     cudaFree(da); cudaFree(db); cudaFree(dp); cudaFree(dd); cudaFree(dc);

@@ -232,3 +232,48 @@ def test_plus_small_centred_norms_vs_oracle(built_lib, norm, impl):
     err = O.rel_l2(out.cpu().numpy(), ref)
     print(f"\n[FullSubNet+ {norm} {impl}] cIRM {err:.3e}")
     assert err < MASK_TOL
+
+
+def test_config4_causal_fullsubnet_long_clip(built_lib):
+    """BASELINE config #4 (streaming/causal): fullsubnet.Model + cumulative_laplace_norm, look_ahead=2.
+    (a) parity with the oracle on a 6 s clip; (b) causality on a 30 s clip (T=1876): changing the input from frame t0 on
+    must leave every output frame before t0 - look_ahead untouched -- the property a frame-by-frame deployment relies on."""
+    cfg = O.default_fsn_config()
+    cfg["norm_type"] = "cumulative_laplace_norm"
+    params = O.make_params_fsn(cfg, seed=21)
+    m = build_fsn(cfg, params)
+    mag6 = np.abs(O.stft(O.synth_clips(1, num_samples=96000, seed0=77)))[:, None].astype(np.float32)       # [1,1,257,376]
+    ref = O.fullsubnet_forward(params, cfg, mag6)
+    with torch.no_grad():
+        out = m(_t(mag6))
+    err = O.rel_l2(out.cpu().numpy(), ref)
+    print(f"\n[config4 6 s] cIRM rel-L2 {err:.3e}")
+    assert err < MASK_TOL
+    mag30 = np.abs(O.stft(O.synth_clips(1, num_samples=480000, seed0=78)))[:, None].astype(np.float32)     # T = 1876
+    assert mag30.shape[-1] == 1876
+    t0 = 1200
+    alt = mag30.copy()
+    alt[..., t0:] *= 1.7
+    with torch.no_grad():
+        a, b = m(_t(mag30)), m(_t(alt))
+    assert torch.isfinite(a).all()
+    assert torch.equal(a[..., : t0 - 2], b[..., : t0 - 2])
+    assert not torch.equal(a[..., t0:], b[..., t0:])
+
+
+def test_config5_large_model(built_lib):
+    """BASELINE config #5 geometry: num_freqs=513 (n_fft=1024, hop 512 -> T=94 for 3 s), sub-band hidden 512, 3-layer
+    LSTMs (additive num_layers knob; oracle = SequenceModel(num_layers=3) semantics, pinned by tests/golden/lstm3_small)."""
+    cfg = O.default_plus_config()
+    cfg.update(num_freqs=513, sb_model_hidden_size=512, fb_model_hidden_size=512)
+    params = O.make_params_plus(cfg, seed=31, num_layers=3)
+    X = O.stft(O.synth_clips(1, seed0=91), n_fft=1024, hop=512, win=1024)
+    mag, real, imag = (np.abs(X)[:, None].astype(np.float32), X.real[:, None].astype(np.float32), X.imag[:, None].astype(np.float32))
+    assert mag.shape == (1, 1, 513, 94)
+    ref = O.fullsubnet_plus_forward(params, cfg, mag, real, imag, num_layers=3)
+    m = build_plus(cfg, params, num_layers=3)
+    with torch.no_grad():
+        out = m(_t(mag), _t(real), _t(imag))
+    err = O.rel_l2(out.cpu().numpy(), ref)
+    print(f"\n[config5 large, {m.last_lstm_impl()}] cIRM rel-L2 {err:.3e}")
+    assert out.shape == (1, 2, 513, 94) and err < MASK_TOL
