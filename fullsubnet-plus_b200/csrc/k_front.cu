@@ -416,38 +416,54 @@ void launch_sb_stats(const SbPackLaunch& a, cudaStream_t s) {
     sb_stats_kernel<<<a.B, 256, sizeof(float) * 2 * a.F * (1 + a.nfb), s>>>(a);
 }
 
-__global__ void __launch_bounds__(128) sb_pack_kernel(SbPackLaunch a) {
-    const int f = blockIdx.x, b = blockIdx.y, F = a.F, Tp = a.Tp;
-    const int row = b * F + f, tile = row >> 7, r = row & 127;
+// One CTA = (sample, 32 consecutive bins, 32 frames).  The window source rows [f0 - Ns, f0 + 31 + Ns] (reflected) and the
+// full-band rows of the 32 bins are staged once in shared memory; work item = (bin, frame, 16-byte chunk of the 128-byte
+// image row), so 8 consecutive lanes write one full 128-byte line of the SWIZZLE_128B image.
+constexpr int SBP_F = 32, SBP_T = 32;
+__global__ void __launch_bounds__(256) sb_pack_kernel(SbPackLaunch a) {
+    extern __shared__ float sm[];
+    const int F = a.F, Tp = a.Tp, b = blockIdx.z, f0 = blockIdx.y * SBP_F, t0 = blockIdx.x * SBP_T;
+    const int nw = 2 * a.Ns + 1, nf = 2 * a.Nf + 1, I = nw + a.nfb * nf;
+    const int wrows = SBP_F + 2 * a.Ns, frows = SBP_F + 2 * a.Nf;
+    float* wsm = sm;                                   // [wrows][SBP_T + 1]
+    float* fsm = sm + wrows * (SBP_T + 1);             // [nfb][frows][SBP_T + 1]
     const bool gauss = (a.norm_type == FSN_NORM_OFFLINE_GAUSSIAN);
     const float inv = gauss ? 1.0f / (a.sigma[b] + 1e-5f) : 1.0f / (a.mu[b] + 1e-5f);
-    const float sub = gauss ? a.mu[b] : 0.f;                  // (v - mu) / (sigma + 1e-5)  (base_model.py:260-275)
-    const int nw = 2 * a.Ns + 1, nf = 2 * a.Nf + 1;
-    const int I = nw + a.nfb * nf;
-    for (int t = threadIdx.x; t < Tp; t += blockDim.x) {
-        auto val = [&](int k) -> float {          // k-th channel of the concatenated sub-band input
-            float v = 0.f;
-            if (k < nw) v = a.win[((size_t)b * F + reflect_idx(f + k - a.Ns, F)) * a.Pw + t];
-            else if (k < I) {
-                const int kk = k - nw, q = kk / nf, j = kk % nf;
-                const float* src = (q == 0) ? a.fb[0] : (q == 1) ? a.fb[1] : a.fb[2];
-                v = src[((size_t)b * F + reflect_idx(f + j - a.Nf, F)) * a.P + t];
-            }
-            return (k < I) ? fminf(fmaxf((v - sub) * inv, -65504.f), 65504.f) : 0.f;
-        };
-        char* img = reinterpret_cast<char*>(a.ximg) + ((size_t)tile * Tp + t) * (128 * 128);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint4 u;
-            u.x = pack_half2(val(c * 8 + 0), val(c * 8 + 1));
-            u.y = pack_half2(val(c * 8 + 2), val(c * 8 + 3));
-            u.z = pack_half2(val(c * 8 + 4), val(c * 8 + 5));
-            u.w = pack_half2(val(c * 8 + 6), val(c * 8 + 7));
-            *reinterpret_cast<uint4*>(img + sw128_offset(r, c * 8)) = u;
+    const float sub = gauss ? a.mu[b] : 0.f;
+    for (int e = threadIdx.x; e < wrows * SBP_T; e += blockDim.x) {
+        const int rr = e / SBP_T, tt = e % SBP_T, t = t0 + tt;
+        const int f = reflect_idx(min(f0 + rr - a.Ns, F - 1 + a.Ns), F);
+        wsm[rr * (SBP_T + 1) + tt] = (t < Tp) ? a.win[((size_t)b * F + f) * a.Pw + t] : 0.f;
+    }
+    for (int q = 0; q < a.nfb; ++q) {
+        const float* src = (q == 0) ? a.fb[0] : (q == 1) ? a.fb[1] : a.fb[2];
+        for (int e = threadIdx.x; e < frows * SBP_T; e += blockDim.x) {
+            const int rr = e / SBP_T, tt = e % SBP_T, t = t0 + tt;
+            const int f = reflect_idx(min(f0 + rr - a.Nf, F - 1 + a.Nf), F);
+            fsm[(q * frows + rr) * (SBP_T + 1) + tt] = (t < Tp) ? src[((size_t)b * F + f) * a.P + t] : 0.f;
         }
     }
+    __syncthreads();
+    const int c = threadIdx.x & 7, fr = threadIdx.x >> 3;          // chunk, bin inside the tile
+    const int f = f0 + fr;
+    if (f >= F) return;
+    const int row = b * F + f, tile = row >> 7, r = row & 127;
+    auto val = [&](int k, int tt) -> float {
+        float v = 0.f;
+        if (k < nw) v = wsm[(fr + k) * (SBP_T + 1) + tt];
+        else if (k < I) { const int kk = k - nw, q = kk / nf, j = kk % nf; v = fsm[(q * frows + fr + j) * (SBP_T + 1) + tt]; }
+        return (k < I) ? fminf(fmaxf((v - sub) * inv, -65504.f), 65504.f) : 0.f;
+    };
+    for (int tt = 0; tt < SBP_T && t0 + tt < Tp; ++tt) {
+        uint4 u;
+        u.x = pack_half2(val(c * 8 + 0, tt), val(c * 8 + 1, tt));
+        u.y = pack_half2(val(c * 8 + 2, tt), val(c * 8 + 3, tt));
+        u.z = pack_half2(val(c * 8 + 4, tt), val(c * 8 + 5, tt));
+        u.w = pack_half2(val(c * 8 + 6, tt), val(c * 8 + 7, tt));
+        char* img = reinterpret_cast<char*>(a.ximg) + ((size_t)tile * Tp + t0 + tt) * (128 * 128);
+        *reinterpret_cast<uint4*>(img + sw128_offset(r, c * 8)) = u;
+    }
 }
-
 
 // Cumulative norms of the 4-D sub-band input (base_model.py:227-258 / :277-316 with dim 1 = F folded into the batch): every
 // sequence (b, f) is normalised by the running mean (and std) over its I channels.  One warp per sequence, lanes over
@@ -507,7 +523,11 @@ void launch_sb_pack(const SbPackLaunch& a, cudaStream_t s) {
     if (a.norm_type == FSN_NORM_CUMULATIVE_LAPLACE || a.norm_type == FSN_NORM_CUMULATIVE_LAYER)
         sb_pack_cum_kernel<<<(a.B * a.F + 3) / 4, 128, 0, s>>>(a);
     else
-        sb_pack_kernel<<<dim3(a.F, a.B), 128, 0, s>>>(a);
+    {
+        const size_t smem = sizeof(float) * (SBP_T + 1) * ((SBP_F + 2 * a.Ns) + a.nfb * (SBP_F + 2 * a.Nf));
+        cudaFuncSetAttribute(sb_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sb_pack_kernel<<<dim3((a.Tp + SBP_T - 1) / SBP_T, (a.F + SBP_F - 1) / SBP_F, a.B), 256, smem, s>>>(a);
+    }
 }
 
 

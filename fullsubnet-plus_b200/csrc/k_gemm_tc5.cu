@@ -22,7 +22,8 @@
 
 namespace fsn {
 
-constexpr int G5_THREADS = 192;      // warp 0 TMA producer, warp 1 MMA issuer + TMEM alloc, warps 2-5 epilogue
+constexpr int G5_EPI_WARPS = 8;       // two warps per TMEM lane quarter, each takes half of the 16-column chunks of a tile
+constexpr int G5_THREADS = (2 + G5_EPI_WARPS) * 32;   // warp 0 TMA producer, warp 1 MMA issuer + TMEM alloc, warps 2-9 epilogue
 constexpr int G5_A_BYTES = 128 * 128;
 
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
@@ -60,7 +61,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     if (tid == 0) {
         for (int i = 0; i < nstage; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&accfull[i], 1); mbar_init(&accempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&accfull[i], 1); mbar_init(&accempty[i], G5_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -116,8 +117,9 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else {
-        const int q = warp & 3, r = q * 32 + lane;
+        const int q = warp & 3, r = q * 32 + lane, half = (warp - 2) >> 2;
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+        const int nchunk = NT / 16, cbeg = half ? (nchunk + 1) / 2 : 0, cend = half ? nchunk : (nchunk + 1) / 2;
         uint32_t use[2] = {0, 0}, it = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
             const int br = tile / tiles_per_branch, rem = tile % tiles_per_branch;
@@ -143,7 +145,13 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             mbar_wait(&accfull[buf], use[buf] & 1);
             ++use[buf];
             tc5_fence_after();
-            for (int c = 0; c < NT / 16; ++c) {
+            float4 xpre[4];
+            if (EPI == EPI5_GLN_RES && valid && cbeg < cend) {
+                const float4* xo = reinterpret_cast<const float4*>(a.Xold + grow * a.ldY + n0 + cbeg * 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xpre[i] = xo[i];
+            }
+            for (int c = cbeg; c < cend; ++c) {
                 uint32_t v[16];
                 tmem_ld16(tl + buf * 256 + c * 16, v);
                 tmem_wait_ld();
@@ -151,9 +159,15 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 float y[16];
                 if (EPI == EPI5_PRELU_STATS) {
                     float ls = 0.f, lq = 0.f;
+                    float bvec[16];
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n) + i4);
+                        bvec[4 * i4] = b4.x; bvec[4 * i4 + 1] = b4.y; bvec[4 * i4 + 2] = b4.z; bvec[4 * i4 + 3] = b4.w;
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        float t = __uint_as_float(v[i]) + __ldg(bias + n + i);
+                        float t = __uint_as_float(v[i]) + bvec[i];
                         t = (t >= 0.f) ? t : slope * t;
                         ls += t; lq = fmaf(t, t, lq);
                         y[i] = round_tf32(t);
@@ -166,18 +180,25 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     }
                 } else if (EPI == EPI5_GLN_RES) {
                     if (valid) {
-                        const float4* xo = reinterpret_cast<const float4*>(a.Xold + grow * a.ldY + n);
+                        float4 xcur[4] = {xpre[0], xpre[1], xpre[2], xpre[3]};
+                        if (c + 1 < cend) {                     // residual of the next chunk: in flight during this chunk's math
+                            const float4* xn = reinterpret_cast<const float4*>(a.Xold + grow * a.ldY + n + 16);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) xpre[i] = xn[i];
+                        }
                         float4* dst = reinterpret_cast<float4*>(a.Y + grow * a.ldY + n);
                         float4* dr = a.Xrelu ? reinterpret_cast<float4*>(a.Xrelu + grow * a.ldY + n) : nullptr;
 #pragma unroll
                         for (int i4 = 0; i4 < 4; ++i4) {
-                            const float4 xv = xo[i4];
+                            const float4 xv = xcur[i4];
                             const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+                            const float4 s14 = __ldg(reinterpret_cast<const float4*>(s1 + n) + i4), b4 = __ldg(reinterpret_cast<const float4*>(bias + n) + i4);
+                            const float s1v[4] = {s14.x, s14.y, s14.z, s14.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
                             float o[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const int i = i4 * 4 + e;
-                                const float val = fmaf(rstd, __uint_as_float(v[i]), fmaf(-mean * rstd, __ldg(s1 + n + i), __ldg(bias + n + i)));
+                                const float val = fmaf(rstd, __uint_as_float(v[i]), fmaf(-mean * rstd, s1v[e], bv[e]));
                                 o[e] = xa[e] + val;
                             }
                             dst[i4] = make_float4(o[0], o[1], o[2], o[3]);
@@ -267,30 +288,55 @@ int launch_gemm_tc5(const void* mapA, const void* mapB, GemmTc5Launch a, int num
 }
 
 // gLN1 apply -> depth-wise conv (k=3, dilation d, zero padding in the normalised domain) -> PReLU2 + gLN2 statistics,
-// on the time-major [rows, C] layout (coalesced over channels).  reference: causal_conv.py:100-106.
+// on the time-major [rows, C] layout.  reference: causal_conv.py:100-106.  One CTA = one sample x 64 channels x all
+// frames: the slab (T' x 64 floats, 48 KB for T' = 190) is staged once in shared memory with the gLN already applied,
+// so every input element is read exactly once from HBM/L2 and the three taps come from shared memory.
+constexpr int DW_CH = 64;
 __global__ void __launch_bounds__(256) dwconv_tm_kernel(DwTmLaunch a) {
+    extern __shared__ float slab[];                       // [Tp][DW_CH]
     __shared__ double red[16];
-    const int z = blockIdx.y, g = z / a.B;
+    const int z = blockIdx.y, g = z / a.B, c0 = blockIdx.x * DW_CH;
     const int C = a.C, Tp = a.Tp, d = a.dilation;
     const double cnt = (double)C * (double)Tp;
     const double mu = a.stats_in[2 * z] / cnt;
     const double var = a.stats_in[2 * z + 1] / cnt - mu * mu;
     const float mean = (float)mu, rstd = (float)(1.0 / sqrt((var > 0 ? var : 0) + 1e-8));
     const float slope = __ldg(a.prelu[g]);
-    const int t0 = blockIdx.x * a.tchunk, t1 = min(t0 + a.tchunk, Tp);
-    const size_t base = (size_t)z * Tp * C;
+    const size_t base = (size_t)z * Tp * C + c0;
+    const int cq = threadIdx.x & 15, tr = threadIdx.x >> 4;           // 16 float4 columns x 16 frame rows per pass
+    float4 ga, be, w0, w1, w2, bb;
+    {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma[g] + c0) + cq);
+        const float4 bt = __ldg(reinterpret_cast<const float4*>(a.beta[g] + c0) + cq);
+        ga = make_float4(gm.x * rstd, gm.y * rstd, gm.z * rstd, gm.w * rstd);
+        be = make_float4(bt.x - mean * ga.x, bt.y - mean * ga.y, bt.z - mean * ga.z, bt.w - mean * ga.w);
+        const float* wp = a.w[g] + (size_t)(c0 + cq * 4) * 3;
+        w0 = make_float4(__ldg(wp + 0), __ldg(wp + 3), __ldg(wp + 6), __ldg(wp + 9));
+        w1 = make_float4(__ldg(wp + 1), __ldg(wp + 4), __ldg(wp + 7), __ldg(wp + 10));
+        w2 = make_float4(__ldg(wp + 2), __ldg(wp + 5), __ldg(wp + 8), __ldg(wp + 11));
+        bb = __ldg(reinterpret_cast<const float4*>(a.b[g] + c0) + cq);
+    }
+    for (int t = tr; t < Tp; t += 16) {
+        const float4 v = *reinterpret_cast<const float4*>(a.X + base + (size_t)t * C + cq * 4);
+        reinterpret_cast<float4*>(slab + t * DW_CH)[cq] =
+            make_float4(fmaf(v.x, ga.x, be.x), fmaf(v.y, ga.y, be.y), fmaf(v.z, ga.z, be.z), fmaf(v.w, ga.w, be.w));
+    }
+    __syncthreads();
     float ls = 0.f, lq = 0.f;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float ga = __ldg(a.gamma[g] + c) * rstd, be = __ldg(a.beta[g] + c) - mean * rstd * __ldg(a.gamma[g] + c);
-        const float w0 = __ldg(a.w[g] + c * 3), w1 = __ldg(a.w[g] + c * 3 + 1), w2 = __ldg(a.w[g] + c * 3 + 2), bb = __ldg(a.b[g] + c);
-        for (int t = t0; t < t1; ++t) {
-            float acc = fmaf(w1, fmaf(a.X[base + (size_t)t * C + c], ga, be), bb);
-            if (t - d >= 0) acc = fmaf(w0, fmaf(a.X[base + (size_t)(t - d) * C + c], ga, be), acc);
-            if (t + d < Tp) acc = fmaf(w2, fmaf(a.X[base + (size_t)(t + d) * C + c], ga, be), acc);
-            acc = (acc >= 0.f) ? acc : slope * acc;
-            ls += acc; lq = fmaf(acc, acc, lq);
-            a.Y[base + (size_t)t * C + c] = round_tf32(acc);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = tr; t < Tp; t += 16) {
+        const float4 m = reinterpret_cast<const float4*>(slab + t * DW_CH)[cq];
+        const float4 l = (t - d >= 0) ? reinterpret_cast<const float4*>(slab + (t - d) * DW_CH)[cq] : zero;
+        const float4 r = (t + d < Tp) ? reinterpret_cast<const float4*>(slab + (t + d) * DW_CH)[cq] : zero;
+        float o[4] = {fmaf(w0.x, l.x, fmaf(w1.x, m.x, fmaf(w2.x, r.x, bb.x))), fmaf(w0.y, l.y, fmaf(w1.y, m.y, fmaf(w2.y, r.y, bb.y))),
+                      fmaf(w0.z, l.z, fmaf(w1.z, m.z, fmaf(w2.z, r.z, bb.z))), fmaf(w0.w, l.w, fmaf(w1.w, m.w, fmaf(w2.w, r.w, bb.w)))};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o[i] = (o[i] >= 0.f) ? o[i] : slope * o[i];
+            ls += o[i]; lq = fmaf(o[i], o[i], lq);
+            o[i] = round_tf32(o[i]);
         }
+        *reinterpret_cast<float4*>(a.Y + base + (size_t)t * C + cq * 4) = make_float4(o[0], o[1], o[2], o[3]);
     }
     double s1 = warp_sum_d((double)ls), s2 = warp_sum_d((double)lq);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -305,7 +351,9 @@ __global__ void __launch_bounds__(256) dwconv_tm_kernel(DwTmLaunch a) {
 }
 
 void launch_dwconv_tm(const DwTmLaunch& a, cudaStream_t s) {
-    dwconv_tm_kernel<<<dim3((a.Tp + a.tchunk - 1) / a.tchunk, a.Z), 256, 0, s>>>(a);
+    const size_t smem = (size_t)a.Tp * DW_CH * sizeof(float);
+    cudaFuncSetAttribute(dwconv_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dwconv_tm_kernel<<<dim3(a.C / DW_CH, a.Z), 256, smem, s>>>(a);
 }
 
 }  // namespace fsn
