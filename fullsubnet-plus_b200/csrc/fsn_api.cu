@@ -71,6 +71,11 @@ struct fsn_model {
     alignas(64) unsigned char mapX0[128], mapXa[128], mapXb[128], mapXr[128], mapY2[128];
     int64_t launches = 0;
     int last_impl = 0;
+    // async host pipeline: two staging slots, copy-in / copy-out streams, per-slot events
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_h2d[2] = {}, ev_fwd[2] = {}, ev_d2h[2] = {};
+    DevBuf a_in[2][3], a_out[2];
+    int64_t nasync = 0;
     static const int NEV = 32;
     cudaEvent_t ev0[NEV] = {}, ev1[NEV] = {};
     int64_t nfwd = 0;                                 // forwards whose LSTM events were recorded
@@ -303,6 +308,8 @@ extern "C" void fsn_model_destroy(fsn_model* m) {
                      &m->mu, &m->ximg, &m->cstate, &m->magpad, &m->fbx, &m->hseq, &m->stage_in[0], &m->stage_in[1], &m->stage_in[2],
                      &m->stage_out, &m->tW1, &m->tW2, &m->tWfc, &m->tS1, &m->tS2b, &m->tBfc, &m->x0, &m->xr, &m->xn, &m->sigma};
     for (auto* b : all) b->release();
+    if (m->s_in) { cudaStreamDestroy(m->s_in); cudaStreamDestroy(m->s_out); for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_h2d[i]); cudaEventDestroy(m->ev_fwd[i]); cudaEventDestroy(m->ev_d2h[i]); } }
+    for (int i = 0; i < 2; ++i) { m->a_out[i].release(); for (int j = 0; j < 3; ++j) m->a_in[i][j].release(); }
     for (int i = 0; i < fsn_model::NEV; ++i) { if (m->ev0[i]) cudaEventDestroy(m->ev0[i]); if (m->ev1[i]) cudaEventDestroy(m->ev1[i]); }
     for (int i = 0; i < 4; ++i) { m->sb_frag[i].release(); m->sb_bias[i].release(); m->fb_frag[i].release(); m->fb_bias[i].release(); }
     delete m;
@@ -720,6 +727,58 @@ extern "C" int fsn_model_forward_host(fsn_model* m, const float* h_mag, const fl
     if (rc) return rc;
     CK(cudaMemcpyAsync(h_out, m->stage_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return FSN_OK;
+}
+
+extern "C" int fsn_model_forward_host_async(fsn_model* m, const float* h_mag, const float* h_real, const float* h_imag, int32_t B, int32_t T,
+                                            float* h_out, void* stream) {
+    if (!m || !h_mag || !h_out) return fail(FSN_EINVAL, "null argument");
+    const fsn_config& c = m->cfg;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!m->s_in) {
+        CK(cudaStreamCreateWithFlags(&m->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&m->ev_fwd[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&m->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    const int slot = (int)(m->nasync & 1);
+    const bool reuse = m->nasync >= 2;
+    const size_t in_bytes = (size_t)B * c.num_freqs * T * 4, out_bytes = (size_t)B * c.output_size * c.num_freqs * T * 4;
+    const float* hin[3] = {h_mag, h_real, h_imag};
+    const int nin = (c.model_kind == FSN_KIND_PLUS) ? 3 : 1;
+    if (reuse) CK(cudaStreamWaitEvent(m->s_in, m->ev_fwd[slot], 0));          // the forward that read this input slot is done
+    for (int i = 0; i < nin; ++i) {
+        if (!hin[i]) return fail(FSN_EINVAL, "missing input %d", i);
+        if (m->a_in[slot][i].bytes < in_bytes) {
+            CK(cudaDeviceSynchronize());                                       // (re)allocation only on the first calls / size changes
+            if (m->a_in[slot][i].ensure(in_bytes, false)) return fail(FSN_ECUDA, "staging allocation failed");
+        }
+        CK(cudaMemcpyAsync(m->a_in[slot][i].p, hin[i], in_bytes, cudaMemcpyHostToDevice, m->s_in));
+    }
+    CK(cudaEventRecord(m->ev_h2d[slot], m->s_in));
+    if (m->a_out[slot].bytes < out_bytes) {
+        CK(cudaDeviceSynchronize());
+        if (m->a_out[slot].ensure(out_bytes, false)) return fail(FSN_ECUDA, "staging allocation failed");
+    }
+    CK(cudaStreamWaitEvent(s, m->ev_h2d[slot], 0));
+    if (reuse) CK(cudaStreamWaitEvent(s, m->ev_d2h[slot], 0));                // the copy-out that read this output slot is done
+    int rc = fsn_model_forward(m, static_cast<const float*>(m->a_in[slot][0].p), static_cast<const float*>(m->a_in[slot][1].p),
+                               static_cast<const float*>(m->a_in[slot][2].p), B, T, static_cast<float*>(m->a_out[slot].p), stream);
+    if (rc) return rc;
+    CK(cudaEventRecord(m->ev_fwd[slot], s));
+    CK(cudaStreamWaitEvent(m->s_out, m->ev_fwd[slot], 0));
+    CK(cudaMemcpyAsync(h_out, m->a_out[slot].p, out_bytes, cudaMemcpyDeviceToHost, m->s_out));
+    CK(cudaEventRecord(m->ev_d2h[slot], m->s_out));
+    m->nasync++;
+    return FSN_OK;
+}
+
+extern "C" int fsn_model_sync_host(fsn_model* m) {
+    if (!m) return fail(FSN_EINVAL, "null model");
+    if (m->s_in) { CK(cudaStreamSynchronize(m->s_in)); CK(cudaStreamSynchronize(m->s_out)); }
     return FSN_OK;
 }
 

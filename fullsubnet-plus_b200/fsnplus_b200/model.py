@@ -176,9 +176,11 @@ class _B200Model(nn.Module):
             _lib.check(lib.fsn_model_forward(self._handle, ptr(ins[0]), ptr(ins[1]), ptr(ins[2]), B, T, ptr(out), stream))
         return out
 
-    def forward_host(self, mag, real=None, imag=None, out=None, device="cuda:0"):
+    def forward_host(self, mag, real=None, imag=None, out=None, device="cuda:0", pipelined=False):
         """Same forward through the HOST-buffer entry point of the C ABI (H2D + forward + D2H in one call).
-        ``mag/real/imag``: CPU float32 tensors [B, 1, F, T] (pinned for best bandwidth); returns a CPU tensor."""
+        ``mag/real/imag``: CPU float32 tensors [B, 1, F, T] (pinned for best bandwidth); returns a CPU tensor.
+        ``pipelined=True`` uses the double-buffered async entry point (copies overlap the previous/next forward);
+        the returned tensor is valid after ``sync_host()``."""
         B, _, F, T = mag.shape
         dev = torch.device(device)
         with torch.cuda.device(dev):
@@ -187,8 +189,14 @@ class _B200Model(nn.Module):
                 out = torch.empty((B, self._cfg.output_size, F, T), dtype=torch.float32).pin_memory()
             ptr = lambda x: C.c_void_p(x.data_ptr()) if x is not None else C.c_void_p()
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            _lib.check(lib.fsn_model_forward_host(self._handle, ptr(mag), ptr(real), ptr(imag), B, T, ptr(out), stream))
+            fn = lib.fsn_model_forward_host_async if pipelined else lib.fsn_model_forward_host
+            _lib.check(fn(self._handle, ptr(mag), ptr(real), ptr(imag), B, T, ptr(out), stream))
         return out
+
+    def sync_host(self):
+        """Wait for every forward_host(..., pipelined=True) issued so far (their outputs are then valid)."""
+        if self._handle is not None:
+            _lib.check(_lib.load_library().fsn_model_sync_host(self._handle))
 
     # -- introspection used by tests / bench -----------------------------------------------------
     def last_lstm_impl(self):

@@ -99,6 +99,14 @@ int fsn_model_forward(fsn_model* m, const float* d_mag, const float* d_real, con
 int fsn_model_forward_host(fsn_model* m, const float* h_mag, const float* h_real, const float* h_imag, int32_t B, int32_t T,
                            float* h_out, void* stream);
 
+/* Pipelined variant for streams of batches: returns as soon as the work is enqueued.  Inputs are copied on an internal
+ * copy stream into one of two device staging slots, the forward runs on `stream`, the mask is copied back on a second
+ * copy stream -- so the H2D of batch i+1 and the D2H of batch i-1 overlap the forward of batch i.  The host buffers must be
+ * pinned and must stay untouched (h_out unread) until fsn_model_sync_host() returns. */
+int fsn_model_forward_host_async(fsn_model* m, const float* h_mag, const float* h_real, const float* h_imag, int32_t B, int32_t T,
+                                 float* h_out, void* stream);
+int fsn_model_sync_host(fsn_model* m);
+
 /* Test hooks: copy an intermediate of the LAST forward to a device buffer.
  *   "fb_in"  [nbranch, B, F, T+look_ahead]  post-norm (and post-attention) full-band inputs
  *   "fb_out" [nbranch, B, F, T+look_ahead]  full-band model outputs

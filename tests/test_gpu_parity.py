@@ -199,6 +199,13 @@ def test_host_buffer_entry_point(built_lib):
     pin = lambda x: torch.from_numpy(x).pin_memory()
     host = m.forward_host(pin(mag), pin(real), pin(imag), device=DEV)
     assert torch.equal(host, dev)
+    # pipelined (double-buffered, async) variant: several batches in flight, results valid after sync_host()
+    outs = [m.forward_host(pin(mag * s), pin(real * s), pin(imag * s), device=DEV, pipelined=True) for s in (1.0, 2.0, 1.0, 0.5)]
+    m.sync_host()
+    assert torch.equal(outs[0], dev) and torch.equal(outs[2], dev)
+    with torch.no_grad():
+        ref2 = m(_t(mag * 2), _t(real * 2), _t(imag * 2)).cpu()
+    assert torch.equal(outs[1], ref2)
 
 
 @pytest.mark.parametrize("norm", ["offline_laplace_norm", "cumulative_laplace_norm", "offline_gaussian_norm", "cumulative_layer_norm"])
