@@ -804,6 +804,102 @@ extern "C" int fsn_model_get_stage(fsn_model* m, const char* name, float* d_dst,
     return fail(FSN_EINVAL, "unknown stage %s", name);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// streaming step API (causal fullsubnet.Model)
+// ---------------------------------------------------------------------------------------------
+struct fsn_stream {
+    fsn_model* m;
+    int B, n = 0;
+    DevBuf cum_in, cum_sb, fbin, fbx, hseq, fbout, ximg, c_fb, c_sb, h_fb, h_sb;
+    int ra_fb = 0, ra_sb = 0, rows_pad = 0, Ipad = 0;
+};
+
+extern "C" int fsn_stream_create(fsn_model* m, int32_t B, fsn_stream** out) {
+    if (!m || !out || B < 1) return fail(FSN_EINVAL, "bad argument");
+    if (!m->finalized) return fail(FSN_ESTATE, "fsn_model_finalize has not been called");
+    const fsn_config& c = m->cfg;
+    if (c.model_kind != FSN_KIND_FSN) return fail(FSN_EINVAL, "streaming needs fullsubnet.Model (FullSubNet+ is not causal: TSSE pools over all time)");
+    if (c.norm_type != FSN_NORM_CUMULATIVE_LAPLACE && c.norm_type != FSN_NORM_CUMULATIVE_LAYER)
+        return fail(FSN_EINVAL, "streaming needs a cumulative norm_type");
+    fsn_stream* st = new fsn_stream();
+    st->m = m; st->B = B;
+    const int F = c.num_freqs, rows = B * F, ntiles = (rows + 127) / 128;
+    st->Ipad = (F + 15) / 16 * 16; st->rows_pad = (B + 63) / 64 * 64;
+    int e = 0;
+    e |= st->cum_in.ensure((size_t)B * 2 * sizeof(double), true);
+    e |= st->cum_sb.ensure((size_t)rows * 2 * sizeof(double), true);
+    e |= st->fbin.ensure((size_t)B * F * 4 * 4, true);
+    e |= st->fbx.ensure((size_t)st->rows_pad * st->Ipad * 2, true);
+    e |= st->hseq.ensure((size_t)B * c.fb_hidden * 4 * 4, true);
+    e |= st->fbout.ensure((size_t)B * F * 4 * 4, true);
+    e |= st->ximg.ensure((size_t)ntiles * 16384, true);
+    e |= st->c_fb.ensure(lstm_mma_cstate_bytes(c.num_layers, B, c.fb_hidden, &st->ra_fb), true);
+    e |= st->c_sb.ensure(lstm_mma_cstate_bytes(c.num_layers, rows, c.sb_hidden, &st->ra_sb), true);
+    e |= st->h_fb.ensure((size_t)c.num_layers * st->ra_fb * c.fb_hidden * 2, true);
+    e |= st->h_sb.ensure((size_t)c.num_layers * st->ra_sb * c.sb_hidden * 2, true);
+    if (e) { delete st; return fail(FSN_ECUDA, "stream state allocation failed"); }
+    *out = st;
+    return FSN_OK;
+}
+
+extern "C" void fsn_stream_destroy(fsn_stream* st) {
+    if (!st) return;
+    DevBuf* all[] = {&st->cum_in, &st->cum_sb, &st->fbin, &st->fbx, &st->hseq, &st->fbout, &st->ximg, &st->c_fb, &st->c_sb, &st->h_fb, &st->h_sb};
+    for (auto* b : all) b->release();
+    delete st;
+}
+
+extern "C" int fsn_stream_step(fsn_stream* st, const float* d_mag, float* d_mask, int32_t* h_valid, void* stream) {
+    if (!st || !d_mag || !d_mask) return fail(FSN_EINVAL, "null argument");
+    fsn_model* m = st->m;
+    const fsn_config& c = m->cfg;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int B = st->B, F = c.num_freqs, n = st->n, resume = n > 0;
+    StreamNormLaunch na{d_mag, static_cast<float*>(st->fbin.p), static_cast<double*>(st->cum_in.p), B, F, 4, n, c.norm_type};
+    launch_stream_norm(na, s);
+    launch_fb_pack(static_cast<const float*>(st->fbin.p), static_cast<__half*>(st->fbx.p), B, F, 1, 4, st->rows_pad, st->Ipad, s);
+    LstmMmaLaunch a{};
+    for (int l = 0; l < c.num_layers; ++l) { a.w.wfrag[l] = static_cast<const uint4*>(m->fb_frag[l].p); a.w.bias[l] = static_cast<const float*>(m->fb_bias[l].p); }
+    a.L = c.num_layers; a.H = c.fb_hidden; a.I = F; a.Ipad = st->Ipad; a.rows = B; a.Tp = 1;
+    a.xplain = static_cast<const __half*>(st->fbx.p); a.rows_pad = st->rows_pad;
+    a.cstate = static_cast<float*>(st->c_fb.p); a.rows_alloc = st->ra_fb;
+    a.hseq = static_cast<float*>(st->hseq.p); a.P = 4; a.fast = c.fast_math;
+    a.hstate = static_cast<__half*>(st->h_fb.p); a.resume = resume;
+    int e = launch_lstm_mma(a, s);
+    if (e) return fail(FSN_ECUDA, "full-band LSTM step failed: %s", cudaGetErrorString((cudaError_t)e));
+    ConvLaunch cf{};
+    cf.X = static_cast<const float*>(st->hseq.p); cf.Y = static_cast<float*>(st->fbout.p);
+    cf.Z = B; cf.zper = B; cf.M = F; cf.K = c.fb_hidden; cf.Tp = 1; cf.P = 4;
+    cf.pro = PRO_NONE; cf.epi = EPI_ACT; cf.act = c.fb_act;
+    cf.W[0] = P(m, "fb_model.fc_output_layer.weight"); cf.bias[0] = P(m, "fb_model.fc_output_layer.bias");
+    launch_conv1x1(cf, s);
+    StreamPackLaunch pa{d_mag, static_cast<const float*>(st->fbout.p), 4, static_cast<double*>(st->cum_sb.p), static_cast<__half*>(st->ximg.p),
+                        B, F, c.sb_num_neighbors, c.fb_num_neighbors, n, c.norm_type};
+    launch_stream_pack(pa, s);
+    LstmMmaLaunch b{};
+    for (int l = 0; l < c.num_layers; ++l) { b.w.wfrag[l] = static_cast<const uint4*>(m->sb_frag[l].p); b.w.bias[l] = static_cast<const float*>(m->sb_bias[l].p); }
+    b.w.fc_w = P(m, "sb_model.fc_output_layer.weight"); b.w.fc_b = P(m, "sb_model.fc_output_layer.bias");
+    b.L = c.num_layers; b.H = c.sb_hidden; b.I = m->Isb; b.Ipad = 64; b.rows = B * F; b.Tp = 1;
+    b.img = static_cast<const __half*>(st->ximg.p); b.ntiles = (B * F + 127) / 128;
+    b.cstate = static_cast<float*>(st->c_sb.p); b.rows_alloc = st->ra_sb;
+    b.out = d_mask; b.O = c.output_size; b.F = F; b.la = 0; b.act = c.sb_act; b.fast = c.fast_math;
+    b.hstate = static_cast<__half*>(st->h_sb.p); b.resume = resume;
+    e = launch_lstm_mma(b, s);
+    if (e) return fail(FSN_ECUDA, "sub-band LSTM step failed: %s", cudaGetErrorString((cudaError_t)e));
+    CK(cudaGetLastError());
+    if (h_valid) *h_valid = (n >= c.look_ahead) ? 1 : 0;
+    st->n++;
+    return FSN_OK;
+}
+
+extern "C" int fsn_apply_cirm(const float* d_crm, const float* d_noisy, float* d_enh, int32_t B, int32_t F, int32_t T, void* stream) {
+    if (!d_crm || !d_noisy || !d_enh || B < 1 || F < 1 || T < 1) return fail(FSN_EINVAL, "bad argument");
+    launch_apply_cirm(d_crm, reinterpret_cast<const float2*>(d_noisy), reinterpret_cast<float2*>(d_enh), B, F, T, static_cast<cudaStream_t>(stream));
+    CK(cudaGetLastError());
+    return FSN_OK;
+}
+
 extern "C" int64_t fsn_model_last_launch_count(const fsn_model* m) { return m ? m->launches : 0; }
 extern "C" int fsn_model_lstm_ms_history(fsn_model* m, float* h_ms, int32_t n) {
     if (!m || !h_ms || n < 1) return 0;

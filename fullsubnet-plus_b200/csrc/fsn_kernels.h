@@ -85,6 +85,14 @@ void launch_pad_copy(const float* x, float* y, int B, int F, int T, int P, cudaS
 // full-band LSTM input: [B, F, P] fp32 -> [Tp, Bpad, Ipad] fp16 (rows >= B and k >= F zero)
 void launch_fb_pack(const float* x, __half* y, int B, int F, int Tp, int P, int rows_pad, int Ipad, cudaStream_t s);
 
+void launch_apply_cirm(const float* crm, const float2* noisy, float2* enh, int B, int F, int T, cudaStream_t s);
+
+// streaming step kernels (k_front.cu): one frame of the cumulative norms with running sums carried in global memory
+struct StreamNormLaunch { const float* x; float* y; double* cum; int B, F, P, n, type; };       // x [B,F] -> y [B,F,P] (t = 0)
+void launch_stream_norm(const StreamNormLaunch& a, cudaStream_t s);
+struct StreamPackLaunch { const float* mag; const float* fb; int Pfb; double* cum; __half* ximg; int B, F, Ns, Nf, n, type; };
+void launch_stream_pack(const StreamPackLaunch& a, cudaStream_t s);
+
 // ---- k_lstm_mma.cu ---------------------------------------------------------------------------
 struct LstmMmaWeights {       // device, produced by pack (fsn_api.cu)
     const uint4* wfrag[4];    // per layer: [H/8 groups][K/16][32 lanes][2 x uint4]
@@ -106,6 +114,8 @@ struct LstmMmaLaunch {
     // output B: top-layer h as fp32 [rows, H, P]
     float* hseq; int P;
     int fast;
+    // streaming: hidden state carried across launches ([L, rows_alloc, H] fp16); resume = 1 continues from it
+    __half* hstate; int resume;
 };
 size_t lstm_mma_cstate_bytes(int L, int rows, int H, int* rows_alloc);
 int launch_lstm_mma(const LstmMmaLaunch& a, cudaStream_t s);   // returns 0 or cudaError

@@ -531,6 +531,91 @@ void launch_sb_pack(const SbPackLaunch& a, cudaStream_t s) {
 }
 
 
+
+// =============================================================================================
+// Streaming (frame-by-frame) forms of the cumulative norms: the running sums live in global memory (fp64) and one
+// launch handles frame n.  reference: base_model.py:227-258 / :277-316 evaluated one column at a time.
+// =============================================================================================
+__global__ void __launch_bounds__(256) stream_norm_kernel(StreamNormLaunch a) {
+    __shared__ double red[16];
+    __shared__ float s_a, s_b;
+    const int b = blockIdx.x, F = a.F;
+    const float* x = a.x + (size_t)b * F;
+    double s = 0, q = 0;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) { const double v = x[f]; s += v; q += v * v; }
+    s = warp_sum_d(s); q = warp_sum_d(q);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[warp] = s; red[8 + warp] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0, tq = 0;
+        for (int i = 0; i < 8; ++i) { ts += red[i]; tq += red[8 + i]; }
+        const double EPS = 1.1920928955078125e-07;
+        const double cs = (a.n == 0 ? 0.0 : a.cum[2 * b]) + ts, cq = (a.n == 0 ? 0.0 : a.cum[2 * b + 1]) + tq;
+        a.cum[2 * b] = cs; a.cum[2 * b + 1] = cq;
+        const double cnt = (double)F * (a.n + 1), cm = cs / cnt;
+        if (a.type == FSN_NORM_CUMULATIVE_LAPLACE) { s_a = (float)(1.0 / (cm + EPS)); s_b = 0.f; }
+        else { const double cv = (cq - 2.0 * cm * cs) / cnt + cm * cm, inv = 1.0 / sqrt(cv + EPS); s_a = (float)inv; s_b = (float)(-cm * inv); }
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < F; f += blockDim.x) a.y[((size_t)b * F + f) * a.P] = fmaf(x[f], s_a, s_b);
+}
+void launch_stream_norm(const StreamNormLaunch& a, cudaStream_t s) { stream_norm_kernel<<<a.B, 256, 0, s>>>(a); }
+
+// one frame of the sub-band input with the per-sequence cumulative norm; thread = sequence (b, f)
+__global__ void __launch_bounds__(128) stream_pack_kernel(StreamPackLaunch a) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x, F = a.F;
+    if (row >= a.B * F) return;
+    const int b = row / F, f = row % F, tile = row >> 7, r = row & 127;
+    const int nw = 2 * a.Ns + 1, nf = 2 * a.Nf + 1, I = nw + nf;
+    float v[64];
+    double s = 0, q = 0;
+#pragma unroll
+    for (int k = 0; k < 64; ++k) {
+        float x = 0.f;
+        if (k < nw) x = a.mag[(size_t)b * F + reflect_idx(f + k - a.Ns, F)];
+        else if (k < I) x = a.fb[((size_t)b * F + reflect_idx(f + (k - nw) - a.Nf, F)) * a.Pfb];
+        v[k] = x; s += x; q += (double)x * x;
+    }
+    const double EPS = 1.1920928955078125e-07;
+    const double cs = (a.n == 0 ? 0.0 : a.cum[2 * row]) + s, cq = (a.n == 0 ? 0.0 : a.cum[2 * row + 1]) + q;
+    a.cum[2 * row] = cs; a.cum[2 * row + 1] = cq;
+    const double cnt = (double)I * (a.n + 1), cm = cs / cnt;
+    float sc, sh;
+    if (a.type == FSN_NORM_CUMULATIVE_LAPLACE) { sc = (float)(1.0 / (cm + EPS)); sh = 0.f; }
+    else { const double cv = (cq - 2.0 * cm * cs) / cnt + cm * cm, inv = 1.0 / sqrt(cv + EPS); sc = (float)inv; sh = (float)(-cm * inv); }
+    char* img = reinterpret_cast<char*>(a.ximg) + (size_t)tile * (128 * 128);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = (c * 8 + i < I) ? fminf(fmaxf(fmaf(v[c * 8 + i], sc, sh), -65504.f), 65504.f) : 0.f;
+        *reinterpret_cast<uint4*>(img + sw128_offset(r, c * 8)) =
+            make_uint4(pack_half2(w[0], w[1]), pack_half2(w[2], w[3]), pack_half2(w[4], w[5]), pack_half2(w[6], w[7]));
+    }
+}
+void launch_stream_pack(const StreamPackLaunch& a, cudaStream_t s) { stream_pack_kernel<<<(a.B * a.F + 127) / 128, 128, 0, s>>>(a); }
+
+// decompress_cIRM + complex multiply (inferencer.py:152-157, mask.py:60-63) in one pass.
+__global__ void apply_cirm_kernel(const float* crm, const float2* noisy, float2* enh, int FT, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t b = i / FT, e = i % FT;
+    float m[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        float v = crm[(b * 2 + c) * FT + e];
+        v = (v >= 9.9f) ? 9.9f : ((v <= -9.9f) ? -9.9f : v);           // limit * (m >= limit) - limit * (m <= -limit) + m * (|m| < limit)
+        m[c] = -10.f * logf((10.f - v) / (10.f + v));
+    }
+    const float2 x = noisy[i];
+    enh[i] = make_float2(m[0] * x.x - m[1] * x.y, m[1] * x.x + m[0] * x.y);
+}
+void launch_apply_cirm(const float* crm, const float2* noisy, float2* enh, int B, int F, int T, cudaStream_t s) {
+    const size_t n = (size_t)B * F * T;
+    apply_cirm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(crm, noisy, enh, F * T, n);
+}
+
 __global__ void pad_copy_kernel(const float* x, float* y, int rows, int T, int P) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * P) return;

@@ -40,6 +40,14 @@ __global__ void __launch_bounds__(256, 1) lstm_mma_kernel(LstmMmaLaunch a) {
     const int ngroups = H / 8;
 
     for (int i = tid; i < (int)((size_t)L * 2 * R * HS / 2); i += blockDim.x) reinterpret_cast<uint32_t*>(hb)[i] = 0u;
+    if (a.hstate && a.resume) {                          // streaming: h_{-1} of every layer goes into the "previous" buffer (index 1 at t = 0)
+        __syncthreads();
+        for (int e = tid; e < L * R * (H / 2); e += blockDim.x) {
+            const int l = e / (R * (H / 2)), r = (e / (H / 2)) % R, u2 = e % (H / 2);
+            reinterpret_cast<uint32_t*>(hb + ((size_t)l * 2 + 1) * R * HS + (size_t)r * HS)[u2] =
+                reinterpret_cast<const uint32_t*>(a.hstate + ((size_t)l * a.rows_alloc + row0 + r) * H)[u2];
+        }
+    }
     if (a.out) for (int i = tid; i < a.O * H; i += blockDim.x) fcw[i] = a.w.fc_w[i];
     __syncthreads();
 
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(256, 1) lstm_mma_kernel(LstmMmaLaunch a) {
                         const size_t ci = (size_t)(row0 + r) * H + u;
                         const float gi = acc[mt][0][q] + bias[u], gf = acc[mt][1][q] + bias[H + u];
                         const float gg = acc[mt][2][q] + bias[2 * H + u], go = acc[mt][3][q] + bias[3 * H + u];
-                        const float cprev = (t == 0) ? 0.f : cst[ci];
+                        const float cprev = (t == 0 && !a.resume) ? 0.f : cst[ci];
                         const float c = sigm<FAST>(gf) * cprev + sigm<FAST>(gi) * tanh_<FAST>(gg);
                         const float h = sigm<FAST>(go) * tanh_<FAST>(c);
                         cst[ci] = c;
@@ -140,6 +148,15 @@ __global__ void __launch_bounds__(256, 1) lstm_mma_kernel(LstmMmaLaunch a) {
             }
         }
         // (the next iteration's x staging is separated from these reads by the barrier after it)
+    }
+    if (a.hstate) {                                      // streaming: carry the last hidden state of every layer
+        __syncthreads();
+        const int pl = (Tp - 1) & 1;
+        for (int e = tid; e < L * R * (H / 2); e += blockDim.x) {
+            const int l = e / (R * (H / 2)), r = (e / (H / 2)) % R, u2 = e % (H / 2);
+            reinterpret_cast<uint32_t*>(a.hstate + ((size_t)l * a.rows_alloc + row0 + r) * H)[u2] =
+                reinterpret_cast<const uint32_t*>(hb + ((size_t)l * 2 + pl) * R * HS + (size_t)r * HS)[u2];
+        }
     }
 }
 

@@ -14,7 +14,7 @@ LSTM_IMPL = {"auto": 0, "mma": 1, "tcgen05": 2}
 SYMBOLS = [
     "fsn_version", "fsn_last_error", "fsn_model_create", "fsn_model_destroy", "fsn_model_set_param",
     "fsn_model_num_params", "fsn_model_param_info", "fsn_model_finalize", "fsn_model_forward",
-    "fsn_model_forward_host", "fsn_model_forward_host_async", "fsn_model_sync_host", "fsn_model_get_stage", "fsn_model_last_launch_count", "fsn_model_last_lstm_impl", "fsn_model_last_lstm_ms", "fsn_model_lstm_ms_history",
+    "fsn_model_forward_host", "fsn_model_forward_host_async", "fsn_model_sync_host", "fsn_apply_cirm", "fsn_stream_create", "fsn_stream_step", "fsn_stream_destroy", "fsn_model_get_stage", "fsn_model_last_launch_count", "fsn_model_last_lstm_impl", "fsn_model_last_lstm_ms", "fsn_model_lstm_ms_history",
     "fsn_sw128_offset", "fsn_tc5_weight_stream_bytes", "fsn_tc5_pack_weights", "fsn_tc5_gate_row", "fsn_probe_tcgen05",
 ]
 
@@ -58,6 +58,11 @@ def load_library():
     lib.fsn_model_forward_host.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     lib.fsn_model_forward_host_async.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     lib.fsn_model_sync_host.argtypes = [vp]
+    lib.fsn_stream_create.argtypes = [vp, i32, C.POINTER(vp)]
+    lib.fsn_stream_step.argtypes = [vp, vp, vp, C.POINTER(i32), vp]
+    lib.fsn_stream_destroy.argtypes = [vp]
+    lib.fsn_stream_destroy.restype = None
+    lib.fsn_apply_cirm.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.fsn_model_get_stage.argtypes = [vp, C.c_char_p, vp, i64, vp]
     lib.fsn_model_last_launch_count.argtypes = [vp]
     lib.fsn_model_last_launch_count.restype = i64

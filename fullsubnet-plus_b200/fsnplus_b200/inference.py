@@ -10,8 +10,12 @@ Multi-GPU: utterances are independent, so a batch is sharded across ranks (one p
 data-path collective; the only exchange is one all-gather of the enhanced waveforms (NCCL on GPUs, gloo in
 the CPU tests of the host logic).
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 def stft(y, n_fft=512, hop_length=256, win_length=512):
@@ -33,6 +37,23 @@ def decompress_cIRM(mask, K=10, limit=9.9):
     return -K * torch.log((K - mask) / (K + mask))
 
 
+def apply_cirm(crm, X):
+    """decompress_cIRM + complex multiply (reference inferencer.py:152-157): one fused CUDA kernel behind the C ABI for
+    CUDA float32 inputs, the torch restatement otherwise (CPU tests of the harness)."""
+    if crm.is_cuda and crm.dtype == torch.float32 and X.dtype == torch.complex64:
+        crm = crm.contiguous()
+        Xr = torch.view_as_real(X.contiguous())
+        out = torch.empty_like(Xr)
+        B, _, F, T = crm.shape
+        with torch.cuda.device(crm.device):
+            stream = C.c_void_p(torch.cuda.current_stream(crm.device).cuda_stream)
+            _lib.check(_lib.load_library().fsn_apply_cirm(C.c_void_p(crm.data_ptr()), C.c_void_p(Xr.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                          B, F, T, stream))
+        return torch.view_as_complex(out)
+    m = decompress_cIRM(crm)                                   # [B, 2, F, T]
+    return torch.complex(m[:, 0] * X.real - m[:, 1] * X.imag, m[:, 1] * X.real + m[:, 0] * X.imag)
+
+
 @torch.no_grad()
 def enhance_batch(model, noisy, n_fft=512, hop_length=256, win_length=512, complex_inputs=True):
     """noisy [B, L] float32 on the model's device -> enhanced [B, L].
@@ -43,10 +64,7 @@ def enhance_batch(model, noisy, n_fft=512, hop_length=256, win_length=512, compl
         crm = model(mag, X.real.unsqueeze(1).contiguous(), X.imag.unsqueeze(1).contiguous())
     else:
         crm = model(mag)
-    m = decompress_cIRM(crm)                                   # [B, 2, F, T]
-    er = m[:, 0] * X.real - m[:, 1] * X.imag
-    ei = m[:, 1] * X.real + m[:, 0] * X.imag
-    return istft(torch.complex(er, ei), n_fft, hop_length, win_length, length=noisy.size(-1))
+    return istft(apply_cirm(crm, X), n_fft, hop_length, win_length, length=noisy.size(-1))
 
 
 def shard_range(n_items, rank, world_size):

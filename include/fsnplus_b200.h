@@ -107,6 +107,21 @@ int fsn_model_forward_host_async(fsn_model* m, const float* h_mag, const float* 
                                  float* h_out, void* stream);
 int fsn_model_sync_host(fsn_model* m);
 
+/* Streaming (frame-by-frame) inference for the causal configuration (BASELINE config #4): fullsubnet.Model with
+ * norm_type cumulative_laplace_norm or cumulative_layer_norm.  State carried between calls: running norm sums, (h, c) of the
+ * full-band and sub-band LSTMs.  Call n consumes magnitude frame n ([B, F] float32, device) and writes the cIRM of frame
+ * n - look_ahead to d_mask ([B, 2, F]); *h_valid = 0 for the first look_ahead calls.  Feeding look_ahead zero frames at the
+ * end flushes the tail, exactly like the reference's right padding (fullsubnet.py:81). */
+typedef struct fsn_stream fsn_stream;
+int fsn_stream_create(fsn_model* m, int32_t B, fsn_stream** out);
+int fsn_stream_step(fsn_stream* st, const float* d_mag_frame, float* d_mask, int32_t* h_valid, void* stream);
+void fsn_stream_destroy(fsn_stream* st);
+
+/* Fused post-processing of the inferencer method (fullsubnet_plus/inferencer/inferencer.py:152-157 and
+ * audio_zen/acoustics/mask.py:60-63): decompress_cIRM (K = 10, limit = 9.9) + complex multiply with the noisy spectrum.
+ * d_crm [B, 2, F, T] float32 (model output), d_noisy / d_enh [B, F, T] complex64 (interleaved re, im). */
+int fsn_apply_cirm(const float* d_crm, const float* d_noisy, float* d_enh, int32_t B, int32_t F, int32_t T, void* stream);
+
 /* Test hooks: copy an intermediate of the LAST forward to a device buffer.
  *   "fb_in"  [nbranch, B, F, T+look_ahead]  post-norm (and post-attention) full-band inputs
  *   "fb_out" [nbranch, B, F, T+look_ahead]  full-band model outputs

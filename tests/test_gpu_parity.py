@@ -284,3 +284,46 @@ def test_config5_large_model(built_lib):
     err = O.rel_l2(out.cpu().numpy(), ref)
     print(f"\n[config5 large, {m.last_lstm_impl()}] cIRM rel-L2 {err:.3e}")
     assert out.shape == (1, 2, 513, 94) and err < MASK_TOL
+
+
+def test_fused_postprocessing_matches_torch(built_lib):
+    """fsn_apply_cirm == decompress_cIRM + complex multiply of the reference inferencer (inferencer.py:152-157)."""
+    from fsnplus_b200 import inference as inf
+    g = torch.Generator().manual_seed(3)
+    crm = (torch.randn(3, 2, 33, 20, generator=g) * 6).to(DEV)            # exercises the +-9.9 clamp
+    X = torch.complex(torch.randn(3, 33, 20, generator=g), torch.randn(3, 33, 20, generator=g)).to(DEV)
+    got = inf.apply_cirm(crm, X)
+    m = inf.decompress_cIRM(crm)
+    want = torch.complex(m[:, 0] * X.real - m[:, 1] * X.imag, m[:, 1] * X.real + m[:, 0] * X.imag)
+    assert torch.allclose(torch.view_as_real(got), torch.view_as_real(want), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("norm", ["cumulative_laplace_norm", "cumulative_layer_norm"])
+def test_streaming_step_api_matches_offline(built_lib, norm):
+    """BASELINE config #4, frame-by-frame: the stateful step API (carried LSTM state + running norm sums) must reproduce
+    the offline forward of the same causal model, frame for frame, and the oracle within the mask tolerance."""
+    from fsnplus_b200.streaming import StreamingFullSubNet
+    cfg = O.default_fsn_config()
+    cfg.update(num_freqs=65, sb_num_neighbors=7, sb_model_hidden_size=64, fb_model_hidden_size=96, norm_type=norm)
+    params = O.make_params_fsn(cfg, seed=13)
+    B, T = 2, 23
+    mag = small_inputs(B, 65, T, 9)[0]
+    ref = O.fullsubnet_forward(params, cfg, mag)
+    m = build_fsn(cfg, params, lstm_impl="mma")
+    with torch.no_grad():
+        offline = m(_t(mag))
+    st = StreamingFullSubNet(m, batch_size=B, device=DEV)
+    frames = []
+    x = _t(mag)
+    for t in range(T):
+        y = st.step(x[:, 0, :, t])
+        assert (y is None) == (t < cfg["look_ahead"])
+        if y is not None:
+            frames.append(y)
+    frames += st.flush()
+    st.close()
+    got = torch.stack(frames, dim=-1)                      # [B, 2, F, T]
+    assert got.shape == offline.shape
+    e_off, e_ref = O.rel_l2(got.cpu().numpy(), offline.cpu().numpy()), O.rel_l2(got.cpu().numpy(), ref)
+    print(f"\n[streaming {norm}] vs offline {e_off:.2e}  vs oracle {e_ref:.2e}")
+    assert e_off < 1e-4 and e_ref < MASK_TOL      # offline scan sums squares in fp32 per column, the step API in fp64
