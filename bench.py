@@ -294,11 +294,15 @@ def main():
         peak, peak_burst, peak_src = pk["bf16_tflops_sustained"], pk["bf16_tflops"], "measured (MEASURED_PEAKS.json, sustained)"
     else:
         peak, peak_burst, peak_src = 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
+    traffic = None                                    # dram read+write bytes per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "lstm_traffic.json")
+    if os.path.exists(tpath) and lstm_impl == "tcgen05" and B == 64:
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     k_ms = statistics.mean([x for x in lstm_ms if x > 0]) if lstm_ms else float("nan")
     achieved = B * sb_flops / (k_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": f"sub-band LSTM ({lstm_impl})", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "frac_of_burst_peak": achieved / peak_burst, "peak_source": peak_src,
-                "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step, "traffic": None,
+                "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step, "traffic": traffic,
                 "algorithmic_flops_per_launch": B * sb_flops}
 
     line = {
