@@ -66,6 +66,7 @@ struct fsn_model {
     int Cp = 0, tcnNT = 0, tcnNtiles = 0, num_sms = 148;
     DevBuf tW1, tW2, tWfc, tS1, tS2b, tBfc;            // [8][3][512][Cp], [8][3][Cp][512], [3][Cp][Cp], [8][3][Cp] x2, [3][Cp]
     DevBuf x0, xr;                                     // time-major fb input / relu'd last residual
+    DevBuf ws_h, ws_bar;                               // weight-stationary full-band LSTM: h exchange buffer, grid barrier
     DevBuf xn, sigma;                                  // pre-normalised inputs / sub-band std for the non-default norm types
     alignas(64) unsigned char mapW1[8][128], mapW2[8][128], mapWfc[128];
     alignas(64) unsigned char mapX0[128], mapXa[128], mapXb[128], mapXr[128], mapY2[128];
@@ -297,6 +298,7 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     m->cfg = c;
     build_specs(m);
     for (int i = 0; i < fsn_model::NEV; ++i) { cudaEventCreate(&m->ev0[i]); cudaEventCreate(&m->ev1[i]); }
+    { cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev); if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) m->num_sms = prop.multiProcessorCount; }
     if (m->Isb > 64) { delete m; return fail(FSN_EINVAL, "sub-band input size %d > 64 not supported", m->Isb); }
     *out = m;
     return FSN_OK;
@@ -306,7 +308,7 @@ extern "C" void fsn_model_destroy(fsn_model* m) {
     if (!m) return;
     DevBuf* all[] = {&m->arena, &m->sb_tc5_stream, &m->sb_tc5_bias, &m->fbin, &m->fbout, &m->xa, &m->xb, &m->y1, &m->y2, &m->stats,
                      &m->mu, &m->ximg, &m->cstate, &m->magpad, &m->fbx, &m->hseq, &m->stage_in[0], &m->stage_in[1], &m->stage_in[2],
-                     &m->stage_out, &m->tW1, &m->tW2, &m->tWfc, &m->tS1, &m->tS2b, &m->tBfc, &m->x0, &m->xr, &m->xn, &m->sigma};
+                     &m->stage_out, &m->tW1, &m->tW2, &m->tWfc, &m->tS1, &m->tS2b, &m->tBfc, &m->x0, &m->xr, &m->xn, &m->sigma, &m->ws_h, &m->ws_bar};
     for (auto* b : all) b->release();
     if (m->s_in) { cudaStreamDestroy(m->s_in); cudaStreamDestroy(m->s_out); for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_h2d[i]); cudaEventDestroy(m->ev_fwd[i]); cudaEventDestroy(m->ev_d2h[i]); } }
     for (int i = 0; i < 2; ++i) { m->a_out[i].release(); for (int j = 0; j < 3; ++j) m->a_in[i][j].release(); }
@@ -389,6 +391,17 @@ extern "C" int fsn_model_finalize(fsn_model* m) {
 }
 
 static const float* P(fsn_model* m, const std::string& k) { return m->dev.at(k); }
+
+
+static void fill_ws(fsn_model* m, LstmWsLaunch& w) {
+    const fsn_config& c = m->cfg;
+    for (int l = 0; l < c.num_layers; ++l) {
+        const std::string s = std::to_string(l);
+        w.w_ih[l] = P(m, "fb_model.sequence_model.weight_ih_l" + s); w.w_hh[l] = P(m, "fb_model.sequence_model.weight_hh_l" + s);
+        w.b_ih[l] = P(m, "fb_model.sequence_model.bias_ih_l" + s); w.b_hh[l] = P(m, "fb_model.sequence_model.bias_hh_l" + s);
+    }
+    w.L = c.num_layers; w.H = c.fb_hidden; w.I = c.num_freqs; w.Ipad = (c.num_freqs + 15) / 16 * 16; w.fast = c.fast_math;
+}
 
 static int ensure_ws(fsn_model* m, int B, int T) {
     const fsn_config& c = m->cfg;
@@ -672,6 +685,20 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
         launch_pad_copy(d_mag, static_cast<float*>(m->magpad.p), B, F, T, Pp, s); m->launches++;
         const int Ipad = (F + 15) / 16 * 16, rows_pad = (B + 63) / 64 * 64;
         launch_fb_pack(static_cast<const float*>(m->fbin.p), static_cast<__half*>(m->fbx.p), B, F, Tp, Pp, rows_pad, Ipad, s); m->launches++;
+        if (lstm_ws_supported(c.num_layers, c.fb_hidden, Ipad, B, m->num_sms) && !getenv("FSN_NO_WS")) {
+            const size_t hb = (size_t)c.num_layers * 2 * 64 * c.fb_hidden * 2;
+            if (m->ws_h.ensure(hb, false) || m->ws_bar.ensure(64, true)) return fail(FSN_ECUDA, "allocation failed");
+            CK(cudaMemsetAsync(m->ws_h.p, 0, hb, s));
+            LstmWsLaunch w{};
+            fill_ws(m, w);
+            w.rows = B; w.rows_pad = rows_pad; w.Tp = Tp;
+            w.x = static_cast<const __half*>(m->fbx.p); w.hbuf = static_cast<__half*>(m->ws_h.p); w.cbuf = nullptr;
+            w.barrier = static_cast<unsigned int*>(m->ws_bar.p);
+            w.hseq = static_cast<float*>(m->hseq.p); w.P = Pp; w.resume = 0; w.t0 = 0;
+            int e = launch_lstm_ws(w, s);
+            if (e) return fail(FSN_ECUDA, "weight-stationary full-band LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
+            m->launches++;
+        } else {
         LstmMmaLaunch a{};
         for (int l = 0; l < c.num_layers; ++l) {
             a.w.wfrag[l] = static_cast<const uint4*>(m->fb_frag[l].p);
@@ -685,6 +712,7 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
         int e = launch_lstm_mma(a, s);
         if (e) return fail(FSN_ECUDA, "full-band LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
         m->launches++;
+        }
         ConvLaunch cf{};
         cf.X = static_cast<const float*>(m->hseq.p); cf.Y = static_cast<float*>(m->fbout.p);
         cf.Z = B; cf.zper = B; cf.M = F; cf.K = c.fb_hidden; cf.Tp = Tp; cf.P = Pp;
@@ -811,7 +839,8 @@ extern "C" int fsn_model_get_stage(fsn_model* m, const char* name, float* d_dst,
 struct fsn_stream {
     fsn_model* m;
     int B, n = 0;
-    DevBuf cum_in, cum_sb, fbin, fbx, hseq, fbout, ximg, c_fb, c_sb, h_fb, h_sb;
+    DevBuf cum_in, cum_sb, fbin, fbx, hseq, fbout, ximg, c_fb, c_sb, h_fb, h_sb, ws_h, ws_c, ws_bar;
+    bool use_ws = false;
     int ra_fb = 0, ra_sb = 0, rows_pad = 0, Ipad = 0;
 };
 
@@ -838,6 +867,12 @@ extern "C" int fsn_stream_create(fsn_model* m, int32_t B, fsn_stream** out) {
     e |= st->c_sb.ensure(lstm_mma_cstate_bytes(c.num_layers, rows, c.sb_hidden, &st->ra_sb), true);
     e |= st->h_fb.ensure((size_t)c.num_layers * st->ra_fb * c.fb_hidden * 2, true);
     e |= st->h_sb.ensure((size_t)c.num_layers * st->ra_sb * c.sb_hidden * 2, true);
+    st->use_ws = lstm_ws_supported(c.num_layers, c.fb_hidden, st->Ipad, B, m->num_sms) && !getenv("FSN_NO_WS");
+    if (st->use_ws) {
+        e |= st->ws_h.ensure((size_t)c.num_layers * 2 * 64 * c.fb_hidden * 2, true);
+        e |= st->ws_c.ensure((size_t)c.num_layers * 64 * c.fb_hidden * 4, true);
+        e |= st->ws_bar.ensure(64, true);
+    }
     if (e) { delete st; return fail(FSN_ECUDA, "stream state allocation failed"); }
     *out = st;
     return FSN_OK;
@@ -845,7 +880,7 @@ extern "C" int fsn_stream_create(fsn_model* m, int32_t B, fsn_stream** out) {
 
 extern "C" void fsn_stream_destroy(fsn_stream* st) {
     if (!st) return;
-    DevBuf* all[] = {&st->cum_in, &st->cum_sb, &st->fbin, &st->fbx, &st->hseq, &st->fbout, &st->ximg, &st->c_fb, &st->c_sb, &st->h_fb, &st->h_sb};
+    DevBuf* all[] = {&st->cum_in, &st->cum_sb, &st->fbin, &st->fbx, &st->hseq, &st->fbout, &st->ximg, &st->c_fb, &st->c_sb, &st->h_fb, &st->h_sb, &st->ws_h, &st->ws_c, &st->ws_bar};
     for (auto* b : all) b->release();
     delete st;
 }
@@ -859,14 +894,25 @@ extern "C" int fsn_stream_step(fsn_stream* st, const float* d_mag, float* d_mask
     StreamNormLaunch na{d_mag, static_cast<float*>(st->fbin.p), static_cast<double*>(st->cum_in.p), B, F, 4, n, c.norm_type};
     launch_stream_norm(na, s);
     launch_fb_pack(static_cast<const float*>(st->fbin.p), static_cast<__half*>(st->fbx.p), B, F, 1, 4, st->rows_pad, st->Ipad, s);
-    LstmMmaLaunch a{};
-    for (int l = 0; l < c.num_layers; ++l) { a.w.wfrag[l] = static_cast<const uint4*>(m->fb_frag[l].p); a.w.bias[l] = static_cast<const float*>(m->fb_bias[l].p); }
-    a.L = c.num_layers; a.H = c.fb_hidden; a.I = F; a.Ipad = st->Ipad; a.rows = B; a.Tp = 1;
-    a.xplain = static_cast<const __half*>(st->fbx.p); a.rows_pad = st->rows_pad;
-    a.cstate = static_cast<float*>(st->c_fb.p); a.rows_alloc = st->ra_fb;
-    a.hseq = static_cast<float*>(st->hseq.p); a.P = 4; a.fast = c.fast_math;
-    a.hstate = static_cast<__half*>(st->h_fb.p); a.resume = resume;
-    int e = launch_lstm_mma(a, s);
+    int e = 0;
+    if (st->use_ws) {
+        LstmWsLaunch w{};
+        fill_ws(m, w);
+        w.rows = B; w.rows_pad = st->rows_pad; w.Tp = 1;
+        w.x = static_cast<const __half*>(st->fbx.p); w.hbuf = static_cast<__half*>(st->ws_h.p); w.cbuf = static_cast<float*>(st->ws_c.p);
+        w.barrier = static_cast<unsigned int*>(st->ws_bar.p);
+        w.hseq = static_cast<float*>(st->hseq.p); w.P = 4; w.resume = resume; w.t0 = n;
+        e = launch_lstm_ws(w, s);
+    } else {
+        LstmMmaLaunch a{};
+        for (int l = 0; l < c.num_layers; ++l) { a.w.wfrag[l] = static_cast<const uint4*>(m->fb_frag[l].p); a.w.bias[l] = static_cast<const float*>(m->fb_bias[l].p); }
+        a.L = c.num_layers; a.H = c.fb_hidden; a.I = F; a.Ipad = st->Ipad; a.rows = B; a.Tp = 1;
+        a.xplain = static_cast<const __half*>(st->fbx.p); a.rows_pad = st->rows_pad;
+        a.cstate = static_cast<float*>(st->c_fb.p); a.rows_alloc = st->ra_fb;
+        a.hseq = static_cast<float*>(st->hseq.p); a.P = 4; a.fast = c.fast_math;
+        a.hstate = static_cast<__half*>(st->h_fb.p); a.resume = resume;
+        e = launch_lstm_mma(a, s);
+    }
     if (e) return fail(FSN_ECUDA, "full-band LSTM step failed: %s", cudaGetErrorString((cudaError_t)e));
     ConvLaunch cf{};
     cf.X = static_cast<const float*>(st->hseq.p); cf.Y = static_cast<float*>(st->fbout.p);

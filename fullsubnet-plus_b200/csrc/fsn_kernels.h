@@ -120,6 +120,20 @@ struct LstmMmaLaunch {
 size_t lstm_mma_cstate_bytes(int L, int rows, int H, int* rows_alloc);
 int launch_lstm_mma(const LstmMmaLaunch& a, cudaStream_t s);   // returns 0 or cudaError
 
+// ---- k_lstm_ws.cu: weight-stationary persistent LSTM for <= 64 rows (full-band LSTM of fullsubnet.Model) ----------
+struct LstmWsLaunch {
+    const float* w_ih[4]; const float* w_hh[4]; const float* b_ih[4]; const float* b_hh[4];   // reference-layout fp32 parameters (device)
+    int L, H, I, Ipad, rows, rows_pad, Tp;
+    const __half* x;          // [Tp, rows_pad >= 64, Ipad]
+    __half* hbuf;             // [L, 2, 64, H] exchange buffer (zeroed by the caller unless resume)
+    float* cbuf;              // [L, 64, H] cell state carried across launches (streaming) or null
+    unsigned int* barrier;    // grid barrier counter
+    float* hseq; int P;       // top-layer h as fp32 [rows, H, P]
+    int fast, resume, t0;     // t0: absolute index of the first step (exchange-buffer parity)
+};
+bool lstm_ws_supported(int L, int H, int Ipad, int rows, int num_sms);
+int launch_lstm_ws(const LstmWsLaunch& a, cudaStream_t s);
+
 // ---- k_lstm_tc5.cu ---------------------------------------------------------------------------
 struct LstmTc5Launch {
     const __half* wstream;    // packed weight stream (fsn_tc5_pack_weights)
