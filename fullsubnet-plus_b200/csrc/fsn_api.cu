@@ -66,6 +66,7 @@ struct fsn_model {
     int Cp = 0, tcnNT = 0, tcnNtiles = 0, num_sms = 148;
     DevBuf tW1, tW2, tWfc, tS1, tS2b, tBfc;            // [8][3][512][Cp], [8][3][Cp][512], [3][Cp][Cp], [8][3][Cp] x2, [3][Cp]
     DevBuf x0, xr;                                     // time-major fb input / relu'd last residual
+    DevBuf tsse_scale, sb_rowsum;
     DevBuf ws_h, ws_bar;                               // weight-stationary full-band LSTM: h exchange buffer, grid barrier
     DevBuf xn, sigma;                                  // pre-normalised inputs / sub-band std for the non-default norm types
     alignas(64) unsigned char mapW1[8][128], mapW2[8][128], mapWfc[128];
@@ -308,7 +309,7 @@ extern "C" void fsn_model_destroy(fsn_model* m) {
     if (!m) return;
     DevBuf* all[] = {&m->arena, &m->sb_tc5_stream, &m->sb_tc5_bias, &m->fbin, &m->fbout, &m->xa, &m->xb, &m->y1, &m->y2, &m->stats,
                      &m->mu, &m->ximg, &m->cstate, &m->magpad, &m->fbx, &m->hseq, &m->stage_in[0], &m->stage_in[1], &m->stage_in[2],
-                     &m->stage_out, &m->tW1, &m->tW2, &m->tWfc, &m->tS1, &m->tS2b, &m->tBfc, &m->x0, &m->xr, &m->xn, &m->sigma, &m->ws_h, &m->ws_bar};
+                     &m->stage_out, &m->tW1, &m->tW2, &m->tWfc, &m->tS1, &m->tS2b, &m->tBfc, &m->x0, &m->xr, &m->xn, &m->sigma, &m->ws_h, &m->ws_bar, &m->tsse_scale, &m->sb_rowsum};
     for (auto* b : all) b->release();
     if (m->s_in) { cudaStreamDestroy(m->s_in); cudaStreamDestroy(m->s_out); for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_h2d[i]); cudaEventDestroy(m->ev_fwd[i]); cudaEventDestroy(m->ev_d2h[i]); } }
     for (int i = 0; i < 2; ++i) { m->a_out[i].release(); for (int j = 0; j < 3; ++j) m->a_in[i][j].release(); }
@@ -414,6 +415,8 @@ static int ensure_ws(fsn_model* m, int B, int T) {
     e |= m->fbout.ensure(act, true);
     e |= m->mu.ensure((size_t)B * 4, true);
     e |= m->sigma.ensure((size_t)B * 4, true);
+    e |= m->tsse_scale.ensure((size_t)nbr * B * F * 4, true);
+    e |= m->sb_rowsum.ensure((size_t)B * 4 * F * 2 * 4, true);
     if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE) e |= m->xn.ensure((size_t)nbr * B * F * Tp * 4, true);
     // images are re-zeroed whenever the geometry changes (rows beyond B*F and k >= I must stay zero)
     const size_t img_bytes = (size_t)ntiles * Tp * 16384;
@@ -534,6 +537,7 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
     sp.B = B; sp.F = F; sp.Tp = Tp; sp.Ns = c.sb_num_neighbors; sp.Nf = c.fb_num_neighbors; sp.P = Pp;
     sp.mu = static_cast<float*>(m->mu.p);
     sp.sigma = static_cast<float*>(m->sigma.p);
+    sp.rowsum = static_cast<float*>(m->sb_rowsum.p);
     sp.norm_type = c.norm_type;
     sp.ximg = static_cast<__half*>(m->ximg.p);
     sp.ntiles = (B * F + 127) / 128;
@@ -556,6 +560,7 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
             ta.p[b].fc2_w = P(m, p + ".fc2.weight"); ta.p[b].fc2_b = P(m, p + ".fc2.bias");
         }
         ta.out = static_cast<float*>(m->fbin.p);
+        ta.scale = static_cast<float*>(m->tsse_scale.p);
         if (m->tcn5) { ta.out_tm = static_cast<float*>(m->x0.p); ta.Cp = m->Cp; }
         if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE) {
             NormLaunch na{};
@@ -565,7 +570,7 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
             for (int b = 0; b < 3; ++b) ta.x[b] = static_cast<const float*>(m->xn.p) + (size_t)b * B * F * Tp;
             ta.T = Tp; ta.prenorm = 1;                                  // padded frames are part of the normalised signal
         }
-        launch_tsse_norm(ta, s); m->launches++;
+        launch_tsse_norm(ta, s); m->launches += 2;
 
         const int Z = 3 * B;
         double* stats = static_cast<double*>(m->stats.p);
@@ -674,6 +679,7 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
         TsseLaunch ta{};
         ta.x[0] = d_mag; ta.nbranch = 1; ta.B = B; ta.F = F; ta.T = T; ta.Tp = Tp; ta.P = Pp; ta.attention = 0;
         ta.out = static_cast<float*>(m->fbin.p);
+        ta.scale = static_cast<float*>(m->tsse_scale.p);
         if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE) {
             NormLaunch na{};
             na.x[0] = d_mag; na.y = static_cast<float*>(m->xn.p);
@@ -681,7 +687,7 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
             launch_input_norm(na, s); m->launches++;
             ta.x[0] = static_cast<const float*>(m->xn.p); ta.T = Tp; ta.prenorm = 1;
         }
-        launch_tsse_norm(ta, s); m->launches++;
+        launch_tsse_norm(ta, s); m->launches += 2;
         launch_pad_copy(d_mag, static_cast<float*>(m->magpad.p), B, F, T, Pp, s); m->launches++;
         const int Ipad = (F + 15) / 16 * 16, rows_pad = (B + 63) / 64 * 64;
         launch_fb_pack(static_cast<const float*>(m->fbin.p), static_cast<__half*>(m->fbx.p), B, F, Tp, Pp, rows_pad, Ipad, s); m->launches++;
@@ -724,7 +730,7 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
         sp.nfb = 1;
         sp.fb[0] = static_cast<const float*>(m->fbout.p);
     }
-    launch_sb_stats(sp, s); m->launches++;
+    launch_sb_stats(sp, s); m->launches += 2;
     launch_sb_pack(sp, s); m->launches++;
     const int evi = (int)(m->nfwd % fsn_model::NEV);
     cudaEventRecord(m->ev0[evi], s);

@@ -23,6 +23,7 @@ struct TsseLaunch {
     int ksz[3];
     int attention;             // 0: norm only (fullsubnet.Model), 1: norm + TSSE
     float* out;                // [nbranch, B, F, P]
+    float* scale;              // [nbranch, B, F] per-row scale handed from the statistics kernel to the apply kernel
     int prenorm;               // 1: input is already normalised (input_norm_kernel), skip the utterance-mean division
     float* out_tm; int Cp;     // optional time-major copy [(branch, b, t), Cp] for the tcgen05 TCN (pad columns stay zero)
 };
@@ -74,6 +75,7 @@ struct SbPackLaunch {
     int B, F, Tp, Ns, Nf;    // neighbours
     float* mu;               // [B] utterance mean of the concatenated sub-band input
     float* sigma;            // [B] unbiased std (offline_gaussian_norm only)
+    float* rowsum;           // [B, 1 + nfb, F, 2] scratch: row sums and sums of squares
     int norm_type;           // FSN_NORM_*
     __half* ximg;            // [ntiles, Tp, 128 rows, 64 halves] SWIZZLE_128B images
     int ntiles;

@@ -61,7 +61,6 @@ __global__ void __launch_bounds__(256) tsse_norm_kernel(TsseLaunch a) {
     }
     __syncthreads();
     const float inv = s_inv;
-    float* out = a.out + ((size_t)br * a.B + b) * F * a.P;
 
     if (a.attention) {
         const TsseParams& p = a.p[br];
@@ -98,35 +97,41 @@ __global__ void __launch_bounds__(256) tsse_norm_kernel(TsseLaunch a) {
         }
         __syncthreads();
     }
+    // per-row scale (gate * 1/(mean + 1e-5)); the bulk multiply + time-major transpose runs in tsse_apply_kernel on the whole GPU
+    for (int f = threadIdx.x; f < F; f += blockDim.x) a.scale[((size_t)br * a.B + b) * F + f] = a.attention ? gate[f] * inv : inv;
+}
+
+// out[z][f][t] = x[z][f][t] * scale[z][f] (zero in the look-ahead pad) in both layouts; one CTA per 32 x 32 tile.
+__global__ void __launch_bounds__(256) tsse_apply_kernel(TsseLaunch a) {
     __shared__ float tr[32][33];
-    float* otm = a.out_tm ? a.out_tm + ((size_t)br * a.B + b) * (size_t)Tp * a.Cp : nullptr;
-    for (int f0 = 0; f0 < F; f0 += 32) {
-        for (int t0 = 0; t0 < a.P; t0 += 32) {
-            for (int rr = warp; rr < 32; rr += nwarp) {
-                const int f = f0 + rr, t = t0 + lane;
-                float v = 0.f;
-                if (f < F && t < a.P) {
-                    const float g = a.attention ? gate[f] * inv : inv;
-                    v = (t < T) ? x[(size_t)f * T + t] * g : 0.f;
-                    out[(size_t)f * a.P + t] = v;
-                }
-                tr[rr][lane] = v;
-            }
-            __syncthreads();
-            if (otm)
-                for (int rr = warp; rr < 32; rr += nwarp) {
-                    const int t = t0 + rr, f = f0 + lane;
-                    if (t < Tp && f < F) otm[(size_t)t * a.Cp + f] = tr[lane][rr];
-                }
-            __syncthreads();
+    const int z = blockIdx.z, br = z / a.B, b = z % a.B, F = a.F, T = a.T, Tp = a.Tp;
+    const int f0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* x = a.x[br] + (size_t)b * F * T;
+    float* out = a.out + (size_t)z * F * a.P;
+    float* otm = a.out_tm ? a.out_tm + (size_t)z * Tp * a.Cp : nullptr;
+    for (int rr = warp; rr < 32; rr += 8) {
+        const int f = f0 + rr, t = t0 + lane;
+        float v = 0.f;
+        if (f < F && t < a.P) {
+            v = (t < T) ? x[(size_t)f * T + t] * a.scale[(size_t)z * F + f] : 0.f;
+            out[(size_t)f * a.P + t] = v;
         }
+        tr[rr][lane] = v;
     }
+    __syncthreads();
+    if (otm)
+        for (int rr = warp; rr < 32; rr += 8) {
+            const int t = t0 + rr, f = f0 + lane;
+            if (t < Tp && f < F) otm[(size_t)t * a.Cp + f] = tr[lane][rr];
+        }
 }
 
 void launch_tsse_norm(const TsseLaunch& a, cudaStream_t s) {
     size_t smem = sizeof(float) * ((size_t)a.F * (3 + 2 * TSSE_KMAX) + a.F / 2 + 8);
     cudaFuncSetAttribute(tsse_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     tsse_norm_kernel<<<dim3(a.B, a.nbranch), 256, smem, s>>>(a);
+    tsse_apply_kernel<<<dim3((a.P + 31) / 32, (a.F + 31) / 32, a.B * a.nbranch), 256, 0, s>>>(a);
 }
 
 
@@ -372,33 +377,36 @@ void launch_dwconv(const DwLaunch& a, cudaStream_t s) {
 // values are written once, in fp16, directly in the per-step 128-row tile images the LSTM kernels
 // stream (K-major, SWIZZLE_128B, 64 halves per row; columns >= I and rows >= B*F are zero).
 // =============================================================================================
+// row sums (and sums of squares) of the window source and the full-band outputs: one warp per row, the whole GPU
+__global__ void __launch_bounds__(256) sb_rowsum_kernel(SbPackLaunch a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int F = a.F, Tp = a.Tp, nsrc = 1 + a.nfb;
+    const int r = blockIdx.x * 8 + warp;                       // (b, which, f)
+    if (r >= a.B * nsrc * F) return;
+    const int b = r / (nsrc * F), which = (r / F) % nsrc, f = r % F;
+    const float* row = (which == 0) ? a.win + ((size_t)b * F + f) * a.Pw
+                                    : ((which == 1) ? a.fb[0] : (which == 2) ? a.fb[1] : a.fb[2]) + ((size_t)b * F + f) * a.P;
+    float acc = 0.f, acq = 0.f;
+    for (int t = lane; t < Tp; t += 32) { const float v = row[t]; acc += v; acq = fmaf(v, v, acq); }
+    acc = warp_sum(acc); acq = warp_sum(acq);
+    if (lane == 0) { a.rowsum[2 * (size_t)r] = acc; a.rowsum[2 * (size_t)r + 1] = acq; }
+}
+
 __global__ void __launch_bounds__(256) sb_stats_kernel(SbPackLaunch a) {
-    extern __shared__ float sm[];
-    const int b = blockIdx.x, F = a.F, Tp = a.Tp;
-    const int nrow = F * (1 + a.nfb);
-    float* S1 = sm;                 // [1 + nfb][F] row sums
-    float* S2 = sm + nrow;          // [1 + nfb][F] row sums of squares
+    const int b = blockIdx.x, F = a.F, Tp = a.Tp, nsrc = 1 + a.nfb;
     __shared__ double red[16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    for (int r = warp; r < nrow; r += nwarp) {
-        const int which = r / F, f = r % F;
-        const float* row = (which == 0) ? a.win + ((size_t)b * F + f) * a.Pw : a.fb[which - 1] + ((size_t)b * F + f) * a.P;
-        float acc = 0.f, acq = 0.f;
-        for (int t = lane; t < Tp; t += 32) { const float v = row[t]; acc += v; acq = fmaf(v, v, acq); }
-        acc = warp_sum(acc); acq = warp_sum(acq);
-        if (lane == 0) { S1[r] = acc; S2[r] = acq; }
-    }
-    __syncthreads();
+    const float* S = a.rowsum + (size_t)b * nsrc * F * 2;        // [which][f][2]
     double tot = 0.0, tq = 0.0;
     const int nw = 2 * a.Ns + 1, nf = 2 * a.Nf + 1;
     for (int e = threadIdx.x; e < F * nw; e += blockDim.x) {
         const int i = reflect_idx(e / nw + e % nw - a.Ns, F);
-        tot += (double)S1[i]; tq += (double)S2[i];
+        tot += (double)S[2 * i]; tq += (double)S[2 * i + 1];
     }
     for (int k = 0; k < a.nfb; ++k)
         for (int e = threadIdx.x; e < F * nf; e += blockDim.x) {
             const int i = (k + 1) * F + reflect_idx(e / nf + e % nf - a.Nf, F);
-            tot += (double)S1[i]; tq += (double)S2[i];
+            tot += (double)S[2 * i]; tq += (double)S[2 * i + 1];
         }
     tot = warp_sum_d(tot); tq = warp_sum_d(tq);
     if (lane == 0) { red[warp] = tot; red[8 + warp] = tq; }
@@ -413,7 +421,8 @@ __global__ void __launch_bounds__(256) sb_stats_kernel(SbPackLaunch a) {
 }
 
 void launch_sb_stats(const SbPackLaunch& a, cudaStream_t s) {
-    sb_stats_kernel<<<a.B, 256, sizeof(float) * 2 * a.F * (1 + a.nfb), s>>>(a);
+    sb_rowsum_kernel<<<(a.B * (1 + a.nfb) * a.F + 7) / 8, 256, 0, s>>>(a);
+    sb_stats_kernel<<<a.B, 256, 0, s>>>(a);
 }
 
 // One CTA = (sample, 32 consecutive bins, 32 frames).  The window source rows [f0 - Ns, f0 + 31 + Ns] (reflected) and the

@@ -327,3 +327,35 @@ def test_streaming_step_api_matches_offline(built_lib, norm):
     e_off, e_ref = O.rel_l2(got.cpu().numpy(), offline.cpu().numpy()), O.rel_l2(got.cpu().numpy(), ref)
     print(f"\n[streaming {norm}] vs offline {e_off:.2e}  vs oracle {e_ref:.2e}")
     assert e_off < 1e-4 and e_ref < MASK_TOL      # offline scan sums squares in fp32 per column, the step API in fp64
+
+
+def test_large_batch_multiple_waves_and_long_sequence(built_lib):
+    """More CTA pairs than SMs (B*F = 167*33 rows... small F keeps the oracle cheap; 5511 rows = 44 tiles) is covered by
+    the full-size test; here: (a) odd tile count + a batch whose last pair is half empty, (b) a long sequence (T = 400) on
+    FullSubNet+, both against the oracle."""
+    cfg = small_cfg(64)
+    params = O.make_params_plus(cfg, seed=8)
+    for (B, T) in ((35, 12), (2, 400)):                     # 35*33 = 1155 rows = 10 tiles (pad to 5 pairs) ; long T
+        mag, real, imag = small_inputs(B, 33, T, 11)
+        ref = O.fullsubnet_plus_forward(params, cfg, mag, real, imag)
+        m = build_plus(cfg, params)
+        with torch.no_grad():
+            out = m(_t(mag), _t(real), _t(imag))
+        err = O.rel_l2(out.cpu().numpy(), ref)
+        print(f"\n[B={B} T={T}] cIRM rel-L2 {err:.3e}")
+        assert err < MASK_TOL
+
+
+def test_default_config_batch_130(built_lib, golden):
+    """B = 130 clips at the default geometry: 33 410 rows = 262 tiles = 131 CTA pairs (> 74 resident pairs, two waves)."""
+    g = golden("plus_default")
+    cfg = O.default_plus_config()
+    m = build_plus(cfg, O.make_params_plus(cfg, seed=0))
+    B = 130
+    rep = lambda x: np.repeat(x, B, axis=0)
+    with torch.no_grad():
+        out = m(_t(rep(g["mag"])), _t(rep(g["real"])), _t(rep(g["imag"])))
+    assert out.shape == (B, 2, 257, 188)
+    for i in (0, 64, 129):
+        assert O.rel_l2(out[i:i + 1].cpu().numpy(), g["out"]) < MASK_TOL
+    assert O.rel_l2(out[129].cpu().numpy(), out[0].cpu().numpy()) < 1e-5
