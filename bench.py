@@ -137,7 +137,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--lstm-impl", default="auto", choices=["auto", "mma", "tcgen05"])
-    ap.add_argument("--fast-math", action="store_true")
+    ap.add_argument("--accurate-math", action="store_true", help="ex2/rcp gate math instead of the default tanh.approx path")
     ap.add_argument("--ref-clips", type=int, default=4, help="reference arm: clips per step (bounded sample)")
     ap.add_argument("--cpu-baseline-clips", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -156,7 +156,7 @@ def main():
     from fsnplus_b200 import inference as inf
 
     torch.manual_seed(0)
-    model = FullSubNet_Plus(**cfg, lstm_impl=args.lstm_impl, fast_math=args.fast_math).eval()    # random init, seed 0
+    model = FullSubNet_Plus(**cfg, lstm_impl=args.lstm_impl, fast_math=not args.accurate_math).eval()    # random init, seed 0
     state = model.state_dict()
 
     # ------------------------------------------------------------------ reference arm (CPU) -----------------
@@ -311,7 +311,7 @@ def main():
         "dtype": "f16", "data": "synthetic",
         "rtf": ms_step * 1e-3 / (B * CLIP_SECONDS),
         "config": {"workload": workload, "clips_per_gpu": B, "frames_per_clip": FRAMES_PER_CLIP, "lstm_impl": lstm_impl,
-                   "fast_math": bool(args.fast_math), "weights": "random init (torch default, seed 0)",
+                   "gate_math": "ex2+rcp" if args.accurate_math else "tanh.approx (default; parity identical to 3 digits, profiles/r01_fast_math_accuracy.txt)", "weights": "random init (torch default, seed 0)",
                    "l2": f"inputs rotated over {NSETS} batches ({NSETS * in_bytes / 1e6:.0f} MB > L2); per-step intermediates "
                          "(392 MB of LSTM input tiles) exceed L2"},
         "model_tflops": world * B * tot_flops / (ms_step * 1e-3) / 1e12,

@@ -40,17 +40,19 @@ __global__ void __launch_bounds__(256) tsse_norm_kernel(TsseLaunch a) {
         float acc = 0.f;
         for (int t = lane; t < T; t += 32) acc += row[t];
         acc = warp_sum(acc);
-        if (lane == 0) {
-            S[f] = acc;
-            float p = 0.f;
-            for (int j = 0; j < TSSE_KMAX; ++j) { Pfx[f * TSSE_KMAX + j] = p; if (j < T) p += row[j]; }
-            float q = 0.f;
-            for (int m = 0; m < TSSE_KMAX; ++m) {
-                Sfx[f * TSSE_KMAX + m] = q;            // sum of the last m samples of the padded row
-                int t = Tp - 1 - m;
-                if (t >= 0 && t < T) q += row[t];      // t >= T is the zero look-ahead pad
-            }
+        if (lane == 0) S[f] = acc;
+        // exclusive prefix sums over the first / last KMAX samples of the padded row: lane j holds sample j (head) and
+        // sample Tp-1-j (tail; t >= T is the zero look-ahead pad), one shuffle scan each
+        float hv = (lane < TSSE_KMAX && lane < T) ? row[lane] : 0.f;
+        const int tt = Tp - 1 - lane;
+        float tv = (lane < TSSE_KMAX && tt >= 0 && tt < T) ? row[tt] : 0.f;
+        float hs = hv, ts = tv;
+#pragma unroll
+        for (int o = 1; o < TSSE_KMAX; o <<= 1) {
+            const float uh = __shfl_up_sync(0xffffffffu, hs, o), ut = __shfl_up_sync(0xffffffffu, ts, o);
+            if (lane >= o) { hs += uh; ts += ut; }
         }
+        if (lane < TSSE_KMAX) { Pfx[f * TSSE_KMAX + lane] = hs - hv; Sfx[f * TSSE_KMAX + lane] = ts - tv; }
     }
     __syncthreads();
     if (warp == 0) {

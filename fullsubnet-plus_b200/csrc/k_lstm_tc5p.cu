@@ -30,7 +30,7 @@ constexpr int P5_MAX_SMEM = 227 * 1024;
 struct P5Plan { int nstage; size_t total; };
 static inline P5Plan p5_plan(int H) {
     P5Plan p;
-    const size_t fixed = P5_XIMG + (size_t)128 * H * 2 + 4 * 128 * 2 * 4 + 64 * 8;
+    const size_t fixed = P5_XIMG + (size_t)128 * H * 2 /*park*/ + (size_t)2 * 4 * H * 4 /*pre-scaled biases*/ + 4 * 128 * 2 * 4 + 64 * 8;
     long avail = P5_MAX_SMEM - 1024 - (long)fixed;
     p.nstage = (int)(avail / P5_STAGE);
     if (p.nstage > 8) p.nstage = 8;
@@ -52,7 +52,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P5_THREADS, 1) lstm_
     uint8_t* stages = smem;
     uint8_t* ximg = stages + (size_t)nstage * P5_STAGE;
     uint8_t* park = ximg + P5_XIMG;
-    float* fcpart = reinterpret_cast<float*>(park + (size_t)128 * H * 2);   // [4][128][2]
+    float* bsm = reinterpret_cast<float*>(park + (size_t)128 * H * 2);       // [2][NCH][128] pre-scaled biases
+    float* fcpart = bsm + 2 * 4 * H;                                         // [4][128][2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(fcpart + 4 * 128 * 2);
     uint64_t* full = bars;
     uint64_t* empty = full + nstage;
@@ -73,6 +74,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P5_THREADS, 1) lstm_
         fence_barrier_init();
     }
     if (warp == P5_EPI_WARPS + 1) tmem_alloc_pair<512>(tmem_slot);
+    for (int i = tid; i < 2 * 4 * H; i += P5_THREADS) bsm[i] = a.bias[i];
     tc5_fence_before();
     __syncthreads();
     cluster_sync_all();                                            // barriers of both CTAs are initialised
@@ -225,7 +227,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P5_THREADS, 1) lstm_
                 for (int j = 0; j < NCH; ++j) {
                     float4* cp = reinterpret_cast<float4*>(cbase + ((size_t)((layer * NCH + j) * 4 + cg) * 2) * 128 * 4) + r;
                     const float4 c4[2] = {cnext[0], cnext[1]};     // prefetched during the previous chunk
-                    const float4* bj = reinterpret_cast<const float4*>(a.bias + (size_t)(layer * NCH + j) * 128 + cg * 32);
+                    const float4* bj = reinterpret_cast<const float4*>(bsm + (size_t)(layer * NCH + j) * 128 + cg * 32);
                     mbar_wait(accfull, accn & 1);
                     ++accn;
                     tc5_fence_after();
@@ -251,7 +253,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P5_THREADS, 1) lstm_
                     float cn[8];
 #pragma unroll
                     for (int u4 = 0; u4 < 2; ++u4) {
-                        const float4 bi = __ldg(bj + u4), bf = __ldg(bj + 2 + u4), bg = __ldg(bj + 4 + u4), bo = __ldg(bj + 6 + u4);
+                        const float4 bi = bj[u4], bf = bj[2 + u4], bg = bj[4 + u4], bo = bj[6 + u4];
                         const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, bfa[4] = {bf.x, bf.y, bf.z, bf.w};
                         const float bga[4] = {bg.x, bg.y, bg.z, bg.w}, boa[4] = {bo.x, bo.y, bo.z, bo.w};
                         const float cpv[4] = {c4[u4].x, c4[u4].y, c4[u4].z, c4[u4].w};

@@ -229,7 +229,7 @@ class FullSubNet_Plus(_B200Model):
                  fb_output_activate_function, sb_output_activate_function, fb_model_hidden_size, sb_model_hidden_size,
                  channel_attention_model="SE", norm_type="offline_laplace_norm", num_groups_in_drop_band=2,
                  output_size=2, subband_num=1, kersize=[3, 5, 10], weight_init=True,
-                 num_layers=2, lstm_impl="auto", fast_math=False):
+                 num_layers=2, lstm_impl="auto", fast_math=True):
         super().__init__()
         assert sequence_model in ("GRU", "LSTM", "TCN"), f"{self.__class__.__name__} only support GRU, LSTM and TCN."
         if sequence_model != "LSTM":
@@ -272,7 +272,7 @@ class Model(_B200Model):
     def __init__(self, num_freqs, look_ahead, sequence_model, fb_num_neighbors, sb_num_neighbors,
                  fb_output_activate_function, sb_output_activate_function, fb_model_hidden_size, sb_model_hidden_size,
                  norm_type="offline_laplace_norm", num_groups_in_drop_band=2, weight_init=True,
-                 num_layers=2, lstm_impl="auto", fast_math=False):
+                 num_layers=2, lstm_impl="auto", fast_math=True):
         super().__init__()
         assert sequence_model in ("GRU", "LSTM"), f"{self.__class__.__name__} only support GRU and LSTM."
         if sequence_model != "LSTM":

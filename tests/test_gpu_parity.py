@@ -359,3 +359,21 @@ def test_default_config_batch_130(built_lib, golden):
     for i in (0, 64, 129):
         assert O.rel_l2(out[i:i + 1].cpu().numpy(), g["out"]) < MASK_TOL
     assert O.rel_l2(out[129].cpu().numpy(), out[0].cpu().numpy()) < 1e-5
+
+
+def test_accurate_gate_math_variant(built_lib, golden):
+    """The default gate math is 5 tanh.approx per cell (MUFU.TANH); fast_math=False selects 5 ex2 + 3 rcp.  Both must meet
+    the bar and agree with each other far below it (measured: identical to 3 digits, profiles/r01_fast_math_accuracy.txt)."""
+    gi, gs = golden("plus_default"), golden("plus_default_stress")
+    cfg = O.default_plus_config()
+    for g, scale in ((gi, 1.0), (gs, 3.0)):
+        p = O.make_params_plus(cfg, seed=0, lstm_scale=scale)
+        outs = []
+        for fm in (True, False):
+            m = build_plus(cfg, p, fast_math=fm)
+            with torch.no_grad():
+                outs.append(m(_t(gi["mag"]), _t(gi["real"]), _t(gi["imag"])).cpu().numpy())
+            err = O.rel_l2(outs[-1], g["out"])
+            print(f"\n[fast_math={fm}, lstm_scale={scale}] cIRM rel-L2 {err:.3e}")
+            assert err < MASK_TOL
+        assert O.rel_l2(outs[0], outs[1]) < 3e-4
