@@ -88,13 +88,13 @@ struct fsn_model {
 // ---------------------------------------------------------------------------------------------
 static void add(std::vector<ParamSpec>& v, const std::string& k, int64_t n) { v.push_back({k, n}); }
 
-static void lstm_specs(std::vector<ParamSpec>& v, const std::string& pre, int I, int H, int L, int O) {
-    for (int l = 0; l < L; ++l) {
+static void lstm_specs(std::vector<ParamSpec>& v, const std::string& pre, int I, int H, int L, int O, int G) {
+    for (int l = 0; l < L; ++l) {                                   // G = 4 gate blocks for nn.LSTM, 3 for nn.GRU
         const std::string s = std::to_string(l);
-        add(v, pre + ".sequence_model.weight_ih_l" + s, (int64_t)4 * H * (l == 0 ? I : H));
-        add(v, pre + ".sequence_model.weight_hh_l" + s, (int64_t)4 * H * H);
-        add(v, pre + ".sequence_model.bias_ih_l" + s, 4 * H);
-        add(v, pre + ".sequence_model.bias_hh_l" + s, 4 * H);
+        add(v, pre + ".sequence_model.weight_ih_l" + s, (int64_t)G * H * (l == 0 ? I : H));
+        add(v, pre + ".sequence_model.weight_hh_l" + s, (int64_t)G * H * H);
+        add(v, pre + ".sequence_model.bias_ih_l" + s, G * H);
+        add(v, pre + ".sequence_model.bias_hh_l" + s, G * H);
     }
     add(v, pre + ".fc_output_layer.weight", (int64_t)O * H);
     add(v, pre + ".fc_output_layer.bias", O);
@@ -109,12 +109,15 @@ static void build_specs(fsn_model* m) {
         const char* cn[3] = {"smallConv1d", "middleConv1d", "largeConv1d"};
         for (int b = 0; b < 3; ++b) {
             const std::string p = std::string("channel_attention") + sfx[b];
-            for (int i = 0; i < 3; ++i) {
-                add(v, p + "." + cn[i] + ".0.weight", (int64_t)F * c.kersize[i]);
-                add(v, p + "." + cn[i] + ".0.bias", F);
+            if (c.channel_attention == FSN_ATTN_ECA) { add(v, p + ".conv.weight", 3); continue; }
+            if (c.channel_attention == FSN_ATTN_TSSE) {
+                for (int i = 0; i < 3; ++i) {
+                    add(v, p + "." + cn[i] + ".0.weight", (int64_t)F * c.kersize[i]);
+                    add(v, p + "." + cn[i] + ".0.bias", F);
+                }
+                add(v, p + ".feature_concate_fc.weight", 3);
+                add(v, p + ".feature_concate_fc.bias", 1);
             }
-            add(v, p + ".feature_concate_fc.weight", 3);
-            add(v, p + ".feature_concate_fc.bias", 1);
             add(v, p + ".fc1.weight", (int64_t)(F / 2) * F);
             add(v, p + ".fc1.bias", F / 2);
             add(v, p + ".fc2.weight", (int64_t)F * (F / 2));
@@ -142,10 +145,10 @@ static void build_specs(fsn_model* m) {
         }
         m->Isb = (2 * c.sb_num_neighbors + 1) + 3 * (2 * c.fb_num_neighbors + 1);
     } else {
-        lstm_specs(v, "fb_model", F, c.fb_hidden, c.num_layers, F);
+        lstm_specs(v, "fb_model", F, c.fb_hidden, c.num_layers, F, c.rnn_type == FSN_RNN_GRU ? 3 : 4);
         m->Isb = (2 * c.sb_num_neighbors + 1) + (2 * c.fb_num_neighbors + 1);
     }
-    lstm_specs(v, "sb_model", m->Isb, c.sb_hidden, c.num_layers, c.output_size);
+    lstm_specs(v, "sb_model", m->Isb, c.sb_hidden, c.num_layers, c.output_size, c.rnn_type == FSN_RNN_GRU ? 3 : 4);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -178,6 +181,39 @@ static int upload(DevBuf& b, const void* src, size_t bytes) {
     int e = b.ensure(bytes, false);
     if (e) return e;
     return (int)cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice);
+}
+
+// nn.GRU (sequence_model.py:39-46) on the LSTM kernels: rewrite the (r, z, n) parameters as four pseudo-gate blocks
+//   r: [W_ir | W_hr], z: [W_iz | W_hz], n_x: [W_in | 0], n_h: [0 | W_hn]   (biases alike)
+// in the nn.LSTM layout; the expanded arrays replace the originals in m->host, so every packer downstream is unchanged.
+static void expand_gru(fsn_model* m, const std::string& pre, int I, int H, int L) {
+    for (int l = 0; l < L; ++l) {
+        const std::string s = std::to_string(l);
+        const int K = (l == 0) ? I : H;
+        auto& wi = m->host[pre + ".sequence_model.weight_ih_l" + s];
+        auto& wh = m->host[pre + ".sequence_model.weight_hh_l" + s];
+        auto& bi = m->host[pre + ".sequence_model.bias_ih_l" + s];
+        auto& bh = m->host[pre + ".sequence_model.bias_hh_l" + s];
+        // each array is expanded on its own size, so a later fsn_model_set_param of a single key re-expands just that key
+        if (wi.size() == (size_t)3 * H * K) {                       // r, z, n_x input blocks; the n_h input block stays zero
+            std::vector<float> w4((size_t)4 * H * K, 0.f);
+            std::copy(wi.begin(), wi.end(), w4.begin());
+            wi.swap(w4);
+        }
+        if (wh.size() == (size_t)3 * H * H) {                       // r, z recurrent blocks; n_x recurrent block zero; n_h <- W_hn
+            std::vector<float> w4((size_t)4 * H * H, 0.f);
+            std::copy(wh.begin(), wh.begin() + (size_t)2 * H * H, w4.begin());
+            std::copy(wh.begin() + (size_t)2 * H * H, wh.end(), w4.begin() + (size_t)3 * H * H);
+            wh.swap(w4);
+        }
+        if (bi.size() == (size_t)3 * H) { bi.resize((size_t)4 * H, 0.f); }
+        if (bh.size() == (size_t)3 * H) {
+            std::vector<float> b4((size_t)4 * H, 0.f);
+            std::copy(bh.begin(), bh.begin() + 2 * H, b4.begin());
+            std::copy(bh.begin() + 2 * H, bh.end(), b4.begin() + 3 * H);
+            bh.swap(b4);
+        }
+    }
 }
 
 static int pack_lstm(fsn_model* m, const std::string& pre, int I, int Ipad, int H, int L, DevBuf* frag, DevBuf* bias) {
@@ -289,10 +325,13 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     if (c.sb_hidden % 16 || c.sb_hidden < 16) return fail(FSN_EINVAL, "sb_model_hidden_size must be a multiple of 16");
     if (c.model_kind == FSN_KIND_FSN && (c.fb_hidden % 16 || c.fb_hidden < 16)) return fail(FSN_EINVAL, "fb_model_hidden_size must be a multiple of 16");
     if (c.output_size < 1 || c.output_size > 8) return fail(FSN_EINVAL, "output_size must be 1..8");
+    if (c.rnn_type != FSN_RNN_LSTM && c.rnn_type != FSN_RNN_GRU) return fail(FSN_EINVAL, "unknown rnn_type %d", c.rnn_type);
     if (c.norm_type < FSN_NORM_OFFLINE_LAPLACE || c.norm_type > FSN_NORM_CUMULATIVE_LAYER) return fail(FSN_EINVAL, "unknown norm_type %d", c.norm_type);
-    if (c.model_kind == FSN_KIND_PLUS)
+    if (c.model_kind == FSN_KIND_PLUS) {
+        if (c.channel_attention < FSN_ATTN_TSSE || c.channel_attention > FSN_ATTN_ECA) return fail(FSN_EINVAL, "unknown channel_attention %d", c.channel_attention);
         for (int i = 0; i < 3; ++i)
-            if (c.kersize[i] < 1 || c.kersize[i] > 16) return fail(FSN_EINVAL, "kersize must be in 1..16");
+            if (c.channel_attention == FSN_ATTN_TSSE && (c.kersize[i] < 1 || c.kersize[i] > 16)) return fail(FSN_EINVAL, "kersize must be in 1..16");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FSN_ECUDA, "no CUDA device: fsnplus_b200 has no CPU fallback");
     fsn_model* m = new fsn_model();
@@ -340,20 +379,24 @@ extern "C" int fsn_model_set_param(fsn_model* m, const char* key, const float* h
 
 extern "C" int fsn_model_finalize(fsn_model* m) {
     if (!m) return fail(FSN_EINVAL, "null model");
-    size_t total = 0;
-    for (const auto& s : m->specs) {
+    const fsn_config& c = m->cfg;
+    for (const auto& s : m->specs)
         if (!m->host.count(s.key)) return fail(FSN_ESTATE, "missing parameter %s", s.key.c_str());
-        total += ((size_t)s.numel * 4 + 255) & ~(size_t)255;
+    if (c.rnn_type == FSN_RNN_GRU) {
+        expand_gru(m, "sb_model", m->Isb, c.sb_hidden, c.num_layers);
+        if (c.model_kind == FSN_KIND_FSN) expand_gru(m, "fb_model", c.num_freqs, c.fb_hidden, c.num_layers);
     }
+    size_t total = 0;
+    for (const auto& s : m->specs) total += (m->host[s.key].size() * 4 + 255) & ~(size_t)255;
     if (m->arena.ensure(total, false)) return fail(FSN_ECUDA, "cudaMalloc of %zu bytes failed", total);
     size_t off = 0;
     for (const auto& s : m->specs) {
+        const auto& hv = m->host[s.key];
         float* d = reinterpret_cast<float*>(static_cast<char*>(m->arena.p) + off);
-        CK(cudaMemcpy(d, m->host[s.key].data(), (size_t)s.numel * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d, hv.data(), hv.size() * 4, cudaMemcpyHostToDevice));
         m->dev[s.key] = d;
-        off += ((size_t)s.numel * 4 + 255) & ~(size_t)255;
+        off += (hv.size() * 4 + 255) & ~(size_t)255;
     }
-    const fsn_config& c = m->cfg;
     if (pack_lstm(m, "sb_model", m->Isb, 64, c.sb_hidden, c.num_layers, m->sb_frag, m->sb_bias)) return fail(FSN_ECUDA, "packing sb_model failed");
     if (c.model_kind == FSN_KIND_FSN) {
         const int Ipad = (c.num_freqs + 15) / 16 * 16;
@@ -377,7 +420,8 @@ extern "C" int fsn_model_finalize(fsn_model* m) {
                 for (int n = 0; n < 128; ++n) {
                     const int row = fsn_tc5_gate_row(H, j, n);
                     // stored pre-scaled: the kernel evaluates exp2(-log2e * (acc + b)) as one FMA (tanh gate: -2 log2e)
-                    const float sc = ((n % 32) / 8 == 2) ? -2.8853900817779268f : -1.4426950408889634f;
+                    const int q = (n % 32) / 8;                        // gate position: i,f,g,o / GRU pseudo-gates r,z,n_x,n_h
+                    const float sc = (q == 2 || (q == 3 && c.rnn_type == FSN_RNN_GRU)) ? -2.8853900817779268f : -1.4426950408889634f;
                     bp[(size_t)l * 4 * H + j * 128 + n] = sc * (bi[row] + bh[row]);
                 }
         }
@@ -401,7 +445,7 @@ static void fill_ws(fsn_model* m, LstmWsLaunch& w) {
         w.w_ih[l] = P(m, "fb_model.sequence_model.weight_ih_l" + s); w.w_hh[l] = P(m, "fb_model.sequence_model.weight_hh_l" + s);
         w.b_ih[l] = P(m, "fb_model.sequence_model.bias_ih_l" + s); w.b_hh[l] = P(m, "fb_model.sequence_model.bias_hh_l" + s);
     }
-    w.L = c.num_layers; w.H = c.fb_hidden; w.I = c.num_freqs; w.Ipad = (c.num_freqs + 15) / 16 * 16; w.fast = c.fast_math;
+    w.L = c.num_layers; w.H = c.fb_hidden; w.I = c.num_freqs; w.Ipad = (c.num_freqs + 15) / 16 * 16; w.fast = c.fast_math; w.gru = c.rnn_type == FSN_RNN_GRU;
 }
 
 static int ensure_ws(fsn_model* m, int B, int T) {
@@ -487,12 +531,13 @@ static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s)
         a.H = c.sb_hidden; a.I = m->Isb; a.rows = rows; a.Tp = Tp;
         a.img = static_cast<const __half*>(m->ximg.p); a.ntiles = ntiles;
         a.cstate = static_cast<float*>(m->cstate.p);
-        a.out = d_out; a.F = F; a.la = c.look_ahead; a.fast = c.fast_math;
+        a.out = d_out; a.F = F; a.la = c.look_ahead; a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU;
         { const char* ev = getenv("FSN_TC5_ELECT"); a.elect = ev ? atoi(ev) : 0; }
         { const char* ev = getenv("FSN_TC5_NSTAGE"); a.nstage_cap = ev ? atoi(ev) : 0; }
         { const char* ev = getenv("FSN_TC5_DEBUG"); a.debug = ev ? atoi(ev) : 0; }
         int pair = 1;
         { const char* ev = getenv("FSN_TC5_PAIR"); if (ev) pair = atoi(ev); }
+        if (a.gru) pair = 1;                                            // the GRU cell exists in the pair kernel only
         int e = pair ? launch_lstm_tc5_pair(a, s) : launch_lstm_tc5(a, s);
         if (e) return fail(FSN_ECUDA, "tcgen05 LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
     } else {
@@ -509,7 +554,7 @@ static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s)
         a.cstate = static_cast<float*>(m->cstate.p);
         lstm_mma_cstate_bytes(c.num_layers, rows, c.sb_hidden, &a.rows_alloc);
         a.out = d_out; a.O = c.output_size; a.F = F; a.la = c.look_ahead; a.act = c.sb_act;
-        a.fast = c.fast_math;
+        a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU;
         int e = launch_lstm_mma(a, s);
         if (e) return fail(FSN_ECUDA, "mma LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
     }
@@ -525,7 +570,7 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
     if (B < 1 || T < 1) return fail(FSN_EINVAL, "bad batch/frames");
     if (c.model_kind == FSN_KIND_PLUS && (!d_real || !d_imag)) return fail(FSN_EINVAL, "FullSubNet_Plus.forward needs mag, real and imag");
     const int F = c.num_freqs, Tp = T + c.look_ahead, Pp = (Tp + 3) & ~3;
-    if (c.model_kind == FSN_KIND_PLUS)
+    if (c.model_kind == FSN_KIND_PLUS && c.channel_attention == FSN_ATTN_TSSE)
         for (int i = 0; i < 3; ++i)
             if (Tp < c.kersize[i]) return fail(FSN_EINVAL, "sequence shorter than the TSSE kernel size");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -547,15 +592,18 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
         const char* cn[3] = {"smallConv1d", "middleConv1d", "largeConv1d"};
         TsseLaunch ta{};
         ta.x[0] = d_mag; ta.x[1] = d_real; ta.x[2] = d_imag;
-        ta.nbranch = 3; ta.B = B; ta.F = F; ta.T = T; ta.Tp = Tp; ta.P = Pp; ta.attention = 1;
+        ta.nbranch = 3; ta.B = B; ta.F = F; ta.T = T; ta.Tp = Tp; ta.P = Pp; ta.attention = 1 + c.channel_attention;
         for (int i = 0; i < 3; ++i) ta.ksz[i] = c.kersize[i];
         for (int b = 0; b < 3; ++b) {
             const std::string p = std::string("channel_attention") + sfx[b];
-            for (int i = 0; i < 3; ++i) {
-                ta.p[b].conv_w[i] = P(m, p + "." + cn[i] + ".0.weight");
-                ta.p[b].conv_b[i] = P(m, p + "." + cn[i] + ".0.bias");
+            if (c.channel_attention == FSN_ATTN_ECA) { ta.p[b].eca_w = P(m, p + ".conv.weight"); continue; }
+            if (c.channel_attention == FSN_ATTN_TSSE) {
+                for (int i = 0; i < 3; ++i) {
+                    ta.p[b].conv_w[i] = P(m, p + "." + cn[i] + ".0.weight");
+                    ta.p[b].conv_b[i] = P(m, p + "." + cn[i] + ".0.bias");
+                }
+                ta.p[b].cat_w = P(m, p + ".feature_concate_fc.weight"); ta.p[b].cat_b = P(m, p + ".feature_concate_fc.bias");
             }
-            ta.p[b].cat_w = P(m, p + ".feature_concate_fc.weight"); ta.p[b].cat_b = P(m, p + ".feature_concate_fc.bias");
             ta.p[b].fc1_w = P(m, p + ".fc1.weight"); ta.p[b].fc1_b = P(m, p + ".fc1.bias");
             ta.p[b].fc2_w = P(m, p + ".fc2.weight"); ta.p[b].fc2_b = P(m, p + ".fc2.bias");
         }
@@ -714,7 +762,7 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
         a.xplain = static_cast<const __half*>(m->fbx.p); a.rows_pad = rows_pad;
         a.cstate = static_cast<float*>(m->cstate.p);
         lstm_mma_cstate_bytes(c.num_layers, B, c.fb_hidden, &a.rows_alloc);
-        a.hseq = static_cast<float*>(m->hseq.p); a.P = Pp; a.fast = c.fast_math;
+        a.hseq = static_cast<float*>(m->hseq.p); a.P = Pp; a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU;
         int e = launch_lstm_mma(a, s);
         if (e) return fail(FSN_ECUDA, "full-band LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
         m->launches++;
@@ -915,7 +963,7 @@ extern "C" int fsn_stream_step(fsn_stream* st, const float* d_mag, float* d_mask
         a.L = c.num_layers; a.H = c.fb_hidden; a.I = F; a.Ipad = st->Ipad; a.rows = B; a.Tp = 1;
         a.xplain = static_cast<const __half*>(st->fbx.p); a.rows_pad = st->rows_pad;
         a.cstate = static_cast<float*>(st->c_fb.p); a.rows_alloc = st->ra_fb;
-        a.hseq = static_cast<float*>(st->hseq.p); a.P = 4; a.fast = c.fast_math;
+        a.hseq = static_cast<float*>(st->hseq.p); a.P = 4; a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU;
         a.hstate = static_cast<__half*>(st->h_fb.p); a.resume = resume;
         e = launch_lstm_mma(a, s);
     }
@@ -935,7 +983,7 @@ extern "C" int fsn_stream_step(fsn_stream* st, const float* d_mag, float* d_mask
     b.L = c.num_layers; b.H = c.sb_hidden; b.I = m->Isb; b.Ipad = 64; b.rows = B * F; b.Tp = 1;
     b.img = static_cast<const __half*>(st->ximg.p); b.ntiles = (B * F + 127) / 128;
     b.cstate = static_cast<float*>(st->c_sb.p); b.rows_alloc = st->ra_sb;
-    b.out = d_mask; b.O = c.output_size; b.F = F; b.la = 0; b.act = c.sb_act; b.fast = c.fast_math;
+    b.out = d_mask; b.O = c.output_size; b.F = F; b.la = 0; b.act = c.sb_act; b.fast = c.fast_math; b.gru = c.rnn_type == FSN_RNN_GRU;
     b.hstate = static_cast<__half*>(st->h_sb.p); b.resume = resume;
     e = launch_lstm_mma(b, s);
     if (e) return fail(FSN_ECUDA, "sub-band LSTM step failed: %s", cudaGetErrorString((cudaError_t)e));

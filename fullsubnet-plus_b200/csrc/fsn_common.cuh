@@ -260,6 +260,34 @@ __device__ __forceinline__ void lstm_cell(float ai, float af, float ag, float ao
     }
 }
 
+// One GRU cell on the same four accumulators: the GRU weights are packed as pseudo-gates (r, z, n_x, n_h) -- n_x holds
+// W_in x + b_in (zero recurrent block), n_h holds W_hn h + b_hn (zero input block) -- so every LSTM kernel computes it
+// unchanged up to this function.  nn.GRU (sequence_model.py:39-46): n = tanh(n_x + r n_h); h = (1 - z) n + z h_prev.
+// ar/az = -log2(e) * pre-activation; anx/anh = -2 log2(e) * pre-activation.  The "cell state" slot carries h in fp32.
+template <bool FAST>
+__device__ __forceinline__ void gru_cell(float ar, float az, float anx, float anh, float hprev, float& h) {
+    float r, z, n;
+    if (FAST) {
+        const float K = -0.34657359027997264f;                                // -0.5 / log2(e)
+        r = fmaf(0.5f, tanh_approx(ar * K), 0.5f);
+        z = fmaf(0.5f, tanh_approx(az * K), 0.5f);
+        n = tanh_approx(fmaf(r, anh, anx) * K);
+    } else {
+        r = rcpf(1.f + ex2f(ar));
+        z = rcpf(1.f + ex2f(az));
+        const float en = ex2f(fminf(fmaxf(fmaf(r, anh, anx), -43.f), 43.f));
+        n = (1.f - en) * rcpf(1.f + en);
+    }
+    h = fmaf(z, hprev - n, n);
+}
+// plain-argument form for the generic kernels
+template <bool FAST>
+__device__ __forceinline__ float gru_cell_plain(float gr, float gz, float gnx, float gnh, float hprev) {
+    const float r = sigm<FAST>(gr), z = sigm<FAST>(gz);
+    const float n = tanh_<FAST>(fmaf(r, gnh, gnx));
+    return fmaf(z, hprev - n, n);
+}
+
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
                  : "memory");

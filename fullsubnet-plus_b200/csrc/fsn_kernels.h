@@ -15,13 +15,14 @@ struct TsseParams {            // device pointers, one set per branch
     const float* fc1_b;        // [C/2]
     const float* fc2_w;        // [C, C/2]
     const float* fc2_b;        // [C]
+    const float* eca_w;        // [3]   ChannelECAlayer.conv.weight
 };
 struct TsseLaunch {
     const float* x[3];         // per branch input [B, F, T]
     TsseParams p[3];
     int nbranch, B, F, T, Tp, P;   // Tp = T + look_ahead, P = row pitch of the output
     int ksz[3];
-    int attention;             // 0: norm only (fullsubnet.Model), 1: norm + TSSE
+    int attention;             // 0: norm only (fullsubnet.Model), 1 + FSN_ATTN_*: norm + that channel attention
     float* out;                // [nbranch, B, F, P]
     float* scale;              // [nbranch, B, F] per-row scale handed from the statistics kernel to the apply kernel
     int prenorm;               // 1: input is already normalised (input_norm_kernel), skip the utterance-mean division
@@ -116,6 +117,7 @@ struct LstmMmaLaunch {
     // output B: top-layer h as fp32 [rows, H, P]
     float* hseq; int P;
     int fast;
+    int gru;                  // 1: pseudo-gate GRU cell (gru_cell), cstate carries h in fp32
     // streaming: hidden state carried across launches ([L, rows_alloc, H] fp16); resume = 1 continues from it
     __half* hstate; int resume;
 };
@@ -132,6 +134,7 @@ struct LstmWsLaunch {
     unsigned int* barrier;    // grid barrier counter
     float* hseq; int P;       // top-layer h as fp32 [rows, H, P]
     int fast, resume, t0;     // t0: absolute index of the first step (exchange-buffer parity)
+    int gru;                  // 1: pseudo-gate GRU cell, cbuf / cst carry h in fp32
 };
 bool lstm_ws_supported(int L, int H, int Ipad, int rows, int num_sms);
 int launch_lstm_ws(const LstmWsLaunch& a, cudaStream_t s);
@@ -148,6 +151,7 @@ struct LstmTc5Launch {
     float* cstate;            // [ntiles][2 layers][H/16 chunks][4][128][4] fp32
     float* out; int F, la;
     int fast;
+    int gru;                  // 1: pseudo-gate GRU cell (pair kernel only)
     int elect;                // tuning knob: 1 = one elected mbarrier arrive per epilogue warp, 0 = every thread arrives
     int nstage_cap;           // tuning knob: cap on the weight ring depth (0 = as many as fit)
     int debug;                // timing experiments only (results invalid): 1 = skip the cell update, 2 = MMA issuer ignores accempty

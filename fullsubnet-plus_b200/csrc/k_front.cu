@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(256) tsse_norm_kernel(TsseLaunch a) {
     float* sq = Sfx + F * TSSE_KMAX;                // [F]
     float* gate = sq + F;                           // [F]
     float* f1 = gate + F;                           // [F/2]
+    float* Mx = f1 + (F / 2 + 1);                   // [F] row max / [F] row min (CBAM squeeze)
+    float* Mn = Mx + F;
     __shared__ float s_inv;
 
     const float* x = a.x[br] + (size_t)b * F * T;
@@ -37,10 +39,12 @@ __global__ void __launch_bounds__(256) tsse_norm_kernel(TsseLaunch a) {
 
     for (int f = warp; f < F; f += nwarp) {
         const float* row = x + (size_t)f * T;
-        float acc = 0.f;
-        for (int t = lane; t < T; t += 32) acc += row[t];
+        float acc = 0.f, mx = -INFINITY, mn = INFINITY;
+        for (int t = lane; t < T; t += 32) { const float v = row[t]; acc += v; mx = fmaxf(mx, v); mn = fminf(mn, v); }
         acc = warp_sum(acc);
-        if (lane == 0) S[f] = acc;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
+        if (lane == 0) { S[f] = acc; Mx[f] = mx; Mn[f] = mn; }
         // exclusive prefix sums over the first / last KMAX samples of the padded row: lane j holds sample j (head) and
         // sample Tp-1-j (tail; t >= T is the zero look-ahead pad), one shuffle scan each
         float hv = (lane < TSSE_KMAX && lane < T) ? row[lane] : 0.f;
@@ -66,36 +70,62 @@ __global__ void __launch_bounds__(256) tsse_norm_kernel(TsseLaunch a) {
 
     if (a.attention) {
         const TsseParams& p = a.p[br];
-        for (int c = threadIdx.x; c < F; c += blockDim.x) {
-            float s = p.cat_b[0];
+        const int kind = a.attention - 1;
+        const float rT = 1.0f / (float)Tp;
+        if (kind == FSN_ATTN_TSSE) {                 // attention_model.py:78-104: three depthwise convs, time-averaged, mixed by a 3 -> 1 linear
+            for (int c = threadIdx.x; c < F; c += blockDim.x) {
+                float s = p.cat_b[0];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const int k = a.ksz[i];
-                const float rlen = 1.0f / (float)(Tp - k + 1);
-                float acc = 0.f;
-                for (int j = 0; j < k; ++j) {
-                    float wsum = S[c] - Pfx[c * TSSE_KMAX + j] - Sfx[c * TSSE_KMAX + (k - 1 - j)];
-                    acc = fmaf(p.conv_w[i][c * k + j], wsum, acc);
+                for (int i = 0; i < 3; ++i) {
+                    const int k = a.ksz[i];
+                    const float rlen = 1.0f / (float)(Tp - k + 1);
+                    float acc = 0.f;
+                    for (int j = 0; j < k; ++j) {
+                        float wsum = S[c] - Pfx[c * TSSE_KMAX + j] - Sfx[c * TSSE_KMAX + (k - 1 - j)];
+                        acc = fmaf(p.conv_w[i][c * k + j], wsum, acc);
+                    }
+                    float feat = fmaxf(fmaf(acc, inv * rlen, p.conv_b[i][c]), 0.f);
+                    s = fmaf(p.cat_w[i], feat, s);
                 }
-                float feat = fmaxf(fmaf(acc, inv * rlen, p.conv_b[i][c]), 0.f);
-                s = fmaf(p.cat_w[i], feat, s);
+                sq[c] = s;
             }
-            sq[c] = s;
+        } else {                                     // SE / CBAM / ECA squeeze: mean over the padded frames (attention_model.py:29,320,353)
+            for (int c = threadIdx.x; c < F; c += blockDim.x) {
+                sq[c] = S[c] * inv * rT;
+                // CBAM max squeeze (:321) of x * inv: the sign of inv picks max or min; the zero look-ahead pad takes part
+                float m = (inv >= 0.f) ? Mx[c] * inv : Mn[c] * inv;
+                if (Tp > T) m = fmaxf(m, 0.f);
+                Mx[c] = m;
+            }
         }
         __syncthreads();
-        const int Cr = F / 2;
-        for (int o = warp; o < Cr; o += nwarp) {
-            float acc = 0.f;
-            for (int c = lane; c < F; c += 32) acc = fmaf(p.fc1_w[(size_t)o * F + c], sq[c], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) f1[o] = fmaxf(acc + p.fc1_b[o], 0.f);
-        }
-        __syncthreads();
-        for (int o = warp; o < F; o += nwarp) {
-            float acc = 0.f;
-            for (int c = lane; c < Cr; c += 32) acc = fmaf(p.fc2_w[(size_t)o * Cr + c], f1[c], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) gate[o] = 1.0f / (1.0f + __expf(-(acc + p.fc2_b[o])));
+        if (kind == FSN_ATTN_ECA) {                  // attention_model.py:355-357: conv1d over the channel axis, k = 3, zero padding, no bias
+            const float w0 = p.eca_w[0], w1 = p.eca_w[1], w2 = p.eca_w[2];
+            for (int c = threadIdx.x; c < F; c += blockDim.x) {
+                const float y = w0 * (c > 0 ? sq[c - 1] : 0.f) + w1 * sq[c] + w2 * (c + 1 < F ? sq[c + 1] : 0.f);
+                gate[c] = 1.0f / (1.0f + __expf(-y));
+            }
+        } else {
+            const int Cr = F / 2;
+            for (int o = warp; o < Cr; o += nwarp) {
+                float acc = 0.f, acm = 0.f;
+                for (int c = lane; c < F; c += 32) {
+                    const float w = p.fc1_w[(size_t)o * F + c];
+                    acc = fmaf(w, sq[c], acc);
+                    acm = fmaf(w, Mx[c], acm);
+                }
+                acc = warp_sum(acc);
+                float v = fmaxf(acc + p.fc1_b[o], 0.f);
+                if (kind == FSN_ATTN_CBAM) { acm = warp_sum(acm); v += fmaxf(acm + p.fc1_b[o], 0.f); }   // shared fc1 on both squeezes (:324-329)
+                if (lane == 0) f1[o] = v;
+            }
+            __syncthreads();
+            for (int o = warp; o < F; o += nwarp) {
+                float acc = 0.f;
+                for (int c = lane; c < Cr; c += 32) acc = fmaf(p.fc2_w[(size_t)o * Cr + c], f1[c], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) gate[o] = 1.0f / (1.0f + __expf(-(acc + p.fc2_b[o])));
+            }
         }
         __syncthreads();
     }
@@ -130,7 +160,7 @@ __global__ void __launch_bounds__(256) tsse_apply_kernel(TsseLaunch a) {
 }
 
 void launch_tsse_norm(const TsseLaunch& a, cudaStream_t s) {
-    size_t smem = sizeof(float) * ((size_t)a.F * (3 + 2 * TSSE_KMAX) + a.F / 2 + 8);
+    size_t smem = sizeof(float) * ((size_t)a.F * (5 + 2 * TSSE_KMAX) + a.F / 2 + 8);
     cudaFuncSetAttribute(tsse_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     tsse_norm_kernel<<<dim3(a.B, a.nbranch), 256, smem, s>>>(a);
     tsse_apply_kernel<<<dim3((a.P + 31) / 32, (a.F + 31) / 32, a.B * a.nbranch), 256, 0, s>>>(a);

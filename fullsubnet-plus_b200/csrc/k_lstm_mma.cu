@@ -117,8 +117,9 @@ __global__ void __launch_bounds__(256, 1) lstm_mma_kernel(LstmMmaLaunch a) {
                         const float gi = acc[mt][0][q] + bias[u], gf = acc[mt][1][q] + bias[H + u];
                         const float gg = acc[mt][2][q] + bias[2 * H + u], go = acc[mt][3][q] + bias[3 * H + u];
                         const float cprev = (t == 0 && !a.resume) ? 0.f : cst[ci];
-                        const float c = sigm<FAST>(gf) * cprev + sigm<FAST>(gi) * tanh_<FAST>(gg);
-                        const float h = sigm<FAST>(go) * tanh_<FAST>(c);
+                        float c, h;
+                        if (a.gru) { h = gru_cell_plain<FAST>(gi, gf, gg, go, cprev); c = h; }
+                        else { c = sigm<FAST>(gf) * cprev + sigm<FAST>(gi) * tanh_<FAST>(gg); h = sigm<FAST>(go) * tanh_<FAST>(c); }
                         cst[ci] = c;
                         hout[(size_t)r * HS + u] = __float2half_rn(h);
                         if (top && a.hseq && row0 + r < a.rows) a.hseq[((size_t)(row0 + r) * H + u) * a.P + t] = h;

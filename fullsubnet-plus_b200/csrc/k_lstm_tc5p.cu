@@ -38,7 +38,7 @@ static inline P5Plan p5_plan(int H) {
     return p;
 }
 
-template <int H, bool FAST>
+template <int H, bool FAST, bool GRU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P5_THREADS, 1) lstm_tc5p_kernel(LstmTc5Launch a, int nstage) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int NCH = H / 32, KBH = H / 64, hcols = H / 2;
@@ -261,9 +261,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P5_THREADS, 1) lstm_
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int u = u4 * 4 + e;
-                            lstm_cell<FAST>(fmaf(__uint_as_float(v[0][u]), -L2E, bia[e]), fmaf(__uint_as_float(v[0][8 + u]), -L2E, bfa[e]),
-                                            fmaf(__uint_as_float(v[1][u]), -2.f * L2E, bga[e]), fmaf(__uint_as_float(v[1][8 + u]), -L2E, boa[e]),
-                                            cpv[e], cn[u], hv[e]);
+                            if (GRU) {
+                                gru_cell<FAST>(fmaf(__uint_as_float(v[0][u]), -L2E, bia[e]), fmaf(__uint_as_float(v[0][8 + u]), -L2E, bfa[e]),
+                                               fmaf(__uint_as_float(v[1][u]), -2.f * L2E, bga[e]), fmaf(__uint_as_float(v[1][8 + u]), -2.f * L2E, boa[e]),
+                                               cpv[e], hv[e]);
+                                cn[u] = hv[e];
+                            } else {
+                                lstm_cell<FAST>(fmaf(__uint_as_float(v[0][u]), -L2E, bia[e]), fmaf(__uint_as_float(v[0][8 + u]), -L2E, bfa[e]),
+                                                fmaf(__uint_as_float(v[1][u]), -2.f * L2E, bga[e]), fmaf(__uint_as_float(v[1][8 + u]), -L2E, boa[e]),
+                                                cpv[e], cn[u], hv[e]);
+                            }
                         }
                         if (layer == 1) {
                             const float4 wa = __ldg(reinterpret_cast<const float4*>(a.fc_w + j * 32 + cg * 8) + u4);
@@ -318,19 +325,19 @@ int launch_lstm_tc5_pair(const LstmTc5Launch& a, cudaStream_t s) {
     if (p.nstage < 2) return (int)cudaErrorInvalidValue;
     const int grid = (a.ntiles + 1) / 2 * 2;                        // whole pairs; the buffers cover the padded tile
     cudaError_t e = cudaErrorInvalidValue;
+#define P5_GO(HH, FF, GG)                                                                                               \
+    {                                                                                                                   \
+        e = cudaFuncSetAttribute(lstm_tc5p_kernel<HH, FF, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);  \
+        if (e != cudaSuccess) return (int)e;                                                                            \
+        lstm_tc5p_kernel<HH, FF, GG><<<grid, P5_THREADS, p.total, s>>>(a, p.nstage);                                   \
+    }
 #define P5_LAUNCH(HH)                                                                                                   \
     if (a.H == HH) {                                                                                                    \
-        if (a.fast) {                                                                                                   \
-            e = cudaFuncSetAttribute(lstm_tc5p_kernel<HH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);   \
-            if (e != cudaSuccess) return (int)e;                                                                        \
-            lstm_tc5p_kernel<HH, true><<<grid, P5_THREADS, p.total, s>>>(a, p.nstage);                                 \
-        } else {                                                                                                        \
-            e = cudaFuncSetAttribute(lstm_tc5p_kernel<HH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);  \
-            if (e != cudaSuccess) return (int)e;                                                                        \
-            lstm_tc5p_kernel<HH, false><<<grid, P5_THREADS, p.total, s>>>(a, p.nstage);                                \
-        }                                                                                                               \
+        if (a.gru) { if (a.fast) P5_GO(HH, true, true) else P5_GO(HH, false, true) }                                    \
+        else { if (a.fast) P5_GO(HH, true, false) else P5_GO(HH, false, false) }                                        \
     }
     P5_LAUNCH(64) P5_LAUNCH(128) P5_LAUNCH(192) P5_LAUNCH(256) P5_LAUNCH(320) P5_LAUNCH(384)
+#undef P5_GO
 #undef P5_LAUNCH
     if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();

@@ -127,8 +127,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_kernel(LstmWsLaunch a) 
                 for (int rr = 0; rr < 2; ++rr) {
                     const float gi = (rr ? acc[2] : acc[0]) + bias[l][0], gf = (rr ? acc[3] : acc[1]) + bias[l][1];
                     const float gg = (rr ? o2 : o0) + bias[l][2], go = (rr ? o3 : o1) + bias[l][3];
-                    const float c = sigm<FAST>(gf) * cst[l][rr] + sigm<FAST>(gi) * tanh_<FAST>(gg);
-                    const float h = sigm<FAST>(go) * tanh_<FAST>(c);
+                    float c, h;
+                    if (a.gru) { h = gru_cell_plain<FAST>(gi, gf, gg, go, cst[l][rr]); c = h; }
+                    else { c = sigm<FAST>(gf) * cst[l][rr] + sigm<FAST>(gi) * tanh_<FAST>(gg); h = sigm<FAST>(go) * tanh_<FAST>(c); }
                     cst[l][rr] = c;
                     const int row = r0 + rr * 8;
                     hout[(size_t)row * H + unit] = __float2half_rn(h);

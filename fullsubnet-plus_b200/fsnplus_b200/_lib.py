@@ -9,6 +9,8 @@ KIND_PLUS, KIND_FSN = 0, 1
 ACT = {None: 0, False: 0, "": 0, "ReLU": 1, "Tanh": 2, "ReLU6": 3}
 NORM = {"offline_laplace_norm": 0, "cumulative_laplace_norm": 1, "offline_gaussian_norm": 2, "cumulative_layer_norm": 3}
 LSTM_IMPL = {"auto": 0, "mma": 1, "tcgen05": 2}
+RNN = {"LSTM": 0, "GRU": 1}                                  # FSN_RNN_* (reference sequence_model.py:31-46)
+ATTENTION = {"TSSE": 0, "SE": 1, "CBAM": 2, "ECA": 3}     # FSN_ATTN_* (reference fullsubnet_plus.py:52-70)
 
 # every symbol include/fsnplus_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -27,7 +29,7 @@ class FsnConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("model_kind", "num_freqs", "look_ahead", "sb_num_neighbors", "fb_num_neighbors",
                                           "fb_hidden", "sb_hidden", "num_layers", "output_size", "fb_act", "sb_act",
                                           "norm_type")] + [("kersize", C.c_int32 * 3), ("lstm_impl", C.c_int32),
-                                                           ("fast_math", C.c_int32)]
+                                                           ("fast_math", C.c_int32), ("channel_attention", C.c_int32), ("rnn_type", C.c_int32)]
 
 
 def lib_path():

@@ -40,6 +40,28 @@ class ChannelTimeSenseSELayer(_NoForward):
         self.fc2 = nn.Linear(num_channels // reduction_ratio, num_channels, bias=True)
 
 
+class ChannelSELayer(_NoForward):
+    """Parameters of the SE attention (reference attention_model.py:6-23)."""
+
+    def __init__(self, num_channels, reduction_ratio=2):
+        super().__init__()
+        self.reduction_ratio = reduction_ratio
+        self.fc1 = nn.Linear(num_channels, num_channels // reduction_ratio, bias=True)
+        self.fc2 = nn.Linear(num_channels // reduction_ratio, num_channels, bias=True)
+
+
+class ChannelCBAMLayer(ChannelSELayer):
+    """Parameters of the CBAM attention (reference attention_model.py:296-315): same two Linear layers as SE."""
+
+
+class ChannelECAlayer(_NoForward):
+    """Parameters of the ECA attention (reference attention_model.py:337-347)."""
+
+    def __init__(self, channel, k_size=3):
+        super().__init__()
+        self.conv = nn.Conv1d(1, 1, kernel_size=k_size, padding=(k_size - 1) // 2, bias=False)
+
+
 class TCNBlock(_NoForward):
     """Parameters of one TCN block (reference causal_conv.py:67-80)."""
 
@@ -59,16 +81,16 @@ class SequenceModel(_NoForward):
 
     def __init__(self, input_size, output_size, hidden_size, num_layers, sequence_model, output_activate_function):
         super().__init__()
-        if sequence_model == "LSTM":
-            self.sequence_model = nn.LSTM(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers,
-                                          batch_first=True, bidirectional=False)
+        if sequence_model in ("LSTM", "GRU"):                                   # sequence_model.py:31-46
+            self.sequence_model = getattr(nn, sequence_model)(input_size=input_size, hidden_size=hidden_size,
+                                                              num_layers=num_layers, batch_first=True, bidirectional=False)
             self.fc_output_layer = nn.Linear(hidden_size, output_size)
         elif sequence_model == "TCN":
             blocks = [TCNBlock(input_size, TCN_HIDDEN, d) for d in TCN_DILATIONS]
             self.sequence_model = nn.Sequential(*blocks, nn.ReLU())
             self.fc_output_layer = nn.Linear(input_size, output_size)
         else:
-            raise NotImplementedError(f"Not implemented {sequence_model} on the B200 path (LSTM and TCN only)")
+            raise NotImplementedError(f"Not implemented {sequence_model}")                           # sequence_model.py:70
         if output_activate_function not in _lib.ACT:
             raise NotImplementedError(f"Not implemented activation function {output_activate_function}")
         self.output_activate_function = output_activate_function
@@ -84,7 +106,7 @@ def _reference_weight_init(m):
     elif isinstance(m, nn.Linear):
         nn.init.xavier_normal_(m.weight.data)
         nn.init.normal_(m.bias.data)
-    elif isinstance(m, nn.LSTM):
+    elif isinstance(m, (nn.LSTM, nn.GRU)):
         for p in m.parameters():
             (nn.init.orthogonal_ if p.dim() >= 2 else nn.init.normal_)(p.data)
 
@@ -95,7 +117,8 @@ class _B200Model(nn.Module):
     _kind = None
 
     def _setup(self, num_freqs, look_ahead, sb_num_neighbors, fb_num_neighbors, fb_hidden, sb_hidden, num_layers,
-               output_size, fb_act, sb_act, norm_type, kersize, lstm_impl, fast_math):
+               output_size, fb_act, sb_act, norm_type, kersize, lstm_impl, fast_math, channel_attention="TSSE",
+               rnn="LSTM"):
         if norm_type not in _lib.NORM:
             raise NotImplementedError("You must set up a type of Norm. e.g. offline_laplace_norm, "
                                       "cumulative_laplace_norm, forgetting_norm, etc.")       # base_model.py:328-329
@@ -110,6 +133,8 @@ class _B200Model(nn.Module):
             cfg.kersize[i] = int(kersize[i])
         cfg.lstm_impl = _lib.LSTM_IMPL[lstm_impl]
         cfg.fast_math = int(bool(fast_math))
+        cfg.channel_attention = _lib.ATTENTION[channel_attention]
+        cfg.rnn_type = _lib.RNN[rnn]
         self._cfg = cfg
         self._handle = None
         self._handle_device = None
@@ -232,16 +257,17 @@ class FullSubNet_Plus(_B200Model):
                  num_layers=2, lstm_impl="auto", fast_math=True):
         super().__init__()
         assert sequence_model in ("GRU", "LSTM", "TCN"), f"{self.__class__.__name__} only support GRU, LSTM and TCN."
-        if sequence_model != "LSTM":
-            raise NotImplementedError("the B200 path implements the LSTM sub-band model (config/inference.toml:35)")
-        if channel_attention_model != "TSSE":
-            raise NotImplementedError(f"Not implemented channel attention model {channel_attention_model} "
-                                      "on the B200 path (TSSE only, config/inference.toml:38)")
+        if sequence_model == "TCN":
+            raise NotImplementedError("a TCN sub-band model is not implemented on the B200 path (LSTM and GRU are)")
+        if channel_attention_model not in _lib.ATTENTION:                                       # fullsubnet_plus.py:69-70
+            raise NotImplementedError(f"Not implemented channel attention model {channel_attention_model}")
         if subband_num != 1:
             raise NotImplementedError("subband_num != 1 is not implemented on the B200 path")
         self.num_channels = num_freqs
         for sfx in ("", "_real", "_imag"):
-            setattr(self, "channel_attention" + sfx, ChannelTimeSenseSELayer(num_freqs, kersize=kersize))
+            setattr(self, "channel_attention" + sfx,                                               # fullsubnet_plus.py:52-68
+                    {"TSSE": lambda: ChannelTimeSenseSELayer(num_freqs, kersize=kersize), "SE": lambda: ChannelSELayer(num_freqs),
+                     "CBAM": lambda: ChannelCBAMLayer(num_freqs), "ECA": lambda: ChannelECAlayer(num_freqs)}[channel_attention_model]())
         for sfx in ("", "_real", "_imag"):                      # full-band models are TCNs (fullsubnet_plus.py:72-100)
             setattr(self, "fb_model" + sfx, SequenceModel(num_freqs, num_freqs, fb_model_hidden_size, 2, "TCN",
                                                           fb_output_activate_function))
@@ -255,7 +281,7 @@ class FullSubNet_Plus(_B200Model):
         self.output_size = output_size
         self._setup(num_freqs, look_ahead, sb_num_neighbors, fb_num_neighbors, fb_model_hidden_size, sb_model_hidden_size,
                     num_layers, output_size, fb_output_activate_function, sb_output_activate_function, norm_type, kersize,
-                    lstm_impl, fast_math)
+                    lstm_impl, fast_math, channel_attention_model, sequence_model)
         if weight_init:
             self.apply(_reference_weight_init)
 
@@ -275,8 +301,6 @@ class Model(_B200Model):
                  num_layers=2, lstm_impl="auto", fast_math=True):
         super().__init__()
         assert sequence_model in ("GRU", "LSTM"), f"{self.__class__.__name__} only support GRU and LSTM."
-        if sequence_model != "LSTM":
-            raise NotImplementedError("the B200 path implements the LSTM sequence model")
         self.fb_model = SequenceModel(num_freqs, num_freqs, fb_model_hidden_size, num_layers, sequence_model,
                                       fb_output_activate_function)
         self.sb_model = SequenceModel((sb_num_neighbors * 2 + 1) + (fb_num_neighbors * 2 + 1), 2, sb_model_hidden_size,
@@ -287,7 +311,7 @@ class Model(_B200Model):
         self.num_groups_in_drop_band = num_groups_in_drop_band
         self._setup(num_freqs, look_ahead, sb_num_neighbors, fb_num_neighbors, fb_model_hidden_size, sb_model_hidden_size,
                     num_layers, 2, fb_output_activate_function, sb_output_activate_function, norm_type, (3, 5, 10),
-                    lstm_impl, fast_math)
+                    lstm_impl, fast_math, "TSSE", sequence_model)
         if weight_init:
             self.apply(_reference_weight_init)
 

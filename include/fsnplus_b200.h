@@ -45,6 +45,16 @@ extern "C" {
 #define FSN_NORM_OFFLINE_GAUSSIAN 2
 #define FSN_NORM_CUMULATIVE_LAYER 3
 
+/* channel_attention_model: fullsubnet_plus.py:52-70 (0 keeps a zero-initialised config on the inference.toml default) */
+#define FSN_ATTN_TSSE 0    /* ChannelTimeSenseSELayer  attention_model.py:43-104  */
+#define FSN_ATTN_SE 1      /* ChannelSELayer           attention_model.py:6-40    */
+#define FSN_ATTN_CBAM 2    /* ChannelCBAMLayer         attention_model.py:296-334 */
+#define FSN_ATTN_ECA 3     /* ChannelECAlayer          attention_model.py:337-359 */
+
+/* sequence_model of the recurrent modules: sequence_model.py:31-46 */
+#define FSN_RNN_LSTM 0
+#define FSN_RNN_GRU 1      /* runs on the LSTM kernels as pseudo-gates (r, z, n_x, n_h) with a GRU cell */
+
 /* lstm_impl */
 #define FSN_LSTM_AUTO 0
 #define FSN_LSTM_MMA 1     /* generic mma.sync kernel (any hidden size / layer count)               */
@@ -65,7 +75,9 @@ typedef struct fsn_config {
     int32_t norm_type;        /*                                      (:42)                      */
     int32_t kersize[3];       /* TSSE kernel sizes                    (:44)                      */
     int32_t lstm_impl;        /* FSN_LSTM_*                                                      */
-    int32_t fast_math;        /* 0: ex2/rcp gates (default); 1: tanh.approx gates                */
+    int32_t fast_math;        /* 0: ex2/rcp gates; 1: tanh.approx gates (the Python mirror's default) */
+    int32_t channel_attention;/* FSN_ATTN_*  channel_attention_model  (:38)                      */
+    int32_t rnn_type;         /* FSN_RNN_*   sequence_model           (:35)                      */
 } fsn_config;
 
 typedef struct fsn_model fsn_model;

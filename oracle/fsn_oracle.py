@@ -56,16 +56,16 @@ def _uni(rng, shape, bound):
     return rng.uniform(-bound, bound, size=shape).astype(np.float32)
 
 
-def _lstm_params(rng, prefix, inp, hid, layers, out, scale=1.0):
-    """Keys/shapes of nn.LSTM + nn.Linear as registered at sequence_model.py:32-38,74-79."""
+def _lstm_params(rng, prefix, inp, hid, layers, out, scale=1.0, gates=4):
+    """Keys/shapes of nn.LSTM (gates=4) / nn.GRU (gates=3) + nn.Linear as registered at sequence_model.py:32-46,74-79."""
     p = {}
     b = scale / np.sqrt(hid)
     for l in range(layers):
         k = inp if l == 0 else hid
-        p[f"{prefix}.sequence_model.weight_ih_l{l}"] = _uni(rng, (4 * hid, k), b)
-        p[f"{prefix}.sequence_model.weight_hh_l{l}"] = _uni(rng, (4 * hid, hid), b)
-        p[f"{prefix}.sequence_model.bias_ih_l{l}"] = _uni(rng, (4 * hid,), b)
-        p[f"{prefix}.sequence_model.bias_hh_l{l}"] = _uni(rng, (4 * hid,), b)
+        p[f"{prefix}.sequence_model.weight_ih_l{l}"] = _uni(rng, (gates * hid, k), b)
+        p[f"{prefix}.sequence_model.weight_hh_l{l}"] = _uni(rng, (gates * hid, hid), b)
+        p[f"{prefix}.sequence_model.bias_ih_l{l}"] = _uni(rng, (gates * hid,), b)
+        p[f"{prefix}.sequence_model.bias_hh_l{l}"] = _uni(rng, (gates * hid,), b)
     p[f"{prefix}.fc_output_layer.weight"] = _uni(rng, (out, hid), 1 / np.sqrt(hid))
     p[f"{prefix}.fc_output_layer.bias"] = _uni(rng, (out,), 1 / np.sqrt(hid))
     return p
@@ -108,6 +108,16 @@ def _tsse_params(rng, prefix, nc, kersize):
     return p
 
 
+def _attn_params(rng, prefix, nc, cfg):
+    kind = cfg.get("channel_attention_model", "TSSE")
+    if kind == "TSSE":
+        return _tsse_params(rng, prefix, nc, cfg["kersize"])
+    if kind == "ECA":                                            # attention_model.py:345
+        return {f"{prefix}.conv.weight": _uni(rng, (1, 1, 3), 1 / np.sqrt(3))}
+    return {f"{prefix}.fc1.weight": _uni(rng, (nc // 2, nc), 1 / np.sqrt(nc)), f"{prefix}.fc1.bias": _uni(rng, (nc // 2,), 1 / np.sqrt(nc)),
+            f"{prefix}.fc2.weight": _uni(rng, (nc, nc // 2), 1 / np.sqrt(nc // 2)), f"{prefix}.fc2.bias": _uni(rng, (nc,), 1 / np.sqrt(nc // 2))}
+
+
 def make_params_plus(cfg, seed=0, lstm_scale=1.0, num_layers=2):
     """state_dict of FullSubNet_Plus(**cfg) (fullsubnet_plus.py:52-110) with
     PyTorch-default-like scales; ``lstm_scale`` > 1 saturates gates like a
@@ -116,12 +126,13 @@ def make_params_plus(cfg, seed=0, lstm_scale=1.0, num_layers=2):
     nf = cfg["num_freqs"]
     p = {}
     for s in ("", "_real", "_imag"):
-        p.update(_tsse_params(rng, f"channel_attention{s}", nf, cfg["kersize"]))
+        p.update(_attn_params(rng, f"channel_attention{s}", nf, cfg))
     for s in ("", "_real", "_imag"):
         p.update(_tcn_params(rng, f"fb_model{s}", nf))
     isb = (2 * cfg["sb_num_neighbors"] + 1) + 3 * (2 * cfg["fb_num_neighbors"] + 1)
+    gates = 3 if cfg.get("sequence_model", "LSTM") == "GRU" else 4
     p.update(_lstm_params(rng, "sb_model", isb, cfg["sb_model_hidden_size"], num_layers,
-                          cfg.get("output_size", 2), lstm_scale))
+                          cfg.get("output_size", 2), lstm_scale, gates))
     return p
 
 
@@ -130,9 +141,10 @@ def make_params_fsn(cfg, seed=0, lstm_scale=1.0, num_layers=2):
     rng = np.random.default_rng(seed)
     nf = cfg["num_freqs"]
     p = {}
-    p.update(_lstm_params(rng, "fb_model", nf, cfg["fb_model_hidden_size"], num_layers, nf, lstm_scale))
+    gates = 3 if cfg.get("sequence_model", "LSTM") == "GRU" else 4
+    p.update(_lstm_params(rng, "fb_model", nf, cfg["fb_model_hidden_size"], num_layers, nf, lstm_scale, gates))
     isb = (2 * cfg["sb_num_neighbors"] + 1) + (2 * cfg["fb_num_neighbors"] + 1)
-    p.update(_lstm_params(rng, "sb_model", isb, cfg["sb_model_hidden_size"], num_layers, 2, lstm_scale))
+    p.update(_lstm_params(rng, "sb_model", isb, cfg["sb_model_hidden_size"], num_layers, 2, lstm_scale, gates))
     return p
 
 
@@ -297,6 +309,38 @@ def tsse(x, p, prefix, kersize):
     return x * f2[:, :, None]
 
 
+def se_layer(x, p, prefix):
+    """ChannelSELayer.forward (attention_model.py:25-40)."""
+    sq = x.mean(axis=2)
+    f1 = np.maximum(sq @ p[f"{prefix}.fc1.weight"].astype(x.dtype).T + p[f"{prefix}.fc1.bias"].astype(x.dtype), 0.0)
+    g = sigmoid(f1 @ p[f"{prefix}.fc2.weight"].astype(x.dtype).T + p[f"{prefix}.fc2.bias"].astype(x.dtype))
+    return x * g[:, :, None]
+
+
+def cbam_layer(x, p, prefix):
+    """ChannelCBAMLayer.forward (attention_model.py:317-334)."""
+    w1, b1 = p[f"{prefix}.fc1.weight"].astype(x.dtype), p[f"{prefix}.fc1.bias"].astype(x.dtype)
+    f1 = np.maximum(x.mean(axis=2) @ w1.T + b1, 0.0) + np.maximum(x.max(axis=2) @ w1.T + b1, 0.0)
+    g = sigmoid(f1 @ p[f"{prefix}.fc2.weight"].astype(x.dtype).T + p[f"{prefix}.fc2.bias"].astype(x.dtype))
+    return x * g[:, :, None]
+
+
+def eca_layer(x, p, prefix):
+    """ChannelECAlayer.forward (attention_model.py:349-359): conv1d over the channel axis, k = 3, zero padding 1, no bias."""
+    w = p[f"{prefix}.conv.weight"].astype(x.dtype).reshape(-1)
+    y = np.pad(x.mean(axis=2), ((0, 0), (1, 1)))
+    g = sigmoid(w[0] * y[:, :-2] + w[1] * y[:, 1:-1] + w[2] * y[:, 2:])
+    return x * g[:, :, None]
+
+
+def channel_attention(x, p, prefix, cfg):
+    """Dispatch of fullsubnet_plus.py:52-70."""
+    kind = cfg.get("channel_attention_model", "TSSE")
+    if kind == "TSSE":
+        return tsse(x, p, prefix, cfg["kersize"])
+    return {"SE": se_layer, "CBAM": cbam_layer, "ECA": eca_layer}[kind](x, p, prefix)
+
+
 def prelu(x, a):
     return np.where(x >= 0, x, a * x)
 
@@ -379,9 +423,36 @@ def lstm_stack(x, p, prefix, num_layers, return_all=False):
     return inp
 
 
-def seq_lstm(x, p, prefix, num_layers, act):
-    """SequenceModel.forward, LSTM branch (sequence_model.py:113-122).  x [N, I, T] -> [N, O, T]."""
-    o = lstm_stack(x.transpose(0, 2, 1), p, prefix, num_layers)
+def gru_stack(x, p, prefix, num_layers):
+    """nn.GRU(batch_first) as built at sequence_model.py:39-46: gate rows r,z,n;
+    n = tanh(W_in x + b_in + r (W_hn h + b_hn)); h_t = (1 - z) n + z h; zero initial state.  x [N, T, I] -> [N, T, H]."""
+    dt = x.dtype
+    N, T, _ = x.shape
+    inp = x
+    for l in range(num_layers):
+        wiT = np.ascontiguousarray(p[f"{prefix}.sequence_model.weight_ih_l{l}"].astype(dt).T)
+        whT = np.ascontiguousarray(p[f"{prefix}.sequence_model.weight_hh_l{l}"].astype(dt).T)
+        bi = p[f"{prefix}.sequence_model.bias_ih_l{l}"].astype(dt)
+        bh = p[f"{prefix}.sequence_model.bias_hh_l{l}"].astype(dt)
+        H = whT.shape[0]
+        h = np.zeros((N, H), dt)
+        out = np.empty((N, T, H), dt)
+        inp_t = np.ascontiguousarray(inp.transpose(1, 0, 2))
+        for t in range(T):
+            gi = inp_t[t] @ wiT + bi
+            gh = h @ whT + bh
+            r = sigmoid(gi[:, :H] + gh[:, :H])
+            z = sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+            n = np.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+            h = (1.0 - z) * n + z * h
+            out[:, t] = h
+        inp = out
+    return inp
+
+
+def seq_lstm(x, p, prefix, num_layers, act, kind="LSTM"):
+    """SequenceModel.forward, LSTM / GRU branch (sequence_model.py:113-122).  x [N, I, T] -> [N, O, T]."""
+    o = (gru_stack if kind == "GRU" else lstm_stack)(x.transpose(0, 2, 1), p, prefix, num_layers)
     w = p[f"{prefix}.fc_output_layer.weight"].astype(x.dtype)
     b = p[f"{prefix}.fc_output_layer.bias"].astype(x.dtype)
     o = activation(o @ w.T + b, act)
@@ -397,7 +468,7 @@ def fullsubnet_plus_forward(p, cfg, mag, real, imag, dtype=np.float64, num_layer
     with every sample treated independently (== the reference called with B=1
     per sample).  Inputs [B, 1, F, T]; returns [B, 2, F, T].  ``stages`` (dict)
     receives the intermediate tensors the kernel-level tests compare against."""
-    assert cfg.get("channel_attention_model", "TSSE") == "TSSE" and cfg.get("subband_num", 1) == 1
+    assert cfg.get("subband_num", 1) == 1
     la, ns, nfb = cfg["look_ahead"], cfg["sb_num_neighbors"], cfg["fb_num_neighbors"]
     norm = NORMS[cfg["norm_type"]]
     pad = lambda x: np.pad(np.asarray(x, dtype), ((0, 0), (0, 0), (0, 0), (0, la)))     # :137-139
@@ -407,7 +478,7 @@ def fullsubnet_plus_forward(p, cfg, mag, real, imag, dtype=np.float64, num_layer
     fb_in, fb_out = [], []
     for x, s in ((mag, ""), (real, "_real"), (imag, "_imag")):
         xi = norm(x).reshape(B, F, T)                                                   # :144,157,162
-        xi = tsse(xi, p, f"channel_attention{s}", cfg["kersize"])                       # :145,158,163
+        xi = channel_attention(xi, p, f"channel_attention{s}", cfg)                         # :145,158,163
         fb_in.append(xi)
         fb_out.append(seq_tcn(xi, p, f"fb_model{s}", cfg["fb_output_activate_function"])
                       .reshape(B, 1, F, T))                                             # :154,159,164
@@ -418,7 +489,7 @@ def fullsubnet_plus_forward(p, cfg, mag, real, imag, dtype=np.float64, num_layer
         stages.update(fb_in=np.stack(fb_in), fb_out=np.stack([o[:, 0] for o in fb_out]), sb_in=sb_in)
     Isb = sb_in.shape[2]
     m = seq_lstm(sb_in.reshape(B * F, Isb, T), p, "sb_model", num_layers,
-                 cfg["sb_output_activate_function"])                                     # :205
+                 cfg["sb_output_activate_function"], cfg.get("sequence_model", "LSTM"))  # :205
     O = m.shape[1]
     m = m.reshape(B, F, O, T).transpose(0, 2, 1, 3)                                      # :206
     return np.ascontiguousarray(m[:, :, :, la:])                                         # :208
@@ -433,7 +504,7 @@ def fullsubnet_forward(p, cfg, mag, dtype=np.float64, num_layers=2, stages=None)
     assert C == 1
     fb_in = norm(mag).reshape(B, F, T)                                                   # :86
     fb_out = seq_lstm(fb_in, p, "fb_model", num_layers,
-                      cfg["fb_output_activate_function"]).reshape(B, 1, F, T)            # :87
+                      cfg["fb_output_activate_function"], cfg.get("sequence_model", "LSTM")).reshape(B, 1, F, T)   # :87
     fb_unf = unfold(fb_out, nfb).reshape(B, F, 2 * nfb + 1, T)                           # :90-91
     mag_unf = unfold(mag, ns).reshape(B, F, 2 * ns + 1, T)                               # :94-95 (raw mag)
     sb_in = norm(np.concatenate([mag_unf, fb_unf], axis=2))                              # :98-99
@@ -441,7 +512,7 @@ def fullsubnet_forward(p, cfg, mag, dtype=np.float64, num_layers=2, stages=None)
         stages.update(fb_in=fb_in, fb_out=fb_out[:, 0], sb_in=sb_in)
     Isb = sb_in.shape[2]
     m = seq_lstm(sb_in.reshape(B * F, Isb, T), p, "sb_model", num_layers,
-                 cfg["sb_output_activate_function"])                                     # :114
+                 cfg["sb_output_activate_function"], cfg.get("sequence_model", "LSTM"))  # :114
     m = m.reshape(B, F, 2, T).transpose(0, 2, 1, 3)                                      # :115
     return np.ascontiguousarray(m[:, :, :, la:])                                         # :117
 

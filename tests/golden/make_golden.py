@@ -161,6 +161,26 @@ def main():
     print(f"plus_small: oracle-vs-reference rel-L2 out={O.rel_l2(oo, out):.2e}")
     save("plus_small", mag=m, real=r, imag=i, out=out, fb_in=fb_in, fb_out=fb_out, sb_in=st["sb_in"], seed=3)
 
+    for attn in ("SE", "ECA", "CBAM"):                                     # fullsubnet_plus.py:52-70
+        acfg = dict(scfg, channel_attention_model=attn)
+        params = O.make_params_plus(acfg, seed=5)
+        out, fb_in, fb_out = run_plus(acfg, params, m, r, i)
+        oo = O.fullsubnet_plus_forward(params, acfg, m, r, i)
+        print(f"plus_small[{attn}]: oracle-vs-reference rel-L2 out={O.rel_l2(oo, out):.2e}")
+        save(f"plus_small_{attn}", out=out, fb_in=fb_in, seed=5)
+
+    # sequence_model = "GRU" (sequence_model.py:39-46): FullSubNet+ sub-band GRU, fullsubnet.Model full-band + sub-band GRU
+    gcfg = dict(scfg, sequence_model="GRU")
+    params = O.make_params_plus(gcfg, seed=8, lstm_scale=2.0)
+    out, fb_in, fb_out = run_plus(gcfg, params, m, r, i)
+    print(f"plus_small[GRU]: oracle-vs-reference rel-L2 out={O.rel_l2(O.fullsubnet_plus_forward(params, gcfg, m, r, i), out):.2e}")
+    save("plus_small_GRU", out=out, seed=8, lstm_scale=2.0)
+    gcfg = dict(small_fsn_cfg(), sequence_model="GRU")
+    params = O.make_params_fsn(gcfg, seed=8, lstm_scale=2.0)
+    out, fb_out = run_fsn(gcfg, params, m)
+    print(f"fsn_small[GRU]: oracle-vs-reference rel-L2 out={O.rel_l2(O.fullsubnet_forward(params, gcfg, m), out):.2e}")
+    save("fsn_small_GRU", out=out, fb_out=fb_out, seed=8, lstm_scale=2.0)
+
     for norm in ("offline_laplace_norm", "cumulative_laplace_norm", "offline_gaussian_norm", "cumulative_layer_norm"):
         c = small_fsn_cfg(norm)
         params = O.make_params_fsn(c, seed=4)

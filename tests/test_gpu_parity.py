@@ -78,6 +78,100 @@ def test_plus_small_golden_from_reference(built_lib, golden):
     assert O.rel_l2(out.cpu().numpy(), g["out"]) < MASK_TOL
 
 
+@pytest.mark.parametrize("attn", ["SE", "ECA", "CBAM"])
+def test_plus_small_other_attentions_golden(built_lib, golden, attn):
+    """channel_attention_model = SE / ECA / CBAM (fullsubnet_plus.py:52-70) against committed reference outputs."""
+    g, gi = golden(f"plus_small_{attn}"), golden("plus_small")
+    cfg = dict(small_cfg(32), channel_attention_model=attn)
+    m = build_plus(cfg, O.make_params_plus(cfg, seed=5))
+    with torch.no_grad():
+        out = m(_t(gi["mag"]), _t(gi["real"]), _t(gi["imag"]))
+    fb_in = m.get_stage("fb_in", (3, 3, 33, 22), DEV).cpu().numpy()
+    e_in, err = O.rel_l2(fb_in, g["fb_in"]), O.rel_l2(out.cpu().numpy(), g["out"])
+    print(f"\n[{attn}] fb_in {e_in:.2e} cIRM {err:.3e}")
+    assert e_in < 1e-5
+    assert err < MASK_TOL
+
+
+@pytest.mark.parametrize("attn", ["SE", "ECA", "CBAM"])
+def test_plus_default_size_other_attentions_vs_oracle(built_lib, golden, attn):
+    """Default geometry (F=257, H=384, tcgen05 path), one clip, oracle as truth; for CBAM the mag branch has all-positive
+    rows and the real/imag branches a negative normaliser, which exercises the min/max selection of the squeeze."""
+    gi = golden("plus_default")
+    cfg = dict(O.default_plus_config(), channel_attention_model=attn)
+    params = O.make_params_plus(cfg, seed=9)
+    ref = O.fullsubnet_plus_forward(params, cfg, gi["mag"], gi["real"], gi["imag"])
+    m = build_plus(cfg, params)
+    with torch.no_grad():
+        out = m(_t(gi["mag"]), _t(gi["real"]), _t(gi["imag"]))
+    err = O.rel_l2(out.cpu().numpy(), ref)
+    print(f"\n[{attn} default size] cIRM {err:.3e}")
+    assert err < MASK_TOL
+
+
+def test_gru_small_goldens_from_reference(built_lib, golden):
+    """sequence_model = "GRU" (sequence_model.py:39-46), committed reference outputs: FullSubNet+ (H = 32 -> mma kernel) and
+    fullsubnet.Model (full-band GRU on the weight-stationary kernel, sub-band GRU on the mma kernel)."""
+    gi = golden("plus_small")
+    cfg = dict(small_cfg(32), sequence_model="GRU")
+    m = build_plus(cfg, O.make_params_plus(cfg, seed=8, lstm_scale=2.0))
+    with torch.no_grad():
+        out = m(_t(gi["mag"]), _t(gi["real"]), _t(gi["imag"]))
+    err = O.rel_l2(out.cpu().numpy(), golden("plus_small_GRU")["out"])
+    cfg = O.default_fsn_config()
+    cfg.update(num_freqs=33, sb_num_neighbors=3, sb_model_hidden_size=32, fb_model_hidden_size=48, sequence_model="GRU")
+    m = build_fsn(cfg, O.make_params_fsn(cfg, seed=8, lstm_scale=2.0))
+    with torch.no_grad():
+        out = m(_t(gi["mag"]))
+    g = golden("fsn_small_GRU")
+    e_fb = O.rel_l2(m.get_stage("fb_out", (3, 33, 22), DEV).cpu().numpy(), g["fb_out"])
+    err2 = O.rel_l2(out.cpu().numpy(), g["out"])
+    print(f"\n[GRU small] FullSubNet+ cIRM {err:.3e}; fullsubnet.Model fb_out {e_fb:.2e} cIRM {err2:.3e}")
+    assert err < MASK_TOL and err2 < MASK_TOL and e_fb < 2e-3
+
+
+@pytest.mark.parametrize("impl,H", [("mma", 64), ("tcgen05", 64), ("tcgen05", 128)])
+@pytest.mark.parametrize("fast", [True, False])
+def test_gru_plus_small_vs_oracle(built_lib, impl, H, fast):
+    cfg = dict(small_cfg(H), sequence_model="GRU")
+    params = O.make_params_plus(cfg, seed=13, lstm_scale=2.0)
+    mag, real, imag = small_inputs(5, 33, 27, 3)
+    ref = O.fullsubnet_plus_forward(params, cfg, mag, real, imag)
+    m = build_plus(cfg, params, lstm_impl=impl, fast_math=fast)
+    with torch.no_grad():
+        out = m(_t(mag), _t(real), _t(imag))
+    assert m.last_lstm_impl() == impl
+    err = O.rel_l2(out.cpu().numpy(), ref)
+    print(f"\n[GRU {impl} H={H} fast={fast}] cIRM {err:.3e}")
+    assert err < MASK_TOL
+
+
+def test_gru_default_size_vs_oracle(built_lib, golden):
+    """Default geometry with a GRU sub-band model (tcgen05 pair kernel, H = 384) and the GRU fullsubnet.Model (H = 512 full
+    band on the weight-stationary kernel); one 3 s clip, oracle fp64 as truth; a parameter update must re-expand the gates."""
+    gi = golden("plus_default")
+    cfg = dict(O.default_plus_config(), sequence_model="GRU")
+    params = O.make_params_plus(cfg, seed=17, lstm_scale=2.0)
+    ref = O.fullsubnet_plus_forward(params, cfg, gi["mag"], gi["real"], gi["imag"])
+    m = build_plus(cfg, params)
+    with torch.no_grad():
+        out = m(_t(gi["mag"]), _t(gi["real"]), _t(gi["imag"]))
+        assert m.last_lstm_impl() == "tcgen05"
+        err = O.rel_l2(out.cpu().numpy(), ref)
+        m.sb_model.sequence_model.bias_hh_l0.mul_(1.0)              # bumps the version -> parameters are pushed again
+        out2 = m(_t(gi["mag"]), _t(gi["real"]), _t(gi["imag"]))
+    assert torch.equal(out, out2)
+    fcfg = dict(O.default_fsn_config(), sequence_model="GRU")
+    fparams = O.make_params_fsn(fcfg, seed=18, lstm_scale=2.0)
+    fref = O.fullsubnet_forward(fparams, fcfg, gi["mag"])
+    fm = build_fsn(fcfg, fparams)
+    with torch.no_grad():
+        fout = fm(_t(gi["mag"]))
+    ferr = O.rel_l2(fout.cpu().numpy(), fref)
+    print(f"\n[GRU default size] FullSubNet+ cIRM {err:.3e}; fullsubnet.Model cIRM {ferr:.3e}")
+    assert err < MASK_TOL and ferr < MASK_TOL
+
+
 @pytest.mark.parametrize("impl", ["tcgen05", "mma"])
 @pytest.mark.parametrize("stress", [False, True])
 def test_plus_default_config_golden(built_lib, golden, impl, stress):
@@ -377,3 +471,34 @@ def test_accurate_gate_math_variant(built_lib, golden):
             print(f"\n[fast_math={fm}, lstm_scale={scale}] cIRM rel-L2 {err:.3e}")
             assert err < MASK_TOL
         assert O.rel_l2(outs[0], outs[1]) < 3e-4
+
+
+def test_command_line_tool_matches_reference_pipeline(built_lib, golden, tmp_path):
+    """fsnplus_b200.tools.inference with the reference's flags / TOML / checkpoint format: the file written for clip 0 must be
+    the reference's enhanced waveform (golden, reference torch.istft) after the int16 scaling of base_inferencer.py:151-152,
+    also when the clip is enhanced inside a batch of equal-length files; an odd-length file runs as its own batch."""
+    from scipy.io import wavfile
+    from fsnplus_b200.tools import inference as T
+    import os
+    REF_TOML = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inference_reference.toml")).read()
+    g = golden("plus_default")
+    clips = O.synth_clips(3).astype(np.float32)
+    noisy = tmp_path / "noisy"
+    noisy.mkdir()
+    for i, c in enumerate(clips):
+        wavfile.write(noisy / f"clip{i}.wav", 16000, c)
+    wavfile.write(noisy / "odd.wav", 16000, clips[1][:20000])
+    cfg = O.default_plus_config()
+    torch.save({"model": {k: torch.from_numpy(v) for k, v in O.make_params_plus(cfg, seed=0).items()}, "epoch": 7}, tmp_path / "ckpt.tar")
+    (tmp_path / "inference.toml").write_text(REF_TOML)
+    T.main(["-C", str(tmp_path / "inference.toml"), "-M", str(tmp_path / "ckpt.tar"), "-I", str(noisy), "-O", str(tmp_path / "out"),
+            "--batch_size", "8"])
+    out_dir = tmp_path / "out" / "enhanced_0007"
+    assert sorted(p.name for p in out_dir.iterdir()) == ["clip0.wav", "clip1.wav", "clip2.wav", "odd.wav"]
+    rate, pcm = wavfile.read(out_dir / "clip0.wav")
+    want = T.to_int16(g["enhanced"][0])
+    assert rate == 16000 and pcm.dtype == np.int16 and pcm.shape == want.shape
+    err = O.rel_l2(pcm.astype(np.float64), want.astype(np.float64))
+    print(f"\n[CLI] int16 enhanced waveform vs reference pipeline rel-L2 {err:.3e}, max |diff| {np.abs(pcm.astype(int) - want.astype(int)).max()} LSB")
+    assert err < 2e-3
+    assert wavfile.read(out_dir / "odd.wav")[1].shape == (20000,)

@@ -40,6 +40,35 @@ def test_state_dict_contract_plus():
     assert m.num_groups_in_drop_band == 2 and m.look_ahead == 2
 
 
+@pytest.mark.parametrize("attn", ["SE", "ECA", "CBAM"])
+def test_state_dict_contract_other_attentions(attn):
+    """SE is the reference constructor's default (fullsubnet_plus.py:27); the same parameter dicts were loaded into the
+    unmodified reference with strict=True by tests/golden/make_golden.py."""
+    from fsnplus_b200.model import FullSubNet_Plus
+    cfg = dict(O.default_plus_config(), channel_attention_model=attn)
+    if attn == "SE":
+        del cfg["channel_attention_model"]                              # constructor default
+    m = FullSubNet_Plus(**cfg)
+    ref = O.make_params_plus(dict(cfg, channel_attention_model=attn), seed=0)
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(ref.keys())
+    for k, v in ref.items():
+        assert tuple(sd[k].shape) == v.shape, k
+
+
+def test_state_dict_contract_gru():
+    from fsnplus_b200.model import FullSubNet_Plus, Model
+    cfg = dict(O.default_plus_config(), sequence_model="GRU")
+    sd, ref = FullSubNet_Plus(**cfg).state_dict(), O.make_params_plus(cfg, seed=0)
+    assert set(sd.keys()) == set(ref.keys())
+    assert all(tuple(sd[k].shape) == v.shape for k, v in ref.items())
+    assert tuple(sd["sb_model.sequence_model.weight_hh_l1"].shape) == (3 * 384, 384)
+    cfg = dict(O.default_fsn_config(), sequence_model="GRU")
+    sd, ref = Model(**cfg).state_dict(), O.make_params_fsn(cfg, seed=0)
+    assert set(sd.keys()) == set(ref.keys())
+    assert all(tuple(sd[k].shape) == v.shape for k, v in ref.items())
+
+
 def test_state_dict_contract_fsn():
     from fsnplus_b200.model import Model
     cfg = O.default_fsn_config()

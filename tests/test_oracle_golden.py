@@ -32,6 +32,31 @@ def test_plus_small_all_stages(golden):
     assert O.rel_l2(st["sb_in"], g["sb_in"]) < TOL
 
 
+@pytest.mark.parametrize("attn", ["SE", "ECA", "CBAM"])
+def test_plus_small_other_attentions(golden, attn):
+    """channel_attention_model variants of fullsubnet_plus.py:52-70 (SE is the reference constructor's default)."""
+    g, gi = golden(f"plus_small_{attn}"), golden("plus_small")
+    cfg = dict(small_plus_cfg(), channel_attention_model=attn)
+    st = {}
+    out = O.fullsubnet_plus_forward(O.make_params_plus(cfg, seed=5), cfg, gi["mag"], gi["real"], gi["imag"], stages=st)
+    assert O.rel_l2(out, g["out"]) < TOL
+    assert O.rel_l2(st["fb_in"], g["fb_in"]) < TOL
+
+
+def test_gru_variants(golden):
+    """sequence_model = "GRU" (sequence_model.py:39-46) for both model classes, gates pushed towards saturation (x2)."""
+    gi = golden("plus_small")
+    cfg = dict(small_plus_cfg(), sequence_model="GRU")
+    out = O.fullsubnet_plus_forward(O.make_params_plus(cfg, seed=8, lstm_scale=2.0), cfg, gi["mag"], gi["real"], gi["imag"])
+    assert O.rel_l2(out, golden("plus_small_GRU")["out"]) < TOL
+    cfg = dict(small_fsn_cfg("offline_laplace_norm"), sequence_model="GRU")
+    st = {}
+    out = O.fullsubnet_forward(O.make_params_fsn(cfg, seed=8, lstm_scale=2.0), cfg, gi["mag"], stages=st)
+    g = golden("fsn_small_GRU")
+    assert O.rel_l2(out, g["out"]) < TOL
+    assert O.rel_l2(st["fb_out"], g["fb_out"]) < TOL
+
+
 @pytest.mark.parametrize("norm", ["offline_laplace_norm", "cumulative_laplace_norm", "offline_gaussian_norm", "cumulative_layer_norm"])
 def test_fsn_small_norms(golden, norm):
     g = golden(f"fsn_small_{norm}")
