@@ -329,6 +329,9 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     if (c.norm_type < FSN_NORM_OFFLINE_LAPLACE || c.norm_type > FSN_NORM_CUMULATIVE_LAYER) return fail(FSN_EINVAL, "unknown norm_type %d", c.norm_type);
     if (c.model_kind == FSN_KIND_PLUS) {
         if (c.channel_attention < FSN_ATTN_TSSE || c.channel_attention > FSN_ATTN_ECA) return fail(FSN_EINVAL, "unknown channel_attention %d", c.channel_attention);
+        if (c.subband_num > 1 && c.channel_attention != FSN_ATTN_ECA)
+            return fail(FSN_EINVAL, "subband_num > 1 needs the ECA attention (the reference forward raises for the others)");
+        if (c.subband_num < 0 || c.subband_num > c.num_freqs / 2) return fail(FSN_EINVAL, "bad subband_num %d", c.subband_num);
         for (int i = 0; i < 3; ++i)
             if (c.channel_attention == FSN_ATTN_TSSE && (c.kersize[i] < 1 || c.kersize[i] > 16)) return fail(FSN_EINVAL, "kersize must be in 1..16");
     }
@@ -592,7 +595,7 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
         const char* cn[3] = {"smallConv1d", "middleConv1d", "largeConv1d"};
         TsseLaunch ta{};
         ta.x[0] = d_mag; ta.x[1] = d_real; ta.x[2] = d_imag;
-        ta.nbranch = 3; ta.B = B; ta.F = F; ta.T = T; ta.Tp = Tp; ta.P = Pp; ta.attention = 1 + c.channel_attention;
+        ta.nbranch = 3; ta.B = B; ta.F = F; ta.T = T; ta.Tp = Tp; ta.P = Pp; ta.attention = 1 + c.channel_attention; ta.sub = c.subband_num;
         for (int i = 0; i < 3; ++i) ta.ksz[i] = c.kersize[i];
         for (int b = 0; b < 3; ++b) {
             const std::string p = std::string("channel_attention") + sfx[b];

@@ -26,6 +26,7 @@ struct TsseLaunch {
     float* out;                // [nbranch, B, F, P]
     float* scale;              // [nbranch, B, F] per-row scale handed from the statistics kernel to the apply kernel
     int prenorm;               // 1: input is already normalised (input_norm_kernel), skip the utterance-mean division
+    int sub;                   // subband_num (ECA, mag branch only): channels are groups of `sub` reflect-padded bins (fullsubnet_plus.py:146-153)
     float* out_tm; int Cp;     // optional time-major copy [(branch, b, t), Cp] for the tcgen05 TCN (pad columns stay zero)
 };
 void launch_tsse_norm(const TsseLaunch& a, cudaStream_t s);

@@ -99,7 +99,25 @@ __global__ void __launch_bounds__(256) tsse_norm_kernel(TsseLaunch a) {
             }
         }
         __syncthreads();
-        if (kind == FSN_ATTN_ECA) {                  // attention_model.py:355-357: conv1d over the channel axis, k = 3, zero padding, no bias
+        if (kind == FSN_ATTN_ECA && a.sub > 1 && br == 0) {
+            // subband_num > 1 (fullsubnet_plus.py:146-153, mag branch): the F bins are reflect-padded to (F / sub + 1) * sub and
+            // every `sub` consecutive bins form one attention channel whose "time" axis is sub * Tp long
+            const int sub = a.sub, Cg = F / sub + 1;
+            const float w0 = p.eca_w[0], w1 = p.eca_w[1], w2 = p.eca_w[2];
+            float* sg = Mx;                           // [Cg] group squeeze, f1: [Cg] group gate (Cg <= F / 2 + 1)
+            for (int c = threadIdx.x; c < Cg; c += blockDim.x) {
+                float acc = 0.f;
+                for (int j = 0; j < sub; ++j) { int f = c * sub + j; if (f >= F) f = 2 * F - 2 - f; acc += S[f]; }
+                sg[c] = acc * inv / ((float)Tp * (float)sub);
+            }
+            __syncthreads();
+            for (int c = threadIdx.x; c < Cg; c += blockDim.x) {
+                const float y = w0 * (c > 0 ? sg[c - 1] : 0.f) + w1 * sg[c] + w2 * (c + 1 < Cg ? sg[c + 1] : 0.f);
+                f1[c] = 1.0f / (1.0f + __expf(-y));
+            }
+            __syncthreads();
+            for (int c = threadIdx.x; c < F; c += blockDim.x) gate[c] = f1[c / sub];
+        } else if (kind == FSN_ATTN_ECA) {           // attention_model.py:355-357: conv1d over the channel axis, k = 3, zero padding, no bias
             const float w0 = p.eca_w[0], w1 = p.eca_w[1], w2 = p.eca_w[2];
             for (int c = threadIdx.x; c < F; c += blockDim.x) {
                 const float y = w0 * (c > 0 ? sq[c - 1] : 0.f) + w1 * sq[c] + w2 * (c + 1 < F ? sq[c + 1] : 0.f);

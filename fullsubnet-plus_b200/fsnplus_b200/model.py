@@ -118,7 +118,7 @@ class _B200Model(nn.Module):
 
     def _setup(self, num_freqs, look_ahead, sb_num_neighbors, fb_num_neighbors, fb_hidden, sb_hidden, num_layers,
                output_size, fb_act, sb_act, norm_type, kersize, lstm_impl, fast_math, channel_attention="TSSE",
-               rnn="LSTM"):
+               rnn="LSTM", subband_num=1):
         if norm_type not in _lib.NORM:
             raise NotImplementedError("You must set up a type of Norm. e.g. offline_laplace_norm, "
                                       "cumulative_laplace_norm, forgetting_norm, etc.")       # base_model.py:328-329
@@ -135,6 +135,7 @@ class _B200Model(nn.Module):
         cfg.fast_math = int(bool(fast_math))
         cfg.channel_attention = _lib.ATTENTION[channel_attention]
         cfg.rnn_type = _lib.RNN[rnn]
+        cfg.subband_num = int(subband_num)
         self._cfg = cfg
         self._handle = None
         self._handle_device = None
@@ -261,13 +262,16 @@ class FullSubNet_Plus(_B200Model):
             raise NotImplementedError("a TCN sub-band model is not implemented on the B200 path (LSTM and GRU are)")
         if channel_attention_model not in _lib.ATTENTION:                                       # fullsubnet_plus.py:69-70
             raise NotImplementedError(f"Not implemented channel attention model {channel_attention_model}")
-        if subband_num != 1:
-            raise NotImplementedError("subband_num != 1 is not implemented on the B200 path")
-        self.num_channels = num_freqs
+        # fullsubnet_plus.py:47-50.  With subband_num > 1 the reference builds all three attentions for F // subband_num + 1
+        # channels but applies the real / imag ones to F channels (:157-163), so its forward only runs with the
+        # channel-agnostic ECA; the containers keep the reference's shapes and forward() raises like the reference otherwise.
+        self.num_channels = num_freqs if subband_num == 1 else num_freqs // subband_num + 1
+        self._subband_runs = subband_num == 1 or channel_attention_model == "ECA"
         for sfx in ("", "_real", "_imag"):
             setattr(self, "channel_attention" + sfx,                                               # fullsubnet_plus.py:52-68
-                    {"TSSE": lambda: ChannelTimeSenseSELayer(num_freqs, kersize=kersize), "SE": lambda: ChannelSELayer(num_freqs),
-                     "CBAM": lambda: ChannelCBAMLayer(num_freqs), "ECA": lambda: ChannelECAlayer(num_freqs)}[channel_attention_model]())
+                    {"TSSE": lambda: ChannelTimeSenseSELayer(self.num_channels, kersize=kersize),
+                     "SE": lambda: ChannelSELayer(self.num_channels), "CBAM": lambda: ChannelCBAMLayer(self.num_channels),
+                     "ECA": lambda: ChannelECAlayer(self.num_channels)}[channel_attention_model]())
         for sfx in ("", "_real", "_imag"):                      # full-band models are TCNs (fullsubnet_plus.py:72-100)
             setattr(self, "fb_model" + sfx, SequenceModel(num_freqs, num_freqs, fb_model_hidden_size, 2, "TCN",
                                                           fb_output_activate_function))
@@ -281,12 +285,16 @@ class FullSubNet_Plus(_B200Model):
         self.output_size = output_size
         self._setup(num_freqs, look_ahead, sb_num_neighbors, fb_num_neighbors, fb_model_hidden_size, sb_model_hidden_size,
                     num_layers, output_size, fb_output_activate_function, sb_output_activate_function, norm_type, kersize,
-                    lstm_impl, fast_math, channel_attention_model, sequence_model)
+                    lstm_impl, fast_math, channel_attention_model, sequence_model, subband_num if self._subband_runs else 1)
         if weight_init:
             self.apply(_reference_weight_init)
 
     def forward(self, noisy_mag, noisy_real, noisy_imag):
         """[B, 1, F, T] x3 -> [B, 2, F, T] (reference fullsubnet_plus.py:122-209, eval semantics per sample)."""
+        if not self._subband_runs:
+            raise RuntimeError(f"subband_num={self.subband_num}: the attention was built for {self.num_channels} channels but the "
+                               "real/imag branches have num_freqs channels (the reference forward raises here too, "
+                               "fullsubnet_plus.py:157-163); only channel_attention_model='ECA' runs with subband_num > 1")
         return self._run(noisy_mag, noisy_real, noisy_imag)
 
 

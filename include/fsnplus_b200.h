@@ -78,6 +78,8 @@ typedef struct fsn_config {
     int32_t fast_math;        /* 0: ex2/rcp gates; 1: tanh.approx gates (the Python mirror's default) */
     int32_t channel_attention;/* FSN_ATTN_*  channel_attention_model  (:38)                      */
     int32_t rnn_type;         /* FSN_RNN_*   sequence_model           (:35)                      */
+    int32_t subband_num;      /* 0 or 1: off; > 1 needs FSN_ATTN_ECA (the only attention whose
+                                 reference forward runs in that mode, fullsubnet_plus.py:146-163) */
 } fsn_config;
 
 typedef struct fsn_model fsn_model;

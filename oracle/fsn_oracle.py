@@ -468,7 +468,10 @@ def fullsubnet_plus_forward(p, cfg, mag, real, imag, dtype=np.float64, num_layer
     with every sample treated independently (== the reference called with B=1
     per sample).  Inputs [B, 1, F, T]; returns [B, 2, F, T].  ``stages`` (dict)
     receives the intermediate tensors the kernel-level tests compare against."""
-    assert cfg.get("subband_num", 1) == 1
+    sub = cfg.get("subband_num", 1)
+    # the reference forward itself raises for subband_num > 1 with TSSE / SE / CBAM (the real / imag attentions are built for
+    # F // subband_num + 1 channels but applied to F, fullsubnet_plus.py:47-50,157-163); only the channel-agnostic ECA runs
+    assert sub == 1 or cfg.get("channel_attention_model", "TSSE") == "ECA"
     la, ns, nfb = cfg["look_ahead"], cfg["sb_num_neighbors"], cfg["fb_num_neighbors"]
     norm = NORMS[cfg["norm_type"]]
     pad = lambda x: np.pad(np.asarray(x, dtype), ((0, 0), (0, 0), (0, 0), (0, la)))     # :137-139
@@ -477,8 +480,13 @@ def fullsubnet_plus_forward(p, cfg, mag, real, imag, dtype=np.float64, num_layer
     assert C == 1
     fb_in, fb_out = [], []
     for x, s in ((mag, ""), (real, "_real"), (imag, "_imag")):
-        xi = norm(x).reshape(B, F, T)                                                   # :144,157,162
-        xi = channel_attention(xi, p, f"channel_attention{s}", cfg)                         # :145,158,163
+        if sub > 1 and s == "":                                                         # :146-153, mag branch only
+            pn = sub - F % sub                                                          # (a whole extra group when F % sub == 0)
+            xi = np.pad(norm(x), ((0, 0), (0, 0), (0, pn), (0, 0)), mode="reflect").reshape(B, (F + pn) // sub, T * sub)
+            xi = channel_attention(xi, p, "channel_attention", cfg).reshape(B, F + pn, T)[:, :F]
+        else:
+            xi = norm(x).reshape(B, F, T)                                               # :144,157,162
+            xi = channel_attention(xi, p, f"channel_attention{s}", cfg)                     # :145,158,163
         fb_in.append(xi)
         fb_out.append(seq_tcn(xi, p, f"fb_model{s}", cfg["fb_output_activate_function"])
                       .reshape(B, 1, F, T))                                             # :154,159,164

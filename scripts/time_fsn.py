@@ -22,3 +22,19 @@ with torch.no_grad():
     for B in (1, 8):
         x = torch.rand(B, 1, 257, 188, device=dev)
         print(f"FullSubNet_Plus B={B}: {timeit(lambda: p(x, x - 0.5, x - 0.3)):.2f} ms  (sub-band LSTM {p.last_lstm_ms():.2f} ms)")
+    # other constructor values: GRU sub-band model (tcgen05 pair kernel with the GRU cell), SE attention, and BASELINE config #5
+    # (F = 513, H = 512, 3 layers, B = 32, T = 94: outside the tcgen05 kernel's TMEM envelope -> generic mma.sync kernel)
+    x = torch.rand(64, 1, 257, 188, device=dev)
+    g = FullSubNet_Plus(**dict(bench.default_cfg(), sequence_model="GRU")).to(dev).eval()
+    print(f"FullSubNet_Plus GRU B=64: {timeit(lambda: g(x, x - 0.5, x - 0.3)):.2f} ms  (sub-band GRU {g.last_lstm_ms():.2f} ms, {g.last_lstm_impl()})")
+    del g
+    a = FullSubNet_Plus(**dict(bench.default_cfg(), channel_attention_model="SE")).to(dev).eval()
+    print(f"FullSubNet_Plus SE attention B=64: {timeit(lambda: a(x, x - 0.5, x - 0.3)):.2f} ms")
+    del a
+    big = dict(bench.default_cfg(), num_freqs=513, sb_model_hidden_size=512, fb_model_hidden_size=512)
+    l = FullSubNet_Plus(**big, num_layers=3).to(dev).eval()
+    xl = torch.rand(32, 1, 513, 94, device=dev)
+    ms = timeit(lambda: l(xl, xl - 0.5, xl - 0.3), n=3)
+    flop = 32 * 525.9e9
+    print(f"config #5 (F=513, H=512, L=3, B=32, T=94): {ms:.2f} ms  (sub-band LSTM {l.last_lstm_ms():.2f} ms, {l.last_lstm_impl()}; "
+          f"{flop / ms / 1e9:.0f} TFLOP/s algorithmic)")

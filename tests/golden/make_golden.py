@@ -64,7 +64,8 @@ def run_plus(cfg, params, mag, real, imag):
         for h in hs:
             h.remove()
         outs.append(y.numpy().copy())
-        fb_in.append(np.stack([cap[n][0] for n in names[:3]]))
+        Fq, Tq = cap[names[1]][0].shape                 # subband_num > 1: the mag attention runs on [(F + pad) / sub, T * sub]
+        fb_in.append(np.stack([cap[n][0].reshape(-1, Tq)[:Fq] for n in names[:3]]))
         fb_out.append(np.stack([cap[n][0] for n in names[3:]]))
     return np.concatenate(outs), np.stack(fb_in, 1), np.stack(fb_out, 1)      # [B,2,F,T], [3,B,F,T'], [3,B,F,T']
 
@@ -168,6 +169,16 @@ def main():
         oo = O.fullsubnet_plus_forward(params, acfg, m, r, i)
         print(f"plus_small[{attn}]: oracle-vs-reference rel-L2 out={O.rel_l2(oo, out):.2e}")
         save(f"plus_small_{attn}", out=out, fb_in=fb_in, seed=5)
+
+    # subband_num > 1 (fullsubnet_plus.py:146-153) runs in the reference only with the channel-agnostic ECA attention;
+    # F = 33: subband_num = 2 pads one bin, subband_num = 3 pads a whole extra group (33 % 3 == 0)
+    for sub in (2, 3):
+        bcfg = dict(scfg, channel_attention_model="ECA", subband_num=sub)
+        params = O.make_params_plus(bcfg, seed=5)
+        out, fb_in, fb_out = run_plus(bcfg, params, m, r, i)
+        print(f"plus_small[ECA, subband_num={sub}]: oracle-vs-reference rel-L2 out="
+              f"{O.rel_l2(O.fullsubnet_plus_forward(params, bcfg, m, r, i), out):.2e}")
+        save(f"plus_small_ECA_sub{sub}", out=out, fb_in=fb_in, seed=5)
 
     # sequence_model = "GRU" (sequence_model.py:39-46): FullSubNet+ sub-band GRU, fullsubnet.Model full-band + sub-band GRU
     gcfg = dict(scfg, sequence_model="GRU")

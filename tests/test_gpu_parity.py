@@ -109,6 +109,20 @@ def test_plus_default_size_other_attentions_vs_oracle(built_lib, golden, attn):
     assert err < MASK_TOL
 
 
+@pytest.mark.parametrize("sub", [2, 3])
+def test_plus_small_subband_num_golden(built_lib, golden, sub):
+    """subband_num > 1 with ECA (the combination the reference forward supports, fullsubnet_plus.py:146-153)."""
+    g, gi = golden(f"plus_small_ECA_sub{sub}"), golden("plus_small")
+    cfg = dict(small_cfg(32), channel_attention_model="ECA", subband_num=sub)
+    m = build_plus(cfg, O.make_params_plus(cfg, seed=5))
+    with torch.no_grad():
+        out = m(_t(gi["mag"]), _t(gi["real"]), _t(gi["imag"]))
+    fb_in = m.get_stage("fb_in", (3, 3, 33, 22), DEV).cpu().numpy()
+    e_in, err = O.rel_l2(fb_in, g["fb_in"]), O.rel_l2(out.cpu().numpy(), g["out"])
+    print(f"\n[ECA subband_num={sub}] fb_in {e_in:.2e} cIRM {err:.3e}")
+    assert e_in < 1e-5 and err < MASK_TOL
+
+
 def test_gru_small_goldens_from_reference(built_lib, golden):
     """sequence_model = "GRU" (sequence_model.py:39-46), committed reference outputs: FullSubNet+ (H = 32 -> mma kernel) and
     fullsubnet.Model (full-band GRU on the weight-stationary kernel, sub-band GRU on the mma kernel)."""
@@ -392,13 +406,13 @@ def test_fused_postprocessing_matches_torch(built_lib):
     assert torch.allclose(torch.view_as_real(got), torch.view_as_real(want), rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("norm", ["cumulative_laplace_norm", "cumulative_layer_norm"])
-def test_streaming_step_api_matches_offline(built_lib, norm):
+@pytest.mark.parametrize("norm,rnn", [("cumulative_laplace_norm", "LSTM"), ("cumulative_layer_norm", "LSTM"), ("cumulative_laplace_norm", "GRU")])
+def test_streaming_step_api_matches_offline(built_lib, norm, rnn):
     """BASELINE config #4, frame-by-frame: the stateful step API (carried LSTM state + running norm sums) must reproduce
     the offline forward of the same causal model, frame for frame, and the oracle within the mask tolerance."""
     from fsnplus_b200.streaming import StreamingFullSubNet
     cfg = O.default_fsn_config()
-    cfg.update(num_freqs=65, sb_num_neighbors=7, sb_model_hidden_size=64, fb_model_hidden_size=96, norm_type=norm)
+    cfg.update(num_freqs=65, sb_num_neighbors=7, sb_model_hidden_size=64, fb_model_hidden_size=96, norm_type=norm, sequence_model=rnn)
     params = O.make_params_fsn(cfg, seed=13)
     B, T = 2, 23
     mag = small_inputs(B, 65, T, 9)[0]
@@ -419,7 +433,7 @@ def test_streaming_step_api_matches_offline(built_lib, norm):
     got = torch.stack(frames, dim=-1)                      # [B, 2, F, T]
     assert got.shape == offline.shape
     e_off, e_ref = O.rel_l2(got.cpu().numpy(), offline.cpu().numpy()), O.rel_l2(got.cpu().numpy(), ref)
-    print(f"\n[streaming {norm}] vs offline {e_off:.2e}  vs oracle {e_ref:.2e}")
+    print(f"\n[streaming {norm} {rnn}] vs offline {e_off:.2e}  vs oracle {e_ref:.2e}")
     assert e_off < 1e-4 and e_ref < MASK_TOL      # offline scan sums squares in fp32 per column, the step API in fp64
 
 

@@ -56,6 +56,22 @@ def test_state_dict_contract_other_attentions(attn):
         assert tuple(sd[k].shape) == v.shape, k
 
 
+def test_subband_num_mirrors_reference():
+    """subband_num > 1: attention containers get F // subband_num + 1 channels (fullsubnet_plus.py:47-50); the forward raises
+    for every attention but ECA, as the reference's does (shape mismatch on the real / imag branches, :157-163)."""
+    from fsnplus_b200.model import FullSubNet_Plus
+    cfg = dict(O.default_plus_config(), subband_num=2)
+    m = FullSubNet_Plus(**cfg)
+    assert m.num_channels == 129
+    assert tuple(m.state_dict()["channel_attention_real.fc1.weight"].shape) == (64, 129)
+    assert tuple(m.state_dict()["channel_attention.smallConv1d.0.weight"].shape) == (129, 1, 3)
+    x = torch.zeros(1, 1, 257, 8)
+    with pytest.raises(RuntimeError):
+        m(x, x, x)
+    e = FullSubNet_Plus(**dict(cfg, channel_attention_model="ECA"))
+    assert tuple(e.state_dict()["channel_attention.conv.weight"].shape) == (1, 1, 3)
+
+
 def test_state_dict_contract_gru():
     from fsnplus_b200.model import FullSubNet_Plus, Model
     cfg = dict(O.default_plus_config(), sequence_model="GRU")

@@ -43,6 +43,18 @@ def test_plus_small_other_attentions(golden, attn):
     assert O.rel_l2(st["fb_in"], g["fb_in"]) < TOL
 
 
+@pytest.mark.parametrize("sub", [2, 3])
+def test_plus_small_subband_num(golden, sub):
+    """subband_num > 1 (fullsubnet_plus.py:146-153) -- runs in the reference only with ECA; F = 33 pads 1 bin (sub = 2) or a
+    whole extra group (sub = 3)."""
+    g, gi = golden(f"plus_small_ECA_sub{sub}"), golden("plus_small")
+    cfg = dict(small_plus_cfg(), channel_attention_model="ECA", subband_num=sub)
+    st = {}
+    out = O.fullsubnet_plus_forward(O.make_params_plus(cfg, seed=5), cfg, gi["mag"], gi["real"], gi["imag"], stages=st)
+    assert O.rel_l2(out, g["out"]) < TOL
+    assert O.rel_l2(st["fb_in"], g["fb_in"]) < TOL
+
+
 def test_gru_variants(golden):
     """sequence_model = "GRU" (sequence_model.py:39-46) for both model classes, gates pushed towards saturation (x2)."""
     gi = golden("plus_small")
