@@ -538,10 +538,10 @@ static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s)
         { const char* ev = getenv("FSN_TC5_ELECT"); a.elect = ev ? atoi(ev) : 0; }
         { const char* ev = getenv("FSN_TC5_NSTAGE"); a.nstage_cap = ev ? atoi(ev) : 0; }
         { const char* ev = getenv("FSN_TC5_DEBUG"); a.debug = ev ? atoi(ev) : 0; }
-        int pair = 1;
+        int pair = 2;                                                   // 2: double-buffered pair kernel, 1: pair kernel, 0: single CTA
         { const char* ev = getenv("FSN_TC5_PAIR"); if (ev) pair = atoi(ev); }
-        if (a.gru) pair = 1;                                            // the GRU cell exists in the pair kernel only
-        int e = pair ? launch_lstm_tc5_pair(a, s) : launch_lstm_tc5(a, s);
+        if (a.gru && pair == 0) pair = 2;                               // the GRU cell exists in the pair kernels only
+        int e = pair == 2 ? launch_lstm_tc5_dbuf(a, s) : pair == 1 ? launch_lstm_tc5_pair(a, s) : launch_lstm_tc5(a, s);
         if (e) return fail(FSN_ECUDA, "tcgen05 LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
     } else {
         LstmMmaLaunch a{};

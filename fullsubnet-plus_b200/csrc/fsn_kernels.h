@@ -161,6 +161,7 @@ size_t lstm_tc5_cstate_bytes(int ntiles, int H);
 bool lstm_tc5_supported(int L, int H, int I, int O);
 int launch_lstm_tc5(const LstmTc5Launch& a, cudaStream_t s);
 int launch_lstm_tc5_pair(const LstmTc5Launch& a, cudaStream_t s);   // k_lstm_tc5p.cu: cta_group::2 version (2-CTA clusters)
+int launch_lstm_tc5_dbuf(const LstmTc5Launch& a, cudaStream_t s);   // k_lstm_tc5d.cu: pair kernel with two 64-column accumulators (default)
 
 // ---- k_gemm_tc5.cu (TCN on tcgen05, time-major activations) ----------------------------------
 enum { EPI5_PRELU_STATS = 1, EPI5_GLN_RES = 2, EPI5_OUT = 3 };

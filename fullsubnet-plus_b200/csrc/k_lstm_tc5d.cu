@@ -1,0 +1,361 @@
+// CTA-pair persistent tcgen05 LSTM with DOUBLE-BUFFERED accumulators (the default sub-band kernel; k_lstm_tc5p.cu is the
+// single-accumulator pair kernel it grew out of, k_lstm_tc5.cu the single-CTA design; reference: sequence_model.py:113-122,
+// fullsubnet_plus.py:205-208).
+//
+// Why: TMEM is full (h0 192 + h1 192 + one 128-column accumulator = 512 columns), so the pair kernel serialises
+// "MMA chunk j -> drain chunk j -> MMA chunk j+1": ncu shows the tensor pipe 77 % active, the rest is 24 drain bubbles of
+// ~600 cycles per time step.  A 64-column cta_group::2 MMA runs at exactly half the time of a 128-column one when issued in
+// blocks of >= 8 (fsn_probe_tcgen05: 32.1 vs 64.1 cycles), so the 128 accumulator columns are split into TWO 64-column
+// accumulators: every 128-gate-column chunk is computed as two half-chunks, the epilogue warps are split into two sets
+// (set = column group & 1), and the MMAs of one half overlap the drain + cell update of the other.
+//   * half h of a chunk = column groups {h, h + 2}: CTA r of the pair contributes rows [32 h, 32 h + 32) of ITS 64-row
+//     half-tile, i.e. column group 2 r + h -- the packed weight stream is unchanged, only the copy order differs
+//     (per chunk: all k-blocks of half 0, then all k-blocks of half 1; 4 KB sub-blocks, ring slots of up to 4 sub-blocks);
+//   * accumulator h lives at columns [384 + 64 h, 448 + 64 h); column group cg reads accumulator cg & 1 at offset 32 (cg >> 1);
+//   * one accfull / accempty mbarrier pair per accumulator (8 epilogue warps per CTA arrive on each).
+// Everything else (producer / relay / leader-issuer roles, multicast commits, h parked in shared memory until the layer's
+// MMAs are done, cell state through L2, fused output Linear) is the pair kernel's protocol.
+#include "fsn_common.cuh"
+#include "fsn_kernels.h"
+#include "../../include/fsnplus_b200.h"
+
+namespace fsn {
+
+constexpr int D5_KB = 8192;         // one k-block of my half-tile in the packed stream: 64 of the 128 gate columns x 64 k x fp16
+constexpr int D5_SUB = 4096;        // the 32 gate columns of one half-chunk of it
+constexpr int D5_STAGE = 4 * D5_SUB; // a ring slot holds a GROUP of up to 4 sub-blocks: one mbarrier wait + one commit per 16 N=64 MMAs
+constexpr int D5_STAGE_FULL = 16384;
+constexpr int D5_XIMG = 16384;
+constexpr int D5_EPI_WARPS = 16;
+constexpr int D5_THREADS = (D5_EPI_WARPS + 2) * 32;
+constexpr int D5_MAX_SMEM = 227 * 1024;
+
+struct D5Plan { int nstage; size_t total; };
+static inline D5Plan d5_plan(int H) {
+    D5Plan p;
+    const size_t fixed = D5_XIMG + (size_t)128 * H * 2 /*park*/ + (size_t)2 * 4 * H * 4 /*pre-scaled biases*/ + 4 * 128 * 2 * 4 + 64 * 8;
+    long avail = D5_MAX_SMEM - 1024 - (long)fixed;
+    p.nstage = (int)(avail / D5_STAGE);
+    if (p.nstage > 8) p.nstage = 8;
+    p.total = fixed + (size_t)p.nstage * D5_STAGE + 1024;
+    return p;
+}
+
+template <int H, bool FAST, bool GRU>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_tc5d_kernel(LstmTc5Launch a, int nstage) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int NCH = H / 32, KBH = H / 64, hcols = H / 2;
+    const int Tp = a.Tp;
+    const int tile = blockIdx.x;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = (rank == 0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* stages = smem;
+    uint8_t* ximg = stages + (size_t)nstage * D5_STAGE;
+    uint8_t* park = ximg + D5_XIMG;
+    float* bsm = reinterpret_cast<float*>(park + (size_t)128 * H * 2);       // [2][NCH][128] pre-scaled biases
+    float* fcpart = bsm + 2 * 4 * H;                                         // [4][128][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fcpart + 4 * 128 * 2);
+    uint64_t* full = bars;
+    uint64_t* empty = full + nstage;
+    uint64_t* xfull = empty + nstage;
+    uint64_t* xempty = xfull + 1;
+    uint64_t* accfull = xempty + 1;                                          // [2]
+    uint64_t* accempty = accfull + 2;                                        // [2]
+    uint64_t* hready = accempty + 2;
+    uint64_t* layerdone = hready + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layerdone + 1);
+
+    if (tid == 0) {
+        for (int i = 0; i < nstage; ++i) { mbar_init(&full[i], leader ? 2 : 1); mbar_init(&empty[i], 1); }
+        mbar_init(xfull, leader ? 2 : 1); mbar_init(xempty, 1);
+        for (int h = 0; h < 2; ++h) { mbar_init(&accfull[h], 1); mbar_init(&accempty[h], D5_EPI_WARPS); }   // 8 warps x 2 CTAs
+        mbar_init(hready, 2 * D5_EPI_WARPS);
+        mbar_init(layerdone, 1);
+        fence_barrier_init();
+    }
+    if (warp == D5_EPI_WARPS + 1) tmem_alloc_pair<512>(tmem_slot);
+    for (int i = tid; i < 2 * 4 * H; i += D5_THREADS) bsm[i] = a.bias[i];
+    tc5_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                            // barriers of both CTAs are initialised
+    tc5_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t acc_col = 2 * hcols;
+
+    if (warp == D5_EPI_WARPS) {
+        // ======================= bulk-copy producer (both CTAs, own half) ===================
+        if (lane == 0) {
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wstream) + (size_t)rank * D5_KB;
+            const uint8_t* xsrc = reinterpret_cast<const uint8_t*>(a.img) + (size_t)tile * Tp * D5_XIMG;
+            int slot = 0; uint32_t ph = 0;
+            mbar_arrive_expect_tx(xfull, D5_XIMG);
+            bulk_g2s(ximg, xsrc, D5_XIMG, xfull);
+            constexpr int NKB0 = 1 + KBH, NKB1 = 2 * KBH;           // k-blocks per chunk: x | h0, h0 | h1
+            for (int t = 0; t < Tp; ++t) {
+                for (int layer = 0; layer < 2; ++layer) {
+                    const int nkb = layer == 0 ? NKB0 : NKB1;
+                    for (int j = 0; j < NCH; ++j) {
+                        const int kb_base = layer == 0 ? j * NKB0 : NCH * NKB0 + j * NKB1;   // k-block index in the per-step stream
+                        for (int half = 0; half < 2; ++half) {
+                            if (layer == 1 && j == NCH / 2 && half == 0 && t + 1 < Tp) {     // x_{t+1}: layer 0 of step t is long done
+                                mbar_wait(xempty, t & 1);
+                                mbar_arrive_expect_tx(xfull, D5_XIMG);
+                                bulk_g2s(ximg, xsrc + (size_t)(t + 1) * D5_XIMG, D5_XIMG, xfull);
+                            }
+                            for (int kb0 = 0; kb0 < nkb; kb0 += 4) {
+                                const int nk = (nkb - kb0 < 4) ? nkb - kb0 : 4;
+                                mbar_wait(&empty[slot], ph ^ 1);
+                                mbar_arrive_expect_tx(&full[slot], nk * D5_SUB);
+                                for (int i = 0; i < nk; ++i)
+                                    bulk_g2s(stages + (size_t)slot * D5_STAGE + i * D5_SUB,
+                                             wsrc + (size_t)(kb_base + kb0 + i) * D5_STAGE_FULL + half * D5_SUB, D5_SUB, &full[slot]);
+                                if (++slot == nstage) { slot = 0; ph ^= 1; }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == D5_EPI_WARPS + 1) {
+        if (leader) {
+            // ======================= MMA issuer for BOTH SMs ===============================
+            // Compile-time chunk / k-block structure, incremental descriptor words, one wait + one commit per group of
+            // up to 8 MMAs: the issue warp must stay below the tensor pipe's 64-74 cycles per instruction.
+            constexpr uint32_t IDESC = umma_idesc_f16(256, 64);
+            constexpr uint32_t DESC_HI = 0x40004040u;              // SBO = 1024 B, version 1, SWIZZLE_128B (umma_desc_sw128)
+            uint32_t d = tmem + acc_col;                           // accumulator of the current half-chunk
+            const uint32_t stage_lo0 = ((smem_u32(stages) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t x_lo = ((smem_u32(ximg) >> 4) & 0x3FFFu) | (1u << 16);
+            int slot = 0; uint32_t ph = 0, accuse = 0, ls = 0;
+            auto mma_ss = [&](uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+                asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+                             "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(IDESC), "r"(acc), "r"(DESC_HI) : "memory");
+            };
+            auto mma_ts = [&](uint32_t a_col, uint32_t b_lo, uint32_t acc) {
+                asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 db, {%2, %5};\n\t"
+                             "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(d), "r"(tmem + a_col), "r"(b_lo), "r"(IDESC), "r"(acc), "r"(DESC_HI) : "memory");
+            };
+            // one k-block = 4 MMAs; kbi = index of the k-block inside its chunk (layer 0: 0 = x block, 1.. = h0; layer 1: h0 then h1)
+            auto kblock = [&](int layer, int kbi, uint32_t b_lo) {
+                if (layer == 0 && kbi == 0) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) mma_ss(x_lo + 2 * kk, b_lo + 2 * kk, kk != 0);
+                } else {
+                    const uint32_t acol = (layer == 0) ? (kbi - 1) * 32 : (kbi < KBH ? kbi * 32 : hcols + (kbi - KBH) * 32);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) mma_ts(acol + kk * 8, b_lo + 2 * kk, (kbi | kk) != 0);
+                }
+            };
+            for (int t = 0; t < Tp; ++t) {
+#pragma unroll
+                for (int layer = 0; layer < 2; ++layer, ++ls) {
+                    mbar_wait(hready, ls & 1);
+                    if (layer == 0) mbar_wait(xfull, t & 1);
+                    tc5_fence_after();
+                    constexpr int NKB0 = 1 + KBH, NKB1 = 2 * KBH;
+                    const int nkb = layer == 0 ? NKB0 : NKB1;
+                    for (int j = 0; j < NCH; ++j) {
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            if (!(a.debug & 2)) mbar_wait(&accempty[half], (accuse & 1) ^ 1);
+                            tc5_fence_after();
+                            d = tmem + acc_col + 64 * half;
+#pragma unroll
+                            for (int kb0 = 0; kb0 < NKB1; kb0 += 4) {
+                                if (kb0 < nkb) {
+                                    mbar_wait(&full[slot], ph);
+                                    tc5_fence_after();
+                                    const uint32_t b_lo = stage_lo0 + slot * (D5_STAGE >> 4);
+                                    if (elect_one()) {
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i)
+                                            if (kb0 + i < nkb) kblock(layer, kb0 + i, b_lo + i * (D5_SUB >> 4));
+                                        umma2_commit_mc(&empty[slot], 3);
+                                        if (kb0 + 4 >= nkb) {
+                                            umma2_commit_mc(&accfull[half], 3);
+                                            if (j == NCH - 1 && half == 1) {
+                                                if (layer == 0) umma2_commit_mc(xempty, 3);
+                                                umma2_commit_mc(layerdone, 3);
+                                            }
+                                        }
+                                    }
+                                    __syncwarp();
+                                    if (++slot == nstage) { slot = 0; ph ^= 1; }
+                                }
+                            }
+                        }
+                        ++accuse;
+                    }
+                }
+            }
+        } else {
+            // ======================= peer relay: my half-tiles have landed -> leader ========
+            if (lane == 0) {
+                const uint32_t r_xfull = mapa_u32(smem_u32(xfull), 0);
+                int slot = 0; uint32_t ph = 0;
+                constexpr int NG = 2 * NCH * ((1 + KBH + 3) / 4 + (2 * KBH + 3) / 4);   // groups per time step (producer loop)
+                for (int t = 0; t < Tp; ++t) {
+                    mbar_wait(xfull, t & 1);
+                    mbar_arrive_remote(r_xfull);
+                    for (int g = 0; g < NG; ++g) {
+                        mbar_wait(&full[slot], ph);
+                        mbar_arrive_remote(mapa_u32(smem_u32(&full[slot]), 0));
+                        if (++slot == nstage) { slot = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else {
+        // ======================= epilogue warps (both CTAs, own 128 sequences) ==============
+        const int cg = warp >> 2;
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+        const int set = cg & 1;                                     // which accumulator / half-chunk this warp serves
+        const uint32_t acc_my = acc_col + 64 * set + 32 * (cg >> 1);
+        uint64_t* my_accfull = &accfull[set];
+        uint64_t* my_accempty = &accempty[set];
+        const uint32_t r_accempty = mapa_u32(smem_u32(my_accempty), 0), r_hready = mapa_u32(smem_u32(hready), 0);
+        {
+            const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int c = cg; c < 2 * NCH * 2; c += 4) tmem_st8(tl + c * 8, z);
+            tmem_wait_st();
+            tc5_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (leader) mbar_arrive(hready); else mbar_arrive_remote(r_hready); }
+        }
+        uint32_t accn = 0, ls = 0;
+        float4 cnext[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};   // t = 0: zero cell state
+        float* cbase = a.cstate + (size_t)tile * 2 * H * 128;
+        uint8_t* mypark = park + ((size_t)cg * NCH * 128 + r) * 16;
+        const int grow = tile * 128 + r;
+        const int ob = grow / a.F, of = grow % a.F;
+        const int Tout = Tp - a.la;
+        const float fcb0 = __ldg(a.fc_b), fcb1 = __ldg(a.fc_b + 1);
+
+        for (int t = 0; t < Tp; ++t) {
+            for (int layer = 0; layer < 2; ++layer, ++ls) {
+                float fc0 = 0.f, fc1 = 0.f;
+                for (int j = 0; j < NCH; ++j) {
+                    float4* cp = reinterpret_cast<float4*>(cbase + ((size_t)((layer * NCH + j) * 4 + cg) * 2) * 128 * 4) + r;
+                    const float4 c4[2] = {cnext[0], cnext[1]};     // prefetched during the previous chunk
+                    const float4* bj = reinterpret_cast<const float4*>(bsm + (size_t)(layer * NCH + j) * 128 + cg * 32);
+                    mbar_wait(my_accfull, accn & 1);
+                    ++accn;
+                    tc5_fence_after();
+                    uint32_t v[2][16];
+                    tmem_ld16(tl + acc_my, v[0]);
+                    tmem_ld16(tl + acc_my + 16, v[1]);
+                    tmem_wait_ld();
+                    tc5_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { if (leader) mbar_arrive(my_accempty); else mbar_arrive_remote(r_accempty); }
+                    {   // cell state of the NEXT chunk in program order: (layer, j+1), else chunk 0 of the other layer (next step after layer 1)
+                        const int nj = (j + 1 < NCH) ? j + 1 : 0;
+                        const int nl = (j + 1 < NCH) ? layer : (layer ^ 1);
+                        const int nt = (j + 1 < NCH || layer == 0) ? t : t + 1;
+                        const float4* np = reinterpret_cast<const float4*>(cbase + ((size_t)((nl * NCH + nj) * 4 + cg) * 2) * 128 * 4) + r;
+                        if (nt == 0 || nt >= Tp) { cnext[0] = make_float4(0.f, 0.f, 0.f, 0.f); cnext[1] = cnext[0]; }
+                        else { cnext[0] = np[0]; cnext[1] = np[128]; }
+                    }
+
+                    if (a.debug & 1) continue;                     // timing experiment: drain only, no cell update
+                    const float L2E = 1.4426950408889634f;
+                    uint32_t hp[4];
+                    float cn[8];
+#pragma unroll
+                    for (int u4 = 0; u4 < 2; ++u4) {
+                        const float4 bi = bj[u4], bf = bj[2 + u4], bg = bj[4 + u4], bo = bj[6 + u4];
+                        const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, bfa[4] = {bf.x, bf.y, bf.z, bf.w};
+                        const float bga[4] = {bg.x, bg.y, bg.z, bg.w}, boa[4] = {bo.x, bo.y, bo.z, bo.w};
+                        const float cpv[4] = {c4[u4].x, c4[u4].y, c4[u4].z, c4[u4].w};
+                        float hv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int u = u4 * 4 + e;
+                            if (GRU) {
+                                gru_cell<FAST>(fmaf(__uint_as_float(v[0][u]), -L2E, bia[e]), fmaf(__uint_as_float(v[0][8 + u]), -L2E, bfa[e]),
+                                               fmaf(__uint_as_float(v[1][u]), -2.f * L2E, bga[e]), fmaf(__uint_as_float(v[1][8 + u]), -2.f * L2E, boa[e]),
+                                               cpv[e], hv[e]);
+                                cn[u] = hv[e];
+                            } else {
+                                lstm_cell<FAST>(fmaf(__uint_as_float(v[0][u]), -L2E, bia[e]), fmaf(__uint_as_float(v[0][8 + u]), -L2E, bfa[e]),
+                                                fmaf(__uint_as_float(v[1][u]), -2.f * L2E, bga[e]), fmaf(__uint_as_float(v[1][8 + u]), -L2E, boa[e]),
+                                                cpv[e], cn[u], hv[e]);
+                            }
+                        }
+                        if (layer == 1) {
+                            const float4 wa = __ldg(reinterpret_cast<const float4*>(a.fc_w + j * 32 + cg * 8) + u4);
+                            const float4 wb = __ldg(reinterpret_cast<const float4*>(a.fc_w + H + j * 32 + cg * 8) + u4);
+                            fc0 = fmaf(hv[0], wa.x, fmaf(hv[1], wa.y, fmaf(hv[2], wa.z, fmaf(hv[3], wa.w, fc0))));
+                            fc1 = fmaf(hv[0], wb.x, fmaf(hv[1], wb.y, fmaf(hv[2], wb.z, fmaf(hv[3], wb.w, fc1))));
+                        }
+                        hp[2 * u4] = pack_half2(hv[0], hv[1]);
+                        hp[2 * u4 + 1] = pack_half2(hv[2], hv[3]);
+                    }
+                    cp[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                    cp[128] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                    *reinterpret_cast<uint4*>(mypark + (size_t)j * 128 * 16) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                }
+                mbar_wait(layerdone, ls & 1);
+                tc5_fence_after();
+                for (int j = 0; j < NCH; ++j) {
+                    const uint4 p0 = *reinterpret_cast<const uint4*>(mypark + (size_t)j * 128 * 16);
+                    const uint32_t hv[4] = {p0.x, p0.y, p0.z, p0.w};
+                    tmem_st4(tl + layer * hcols + j * 16 + cg * 4, hv);
+                }
+                tmem_wait_st();
+                tc5_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (leader) mbar_arrive(hready); else mbar_arrive_remote(r_hready); }
+
+                if (layer == 1) {
+                    if (cg != 0) { fcpart[(cg * 128 + r) * 2] = fc0; fcpart[(cg * 128 + r) * 2 + 1] = fc1; }
+                    asm volatile("bar.sync 1, 512;" ::: "memory");
+                    if (cg == 0 && t >= a.la && grow < a.rows) {
+                        const float o0 = fc0 + fcpart[(128 + r) * 2] + fcpart[(256 + r) * 2] + fcpart[(384 + r) * 2] + fcb0;
+                        const float o1 = fc1 + fcpart[(128 + r) * 2 + 1] + fcpart[(256 + r) * 2 + 1] + fcpart[(384 + r) * 2 + 1] + fcb1;
+                        a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)] = o0;
+                        a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)] = o1;
+                    }
+                    asm volatile("bar.sync 2, 512;" ::: "memory");
+                }
+            }
+        }
+    }
+    tc5_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc5_fence_after();
+    if (warp == D5_EPI_WARPS + 1) tmem_dealloc_pair<512>(tmem);
+}
+
+int launch_lstm_tc5_dbuf(const LstmTc5Launch& a, cudaStream_t s) {
+    if (!lstm_tc5_supported(2, a.H, a.I, 2)) return (int)cudaErrorInvalidValue;
+    D5Plan p = d5_plan(a.H);
+    if (a.nstage_cap > 0 && a.nstage_cap < p.nstage) { p.total -= (size_t)(p.nstage - a.nstage_cap) * D5_STAGE; p.nstage = a.nstage_cap; }
+    if (p.nstage < 2) return (int)cudaErrorInvalidValue;
+    const int grid = (a.ntiles + 1) / 2 * 2;                        // whole pairs; the buffers cover the padded tile
+    cudaError_t e = cudaErrorInvalidValue;
+#define D5_GO(HH, FF, GG)                                                                                               \
+    {                                                                                                                   \
+        e = cudaFuncSetAttribute(lstm_tc5d_kernel<HH, FF, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);  \
+        if (e != cudaSuccess) return (int)e;                                                                            \
+        lstm_tc5d_kernel<HH, FF, GG><<<grid, D5_THREADS, p.total, s>>>(a, p.nstage);                                   \
+    }
+#define D5_LAUNCH(HH)                                                                                                   \
+    if (a.H == HH) {                                                                                                    \
+        if (a.gru) { if (a.fast) D5_GO(HH, true, true) else D5_GO(HH, false, true) }                                    \
+        else { if (a.fast) D5_GO(HH, true, false) else D5_GO(HH, false, false) }                                        \
+    }
+    D5_LAUNCH(64) D5_LAUNCH(128) D5_LAUNCH(192) D5_LAUNCH(256) D5_LAUNCH(320) D5_LAUNCH(384)
+#undef D5_GO
+#undef D5_LAUNCH
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace fsn

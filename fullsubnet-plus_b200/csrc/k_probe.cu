@@ -239,7 +239,7 @@ static float run_issue(long long* dc) {
 
 // ---- probe 5: CTA pair (cta_group::2).  D[256 x 128] = A[256 x 64] * B[128 x 64]^T: each CTA holds its own 128 rows of A and
 // 64 rows of B (CTA rank r: B rows [64 r, 64 r + 64)); the leader issues the MMAs for both SMs; commit multicasts to both.
-struct Probe5Args { const uint8_t* a_img; const uint8_t* b_img; const uint32_t* a_plain; float* d; long long* cycles; int mode; int reps; };
+struct Probe5Args { const uint8_t* a_img; const uint8_t* b_img; const uint32_t* a_plain; float* d; long long* cycles; int mode; int reps; int N; int per; };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe_pair_kernel(Probe5Args p) {
     extern __shared__ uint8_t smem_raw[];
@@ -259,9 +259,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe_pair_k
     const uint32_t tmem = *tslot;
     const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
     if (tid == 0) {
-        mbar_arrive_expect_tx(&bars[0], 16384 + 8192);
+        const uint32_t bbytes = (uint32_t)p.N * 64;          // my N / 2 rows of B (64 halves each)
+        mbar_arrive_expect_tx(&bars[0], 16384 + bbytes);
         bulk_g2s(sa, p.a_img + (size_t)rank * 16384, 16384, &bars[0]);
-        bulk_g2s(sb, p.b_img + (size_t)rank * 8192, 8192, &bars[0]);
+        bulk_g2s(sb, p.b_img + (size_t)rank * bbytes, bbytes, &bars[0]);
     }
     {   // A operand into TMEM columns [256, 288): my row
         const uint32_t* src = p.a_plain + ((size_t)rank * 128 + tid) * 32;
@@ -280,9 +281,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe_pair_k
     cluster_sync_all();                 // both CTAs' operands are in place
     tc5_fence_after();
     if (rank == 0 && warp == 0) {
-        const uint32_t idesc = umma_idesc_f16(256, 128);
+        const uint32_t idesc = umma_idesc_f16(256, p.N);
         const uint64_t adesc = umma_desc_sw128(smem_u32(sa)), bdesc = umma_desc_sw128(smem_u32(sb));
         long long t0 = clock64();
+        if (p.per == 8) {                                    // 8 MMAs per elected block, alternating between two accumulators
+            for (int r = 0; r < p.reps; r += 2) {
+                if (elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint32_t acc = tmem + ((kk & 4) ? (uint32_t)p.N : 0u);
+                        umma2_ts(acc, tmem + 256 + (kk & 3) * 8, bdesc + 2 * (kk & 3), idesc, (r | (kk & 3)) != 0);
+                    }
+                }
+                __syncwarp();
+            }
+        } else
         for (int r = 0; r < p.reps; ++r) {
             if (elect_one()) {
 #pragma unroll
@@ -300,7 +313,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe_pair_k
     }
     mbar_wait(&bars[1], 0);
     tc5_fence_after();
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < p.N / 16; ++c) {
         uint32_t v[16];
         tmem_ld16(tl + c * 16, v);
         tmem_wait_ld();
@@ -428,7 +441,7 @@ int run_probe_tcgen05(float* report, int n) {
         cudaMemcpy(dp2, a2plain.data(), a2plain.size() * 4, cudaMemcpyHostToDevice);
         const size_t smem5 = 16384 + 8192 + 64 + 1024;
         cudaFuncSetAttribute(probe_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
-        Probe5Args q5{da2, db2, dp2, dd2, dc, 0, 1};
+        Probe5Args q5{da2, db2, dp2, dd2, dc, 0, 1, 128, 4};
         bool ok5 = true;
         for (int mode = 0; mode < 2 && ok5; ++mode) {
             q5.mode = mode; q5.reps = 1;
@@ -452,6 +465,38 @@ int run_probe_tcgen05(float* report, int n) {
             long long cyc = 0;
             cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost);
             report[rc++] = (float)cyc / (512.0f * 4.0f);
+        }
+        // N = 64 pair MMAs (two 64-column accumulators fit where one 128-column accumulator does): B rows [32 r, 32 r + 32) per CTA
+        if (ok5 && rc + 5 <= n) {
+            std::vector<uint8_t> b64img(2 * 4096);
+            for (int r = 0; r < 64; ++r)
+                for (int k = 0; k < 64; ++k) std::memcpy(&b64img[(size_t)(r / 32) * 4096 + sw128_offset(r % 32, k)], &B2[r * 64 + k], 2);
+            cudaMemcpy(db2, b64img.data(), b64img.size(), cudaMemcpyHostToDevice);
+            q5.N = 64; q5.mode = 1; q5.per = 4; q5.reps = 1;
+            cudaMemset(dd2, 0, D2.size() * 4);
+            probe_pair_kernel<<<2, 128, smem5>>>(q5);
+            if (cudaDeviceSynchronize() != cudaSuccess) ok5 = false;
+            if (ok5) {
+                cudaMemcpy(D2.data(), dd2, D2.size() * 4, cudaMemcpyDeviceToHost);
+                double maxerr = 0;
+                for (int r = 0; r < 256; ++r)
+                    for (int c = 0; c < 64; ++c) {
+                        double ref = 0;
+                        for (int k = 0; k < 64; ++k) ref += (double)h_val(A2[r * 64 + k]) * (double)h_val(B2[c * 64 + k]);
+                        maxerr = std::fmax(maxerr, std::fabs(ref - (double)D2[r * 128 + c]));
+                    }
+                report[rc++] = (float)maxerr;
+            }
+            const int cfgs[4][2] = {{64, 4}, {64, 8}, {128, 4}, {128, 8}};      // {N, MMAs per elected block}
+            for (int i = 0; i < 4 && ok5; ++i) {
+                if (cfgs[i][0] == 128) cudaMemcpy(db2, b2img.data(), b2img.size(), cudaMemcpyHostToDevice);
+                q5.N = cfgs[i][0]; q5.per = cfgs[i][1]; q5.mode = 1; q5.reps = 512;
+                probe_pair_kernel<<<2, 128, smem5>>>(q5);
+                if (cudaDeviceSynchronize() != cudaSuccess) { ok5 = false; break; }
+                long long cyc = 0;
+                cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost);
+                report[rc++] = (float)cyc / (512.0f * 4.0f);
+            }
         }
         cudaFree(da2); cudaFree(db2); cudaFree(dp2); cudaFree(dd2);
         if (!ok5) rc = -2000 - (int)cudaGetLastError();
