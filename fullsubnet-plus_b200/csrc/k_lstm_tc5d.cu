@@ -64,15 +64,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
     uint64_t* xempty = xfull + 1;
     uint64_t* accfull = xempty + 1;                                          // [2]
     uint64_t* accempty = accfull + 2;                                        // [2]
-    uint64_t* hready = accempty + 2;
-    uint64_t* layerdone = hready + 1;
+    uint64_t* hready = accempty + 2;                                         // [2]: h of layer 0 / layer 1 is in TMEM
+    uint64_t* layerdone = hready + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layerdone + 1);
 
     if (tid == 0) {
         for (int i = 0; i < nstage; ++i) { mbar_init(&full[i], leader ? 2 : 1); mbar_init(&empty[i], 1); }
         mbar_init(xfull, leader ? 2 : 1); mbar_init(xempty, 1);
         for (int h = 0; h < 2; ++h) { mbar_init(&accfull[h], 1); mbar_init(&accempty[h], D5_EPI_WARPS); }   // 8 warps x 2 CTAs
-        mbar_init(hready, 2 * D5_EPI_WARPS);
+        mbar_init(&hready[0], 2 * D5_EPI_WARPS); mbar_init(&hready[1], 2 * D5_EPI_WARPS);
         mbar_init(layerdone, 1);
         fence_barrier_init();
     }
@@ -109,9 +109,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                                 const int nk = (nkb - kb0 < 4) ? nkb - kb0 : 4;
                                 mbar_wait(&empty[slot], ph ^ 1);
                                 mbar_arrive_expect_tx(&full[slot], nk * D5_SUB);
-                                for (int i = 0; i < nk; ++i)
+                                for (int i = 0; i < nk; ++i) {
+                                    int kbs = kb0 + i;                      // layer 1: consumed recurrent part (stream k-blocks KBH..) first
+                                    if (layer == 1) kbs = (kbs < KBH) ? KBH + kbs : kbs - KBH;
                                     bulk_g2s(stages + (size_t)slot * D5_STAGE + i * D5_SUB,
-                                             wsrc + (size_t)(kb_base + kb0 + i) * D5_STAGE_FULL + half * D5_SUB, D5_SUB, &full[slot]);
+                                             wsrc + (size_t)(kb_base + kbs) * D5_STAGE_FULL + half * D5_SUB, D5_SUB, &full[slot]);
+                                }
                                 if (++slot == nstage) { slot = 0; ph ^= 1; }
                             }
                         }
@@ -138,22 +141,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                 asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 db, {%2, %5};\n\t"
                              "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(d), "r"(tmem + a_col), "r"(b_lo), "r"(IDESC), "r"(acc), "r"(DESC_HI) : "memory");
             };
-            // one k-block = 4 MMAs; kbi = index of the k-block inside its chunk (layer 0: 0 = x block, 1.. = h0; layer 1: h0 then h1)
+            // one k-block = 4 MMAs; kbi = index of the k-block inside its chunk (layer 0: 0 = x block, 1.. = h0(t-1); layer 1: h1(t-1)
+            // FIRST, then h0(t): the recurrent half does not depend on the layer-0 epilogue that is still finishing at the boundary)
             auto kblock = [&](int layer, int kbi, uint32_t b_lo) {
                 if (layer == 0 && kbi == 0) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) mma_ss(x_lo + 2 * kk, b_lo + 2 * kk, kk != 0);
                 } else {
-                    const uint32_t acol = (layer == 0) ? (kbi - 1) * 32 : (kbi < KBH ? kbi * 32 : hcols + (kbi - KBH) * 32);
+                    const uint32_t acol = (layer == 0) ? (kbi - 1) * 32 : (kbi < KBH ? hcols + kbi * 32 : (kbi - KBH) * 32);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) mma_ts(acol + kk * 8, b_lo + 2 * kk, (kbi | kk) != 0);
                 }
             };
+            // Dependencies across layer boundaries (one hready barrier per layer; phase 0 of both = the initial zeroing):
+            //   layer 0, step t  reads x(t), h0(t-1): h0(t-1) was awaited by layer 1 of step t-1 -> no wait, the MMAs start while
+            //                    the layer-1 epilogue of step t-1 is still running (it only writes h1 columns);
+            //   layer 1, step t  reads h1(t-1) [hready[1] phase t] from its first MMA and h0(t) [hready[0] phase t+1] from the
+            //                    first h0 k-block of its first half-chunk.
+            mbar_wait(&hready[0], 0);
+            tc5_fence_after();
             for (int t = 0; t < Tp; ++t) {
 #pragma unroll
                 for (int layer = 0; layer < 2; ++layer, ++ls) {
-                    mbar_wait(hready, ls & 1);
                     if (layer == 0) mbar_wait(xfull, t & 1);
+                    else mbar_wait(&hready[1], t & 1);
                     tc5_fence_after();
                     constexpr int NKB0 = 1 + KBH, NKB1 = 2 * KBH;
                     const int nkb = layer == 0 ? NKB0 : NKB1;
@@ -172,7 +183,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                                     if (elect_one()) {
 #pragma unroll
                                         for (int i = 0; i < 4; ++i)
-                                            if (kb0 + i < nkb) kblock(layer, kb0 + i, b_lo + i * (D5_SUB >> 4));
+                                            if (kb0 + i < nkb) {
+                                                if (layer == 1 && kb0 + i == KBH && j == 0 && half == 0) {   // h0(t) is needed from here on
+                                                    mbar_wait(&hready[0], (t + 1) & 1);
+                                                    tc5_fence_after();
+                                                }
+                                                kblock(layer, kb0 + i, b_lo + i * (D5_SUB >> 4));
+                                            }
                                         umma2_commit_mc(&empty[slot], 3);
                                         if (kb0 + 4 >= nkb) {
                                             umma2_commit_mc(&accfull[half], 3);
@@ -218,14 +235,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
         const uint32_t acc_my = acc_col + 64 * set + 32 * (cg >> 1);
         uint64_t* my_accfull = &accfull[set];
         uint64_t* my_accempty = &accempty[set];
-        const uint32_t r_accempty = mapa_u32(smem_u32(my_accempty), 0), r_hready = mapa_u32(smem_u32(hready), 0);
+        const uint32_t r_accempty = mapa_u32(smem_u32(my_accempty), 0);
+        const uint32_t r_hready[2] = {mapa_u32(smem_u32(&hready[0]), 0), mapa_u32(smem_u32(&hready[1]), 0)};
         {
             const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int c = cg; c < 2 * NCH * 2; c += 4) tmem_st8(tl + c * 8, z);
             tmem_wait_st();
             tc5_fence_before();
             __syncwarp();
-            if (lane == 0) { if (leader) mbar_arrive(hready); else mbar_arrive_remote(r_hready); }
+            if (lane == 0)
+                for (int l = 0; l < 2; ++l) { if (leader) mbar_arrive(&hready[l]); else mbar_arrive_remote(r_hready[l]); }
         }
         uint32_t accn = 0, ls = 0;
         float4 cnext[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};   // t = 0: zero cell state
@@ -310,7 +329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                 tmem_wait_st();
                 tc5_fence_before();
                 __syncwarp();
-                if (lane == 0) { if (leader) mbar_arrive(hready); else mbar_arrive_remote(r_hready); }
+                if (lane == 0) { if (leader) mbar_arrive(&hready[layer]); else mbar_arrive_remote(r_hready[layer]); }
 
                 if (layer == 1) {
                     if (cg != 0) { fcpart[(cg * 128 + r) * 2] = fc0; fcpart[(cg * 128 + r) * 2 + 1] = fc1; }
