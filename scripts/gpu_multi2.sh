@@ -2,7 +2,7 @@
 # 2-GPU pass with the current kernels: weak-scaling bench lines, sharded-harness check, and the command line under torchrun
 # (files dealt to the ranks) compared byte for byte with a single-process run.
 cd "$(dirname "$0")/.."
-mkdir -p gpurun_out; export PYTHONDONTWRITEBYTECODE=1 PYTHONPATH=$PWD/fullsubnet-plus_b200:$PWD
+mkdir -p gpurun_out; export PYTHONDONTWRITEBYTECODE=1 PYTHONPATH=$PWD/fullsubnet-plus_b200
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 8 --warmup 3 > gpurun_out/bench_n2.log 2>&1; echo "n2 rc=$?"
 timeout 600 python bench.py --gpus 1 --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1.log 2>&1; echo "n1 rc=$?"
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 tests/dist_check.py > gpurun_out/dist_check.log 2>&1; echo "dist rc=$?"

@@ -172,3 +172,20 @@ def test_tc5_weight_stream_layout(built_lib):
                 s += 1
     assert s == st.shape[0]
     assert built_lib.fsn_tc5_weight_stream_bytes(34, 100) == -1           # unsupported geometry
+
+
+def test_oracle_is_test_infrastructure_only():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import oracle/ (the product path has no CPU route)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    allowed = {os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")}
+    offenders = []
+    for d, dirs, files in os.walk(root):
+        dirs[:] = [x for x in dirs if x not in (".git", "gpurun_out", "tests", "oracle", "__pycache__", "baseline")]
+        for f in files:
+            p = os.path.join(d, f)
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")) and p not in allowed:
+                if re.search(r"^\s*(from|import)\s+oracle\b|oracle/[a-z_]+\.py|oracle\.", open(p, errors="ignore").read(), re.M):
+                    offenders.append(os.path.relpath(p, root))
+    assert not offenders, offenders
