@@ -4,6 +4,8 @@
 #include "fsn_common.cuh"
 #include "fsn_kernels.h"
 
+#include <cublas_v2.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -58,6 +60,10 @@ struct fsn_model {
     DevBuf sb_frag[4], sb_bias[4], sb_tc5_stream, sb_tc5_bias;
     DevBuf fb_frag[4], fb_bias[4];
     bool tc5_ok = false;
+    // layer-wise tcgen05 path (k_lstm_tc5r.cu): per-layer recurrent streams, permuted input-projection matrices, biases
+    bool tc5r_ok = false;
+    DevBuf r_stream[4], r_wih[4], r_bias[4], r_gin, r_hseq;
+    cublasHandle_t cublas = nullptr;
     // workspaces (grow-only, keyed by the last (B, T))
     int wsB = 0, wsT = 0;
     DevBuf fbin, fbout, xa, xb, y1, y2, stats, mu, ximg, cstate, magpad, fbx, hseq, stage_in[3], stage_out;
@@ -353,6 +359,9 @@ extern "C" void fsn_model_destroy(fsn_model* m) {
                      &m->mu, &m->ximg, &m->cstate, &m->magpad, &m->fbx, &m->hseq, &m->stage_in[0], &m->stage_in[1], &m->stage_in[2],
                      &m->stage_out, &m->tW1, &m->tW2, &m->tWfc, &m->tS1, &m->tS2b, &m->tBfc, &m->x0, &m->xr, &m->xn, &m->sigma, &m->ws_h, &m->ws_bar, &m->tsse_scale, &m->sb_rowsum};
     for (auto* b : all) b->release();
+    for (int i = 0; i < 4; ++i) { m->r_stream[i].release(); m->r_wih[i].release(); m->r_bias[i].release(); }
+    m->r_gin.release(); m->r_hseq.release();
+    if (m->cublas) cublasDestroy(m->cublas);
     if (m->s_in) { cudaStreamDestroy(m->s_in); cudaStreamDestroy(m->s_out); for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_h2d[i]); cudaEventDestroy(m->ev_fwd[i]); cudaEventDestroy(m->ev_d2h[i]); } }
     for (int i = 0; i < 2; ++i) { m->a_out[i].release(); for (int j = 0; j < 3; ++j) m->a_in[i][j].release(); }
     for (int i = 0; i < fsn_model::NEV; ++i) { if (m->ev0[i]) cudaEventDestroy(m->ev0[i]); if (m->ev1[i]) cudaEventDestroy(m->ev1[i]); }
@@ -430,6 +439,21 @@ extern "C" int fsn_model_finalize(fsn_model* m) {
         }
         if (upload(m->sb_tc5_bias, bp.data(), bp.size() * 4)) return fail(FSN_ECUDA, "upload failed");
     }
+    m->tc5r_ok = !m->tc5_ok && lstm_tc5r_supported(c.sb_hidden, c.output_size) && m->Isb <= 64;
+    if (m->tc5r_ok) {
+        const int H = c.sb_hidden;
+        for (int l = 0; l < c.num_layers; ++l) {
+            const std::string q = "sb_model.sequence_model.", sl = std::to_string(l);
+            const int Kin = (l == 0) ? m->Isb : H, Kpad = (l == 0) ? 64 : H;
+            std::vector<uint16_t> st, wp;
+            std::vector<float> bp;
+            lstm_tc5r_pack_layer(H, Kin, Kpad, m->host[q + "weight_ih_l" + sl].data(), m->host[q + "weight_hh_l" + sl].data(),
+                                 m->host[q + "bias_ih_l" + sl].data(), m->host[q + "bias_hh_l" + sl].data(), c.rnn_type == FSN_RNN_GRU, st, wp, bp);
+            if (upload(m->r_stream[l], st.data(), st.size() * 2) || upload(m->r_wih[l], wp.data(), wp.size() * 2) ||
+                upload(m->r_bias[l], bp.data(), bp.size() * 4))
+                return fail(FSN_ECUDA, "upload of the layer-wise tcgen05 weights failed");
+        }
+    }
     if (c.model_kind == FSN_KIND_PLUS) {
         int rc = pack_tcn5(m);
         if (rc) return rc;
@@ -450,6 +474,19 @@ static void fill_ws(fsn_model* m, LstmWsLaunch& w) {
     }
     w.L = c.num_layers; w.H = c.fb_hidden; w.I = c.num_freqs; w.Ipad = (c.num_freqs + 15) / 16 * 16; w.fast = c.fast_math; w.gru = c.rnn_type == FSN_RNN_GRU;
 }
+
+// The layer-wise tcgen05 path (k_lstm_tc5r.cu) is opt-in (FSN_TC5R=1) until it has a full round of GPU validation behind it.
+static bool layerwise_enabled() { const char* ev = getenv("FSN_TC5R"); return ev && atoi(ev) != 0; }
+static int pick_impl(const fsn_model* m) {
+    int impl = m->cfg.lstm_impl;
+    const char* env = getenv("FSN_LSTM_IMPL");
+    if (env && *env) impl = atoi(env);
+    if (impl == FSN_LSTM_AUTO) impl = (m->tc5_ok || (m->tc5r_ok && layerwise_enabled())) ? FSN_LSTM_TCGEN05 : FSN_LSTM_MMA;
+    return impl;
+}
+// tcgen05 requested, but the geometry is outside the fused two-layer kernel: run the layer-wise kernel (k_lstm_tc5r.cu)
+static bool use_layerwise(const fsn_model* m) { return layerwise_enabled() && pick_impl(m) == FSN_LSTM_TCGEN05 && !m->tc5_ok && m->tc5r_ok; }
+
 
 static int ensure_ws(fsn_model* m, int B, int T) {
     const fsn_config& c = m->cfg;
@@ -472,6 +509,12 @@ static int ensure_ws(fsn_model* m, int B, int T) {
     int ra = 0;
     size_t cs = lstm_mma_cstate_bytes(c.num_layers, rows, c.sb_hidden, &ra);
     size_t cs5 = lstm_tc5_cstate_bytes(ntiles, c.sb_hidden);
+    if (use_layerwise(m)) {
+        const size_t M = (size_t)ntiles * Tp * 128, csr = lstm_tc5r_cstate_bytes(ntiles, c.sb_hidden);
+        if (csr > cs5) cs5 = csr;
+        e |= m->r_gin.ensure(M * 4 * c.sb_hidden * 2, false);
+        if (c.num_layers > 1) e |= m->r_hseq.ensure(M * c.sb_hidden * 2, false);
+    }
     e |= m->cstate.ensure(cs > cs5 ? cs : cs5, true);
     if (c.model_kind == FSN_KIND_PLUS && m->tcn5) {
         const size_t rows = (size_t)3 * B * Tp;
@@ -511,21 +554,46 @@ static int ensure_ws(fsn_model* m, int B, int T) {
     return FSN_OK;
 }
 
-static int pick_impl(const fsn_model* m) {
-    int impl = m->cfg.lstm_impl;
-    const char* env = getenv("FSN_LSTM_IMPL");
-    if (env && *env) impl = atoi(env);
-    if (impl == FSN_LSTM_AUTO) impl = m->tc5_ok ? FSN_LSTM_TCGEN05 : FSN_LSTM_MMA;
-    return impl;
-}
-
 static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s) {
     const fsn_config& c = m->cfg;
     const int F = c.num_freqs, Tp = T + c.look_ahead, rows = B * F, ntiles = (rows + 127) / 128;
     const int impl = pick_impl(m);
     m->last_impl = impl;
-    if (impl == FSN_LSTM_TCGEN05) {
-        if (!m->tc5_ok) return fail(FSN_EINVAL, "tcgen05 LSTM needs 2 layers, hidden %% 64 == 0 and <= 384, input <= 64, output_size 2");
+    if (use_layerwise(m)) {
+        // one GEMM (input projection of every row and time step) + one recurrent launch per layer
+        if (!m->cublas) {
+            if (cublasCreate(&m->cublas) != CUBLAS_STATUS_SUCCESS) return fail(FSN_ECUDA, "cublasCreate failed");
+        }
+        if (cublasSetStream(m->cublas, s) != CUBLAS_STATUS_SUCCESS) return fail(FSN_ECUDA, "cublasSetStream failed");
+        const int H = c.sb_hidden, ntp = (ntiles + 1) / 2 * 2;
+        const long long M = (long long)ntp * Tp * 128;
+        const float one = 1.f, zero = 0.f;
+        for (int l = 0; l < c.num_layers; ++l) {
+            const int K = (l == 0) ? 64 : H;
+            const void* X = (l == 0) ? m->ximg.p : m->r_hseq.p;
+            // row-major Gin[M, 4H] = X[M, K] * Wp[4H, K]^T  ==  column-major Gin^T[4H, M] = Wp^T(op T) * X^T
+            cublasStatus_t st = cublasGemmEx(m->cublas, CUBLAS_OP_T, CUBLAS_OP_N, 4 * H, (int)M, K, &one, m->r_wih[l].p, CUDA_R_16F, K, X, CUDA_R_16F, K,
+                                             &zero, m->r_gin.p, CUDA_R_16F, 4 * H, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT_TENSOR_OP);
+            if (st != CUBLAS_STATUS_SUCCESS) return fail(FSN_ECUDA, "cublasGemmEx (input projection, layer %d) failed: %d", l, (int)st);
+            m->launches++;
+            LstmTc5rLaunch a{};
+            a.wstream = static_cast<const __half*>(m->r_stream[l].p);
+            a.bias = static_cast<const float*>(m->r_bias[l].p);
+            a.fc_w = P(m, "sb_model.fc_output_layer.weight");
+            a.fc_b = P(m, "sb_model.fc_output_layer.bias");
+            a.H = H; a.rows = rows; a.Tp = Tp; a.ntiles = ntiles;
+            a.gin = static_cast<const __half*>(m->r_gin.p);
+            a.hseq = static_cast<__half*>(m->r_hseq.p);
+            a.cstate = static_cast<float*>(m->cstate.p);
+            a.out = d_out; a.F = F; a.la = c.look_ahead;
+            a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU; a.last = (l == c.num_layers - 1);
+            { const char* ev = getenv("FSN_TC5_DEBUG"); a.debug = ev ? atoi(ev) : 0; }
+            int e = launch_lstm_tc5r(a, s);
+            if (e) return fail(FSN_ECUDA, "layer-wise tcgen05 LSTM launch failed (layer %d): %s", l, cudaGetErrorString((cudaError_t)e));
+            m->launches++;
+        }
+    } else if (impl == FSN_LSTM_TCGEN05) {
+        if (!m->tc5_ok) return fail(FSN_EINVAL, "tcgen05 LSTM needs hidden in {64, 128, 256, 512} (any depth) or 2 layers with hidden %% 64 == 0 and <= 384; input <= 64, output_size 2");
         LstmTc5Launch a{};
         a.wstream = static_cast<const __half*>(m->sb_tc5_stream.p);
         a.bias = static_cast<const float*>(m->sb_tc5_bias.p);
@@ -588,6 +656,7 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
     sp.rowsum = static_cast<float*>(m->sb_rowsum.p);
     sp.norm_type = c.norm_type;
     sp.ximg = static_cast<__half*>(m->ximg.p);
+    sp.plain = use_layerwise(m) ? 1 : 0;                              // the layer-wise path feeds the images to a GEMM as a plain matrix
     sp.ntiles = (B * F + 127) / 128;
 
     if (c.model_kind == FSN_KIND_PLUS) {

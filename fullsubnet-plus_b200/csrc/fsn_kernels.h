@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 
 namespace fsn {
 
@@ -81,6 +82,7 @@ struct SbPackLaunch {
     int norm_type;           // FSN_NORM_*
     __half* ximg;            // [ntiles, Tp, 128 rows, 64 halves] SWIZZLE_128B images
     int ntiles;
+    int plain;               // 1: rows are stored unswizzled (row-major [ntiles * Tp * 128, 64]): the A matrix of the layer-wise path's GEMM
 };
 void launch_sb_stats(const SbPackLaunch& a, cudaStream_t s);
 void launch_sb_pack(const SbPackLaunch& a, cudaStream_t s);
@@ -162,6 +164,26 @@ bool lstm_tc5_supported(int L, int H, int I, int O);
 int launch_lstm_tc5(const LstmTc5Launch& a, cudaStream_t s);
 int launch_lstm_tc5_pair(const LstmTc5Launch& a, cudaStream_t s);   // k_lstm_tc5p.cu: cta_group::2 version (2-CTA clusters)
 int launch_lstm_tc5_dbuf(const LstmTc5Launch& a, cudaStream_t s);   // k_lstm_tc5d.cu: pair kernel with two 64-column accumulators (default)
+
+// ---- k_lstm_tc5r.cu: single-layer recurrent kernel (time-batched input projection) for stacks outside the fused kernel's envelope
+struct LstmTc5rLaunch {
+    const __half* wstream;    // this layer's recurrent weight stream (lstm_tc5r_pack_layer)
+    const float* bias;        // [4H] pre-scaled, chunk column order
+    const float* fc_w;        // [2][H]   (last layer)
+    const float* fc_b;        // [2]
+    int H, rows, Tp, ntiles;
+    const __half* gin;        // [ntiles_pad * Tp * 128, 4H] fp16 input projection X_l W_ih^T, chunk column order
+    __half* hseq;             // [ntiles_pad * Tp * 128, H] fp16 output sequence (not the last layer)
+    float* cstate;            // [ntiles_pad][H/32][4][2][128][4] fp32
+    float* out; int F, la;    // last layer: mask [B, 2, F, Tp - la]
+    int fast, gru, last, debug;
+};
+bool lstm_tc5r_supported(int H, int O);
+size_t lstm_tc5r_cstate_bytes(int ntiles, int H);
+int64_t lstm_tc5r_weight_stream_bytes(int H);
+int launch_lstm_tc5r(const LstmTc5rLaunch& a, cudaStream_t s);
+void lstm_tc5r_pack_layer(int H, int Kin, int Kpad, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, bool gru,
+                          std::vector<uint16_t>& stream, std::vector<uint16_t>& wih_perm, std::vector<float>& bias);
 
 // ---- k_gemm_tc5.cu (TCN on tcgen05, time-major activations) ----------------------------------
 enum { EPI5_PRELU_STATS = 1, EPI5_GLN_RES = 2, EPI5_OUT = 3 };

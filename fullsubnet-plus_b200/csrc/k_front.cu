@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(256) sb_pack_kernel(SbPackLaunch a) {
         u.z = pack_half2(val(c * 8 + 4, tt), val(c * 8 + 5, tt));
         u.w = pack_half2(val(c * 8 + 6, tt), val(c * 8 + 7, tt));
         char* img = reinterpret_cast<char*>(a.ximg) + ((size_t)tile * Tp + t0 + tt) * (128 * 128);
-        *reinterpret_cast<uint4*>(img + sw128_offset(r, c * 8)) = u;
+        *reinterpret_cast<uint4*>(img + (a.plain ? (uint32_t)(r * 128 + c * 16) : sw128_offset(r, c * 8))) = u;
     }
 }
 
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(128) sb_pack_cum_kernel(SbPackLaunch a) {
                 float w[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) w[i] = (c * 8 + i < I) ? fminf(fmaxf(fmaf(v[c * 8 + i], sc, sh), -65504.f), 65504.f) : 0.f;
-                *reinterpret_cast<uint4*>(img + sw128_offset(r, c * 8)) =
+                *reinterpret_cast<uint4*>(img + (a.plain ? (uint32_t)(r * 128 + c * 16) : sw128_offset(r, c * 8))) =
                     make_uint4(pack_half2(w[0], w[1]), pack_half2(w[2], w[3]), pack_half2(w[4], w[5]), pack_half2(w[6], w[7]));
             }
         }

@@ -516,3 +516,42 @@ def test_command_line_tool_matches_reference_pipeline(built_lib, golden, tmp_pat
     print(f"\n[CLI] int16 enhanced waveform vs reference pipeline rel-L2 {err:.3e}, max |diff| {np.abs(pcm.astype(int) - want.astype(int)).max()} LSB")
     assert err < 2e-3
     assert wavfile.read(out_dir / "odd.wav")[1].shape == (20000,)
+
+
+@pytest.mark.parametrize("L,H,rnn", [(1, 64, "LSTM"), (3, 64, "LSTM"), (3, 128, "GRU"), (4, 64, "LSTM")])
+def test_layerwise_tcgen05_vs_oracle(built_lib, monkeypatch, L, H, rnn):
+    """Layer-wise tcgen05 path (k_lstm_tc5r.cu: one cuBLAS input-projection GEMM + one recurrent launch per layer) for stacks
+    outside the fused kernel's envelope; opt-in through FSN_TC5R=1.  First / middle / last layer roles, LSTM and GRU cells,
+    more than one CTA pair (B*F = 5*33 = 165 rows -> 2 tiles) and a half-empty last tile."""
+    monkeypatch.setenv("FSN_TC5R", "1")
+    cfg = dict(small_cfg(H), sequence_model=rnn)
+    params = O.make_params_plus(cfg, seed=40 + L, num_layers=L, lstm_scale=2.0)
+    mag, real, imag = small_inputs(5, 33, 26, 12)
+    ref = O.fullsubnet_plus_forward(params, cfg, mag, real, imag, num_layers=L)
+    m = build_plus(cfg, params, num_layers=L)
+    with torch.no_grad():
+        out = m(_t(mag), _t(real), _t(imag))
+        out2 = m(_t(mag), _t(real), _t(imag))
+    assert m.last_lstm_impl() == "tcgen05"
+    err = O.rel_l2(out.cpu().numpy(), ref)
+    print(f"\n[layer-wise tcgen05 L={L} H={H} {rnn}] cIRM {err:.3e}")
+    assert torch.equal(out, out2)
+    assert err < MASK_TOL
+
+
+def test_layerwise_tcgen05_config5(built_lib, monkeypatch):
+    """BASELINE config #5 geometry (F = 513, H = 512, 3 layers) on the layer-wise tcgen05 path."""
+    monkeypatch.setenv("FSN_TC5R", "1")
+    cfg = O.default_plus_config()
+    cfg.update(num_freqs=513, sb_model_hidden_size=512, fb_model_hidden_size=512)
+    params = O.make_params_plus(cfg, seed=31, num_layers=3)
+    X = O.stft(O.synth_clips(1, seed0=91), n_fft=1024, hop=512, win=1024)
+    mag, real, imag = (np.abs(X)[:, None].astype(np.float32), X.real[:, None].astype(np.float32), X.imag[:, None].astype(np.float32))
+    ref = O.fullsubnet_plus_forward(params, cfg, mag, real, imag, num_layers=3)
+    m = build_plus(cfg, params, num_layers=3)
+    with torch.no_grad():
+        out = m(_t(mag), _t(real), _t(imag))
+    assert m.last_lstm_impl() == "tcgen05"
+    err = O.rel_l2(out.cpu().numpy(), ref)
+    print(f"\n[config5 large, layer-wise tcgen05] cIRM rel-L2 {err:.3e}")
+    assert out.shape == (1, 2, 513, 94) and err < MASK_TOL
