@@ -475,8 +475,9 @@ static void fill_ws(fsn_model* m, LstmWsLaunch& w) {
     w.L = c.num_layers; w.H = c.fb_hidden; w.I = c.num_freqs; w.Ipad = (c.num_freqs + 15) / 16 * 16; w.fast = c.fast_math; w.gru = c.rnn_type == FSN_RNN_GRU;
 }
 
-// The layer-wise tcgen05 path (k_lstm_tc5r.cu) is opt-in (FSN_TC5R=1) until it has a full round of GPU validation behind it.
-static bool layerwise_enabled() { const char* ev = getenv("FSN_TC5R"); return ev && atoi(ev) != 0; }
+// The layer-wise tcgen05 path (k_lstm_tc5r.cu) serves stacks outside the fused kernel's envelope; FSN_TC5R=0 sends them to the
+// generic mma.sync kernel instead.
+static bool layerwise_enabled() { const char* ev = getenv("FSN_TC5R"); return !ev || atoi(ev) != 0; }
 static int pick_impl(const fsn_model* m) {
     int impl = m->cfg.lstm_impl;
     const char* env = getenv("FSN_LSTM_IMPL");
@@ -593,7 +594,7 @@ static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s)
             m->launches++;
         }
     } else if (impl == FSN_LSTM_TCGEN05) {
-        if (!m->tc5_ok) return fail(FSN_EINVAL, "tcgen05 LSTM needs hidden in {64, 128, 256, 512} (any depth) or 2 layers with hidden %% 64 == 0 and <= 384; input <= 64, output_size 2");
+        if (!m->tc5_ok) return fail(FSN_EINVAL, "tcgen05 LSTM needs hidden %% 64 == 0 and <= 512 (<= 384 for the fused two-layer kernel), input <= 64, output_size 2");
         LstmTc5Launch a{};
         a.wstream = static_cast<const __half*>(m->sb_tc5_stream.p);
         a.bias = static_cast<const float*>(m->sb_tc5_bias.p);

@@ -41,7 +41,7 @@ static inline R5Plan r5_plan(int H) {
     return p;
 }
 
-bool lstm_tc5r_supported(int H, int O) { return (H == 64 || H == 128 || H == 256 || H == 512) && O == 2; }
+bool lstm_tc5r_supported(int H, int O) { return H % 64 == 0 && H >= 64 && H <= 512 && O == 2; }
 size_t lstm_tc5r_cstate_bytes(int ntiles, int H) { return (size_t)((ntiles + 1) / 2 * 2) * H * 128 * sizeof(float); }
 int64_t lstm_tc5r_weight_stream_bytes(int H) { return (int64_t)(H / 32) * (H / 64) * R5_STAGE_FULL; }
 
@@ -324,7 +324,11 @@ int launch_lstm_tc5r(const LstmTc5rLaunch& a, cudaStream_t s) {
     switch (a.H) {
         case 64: return r5_dispatch<64>(a, grid, p, s);
         case 128: return r5_dispatch<128>(a, grid, p, s);
+        case 192: return r5_dispatch<192>(a, grid, p, s);
         case 256: return r5_dispatch<256>(a, grid, p, s);
+        case 320: return r5_dispatch<320>(a, grid, p, s);
+        case 384: return r5_dispatch<384>(a, grid, p, s);
+        case 448: return r5_dispatch<448>(a, grid, p, s);
         case 512: return r5_dispatch<512>(a, grid, p, s);
     }
     return (int)cudaErrorInvalidValue;

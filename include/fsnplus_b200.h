@@ -58,7 +58,7 @@ extern "C" {
 /* lstm_impl */
 #define FSN_LSTM_AUTO 0
 #define FSN_LSTM_MMA 1     /* generic mma.sync kernel (any hidden size / layer count)               */
-#define FSN_LSTM_TCGEN05 2 /* persistent tcgen05/TMEM kernel (2 layers, hidden <= 384, input <= 64) */
+#define FSN_LSTM_TCGEN05 2 /* persistent tcgen05/TMEM kernels: fused (2 layers, hidden <= 384) or layer-wise (hidden <= 512); input <= 64 */
 
 typedef struct fsn_config {
     int32_t model_kind;

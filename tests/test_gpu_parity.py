@@ -392,6 +392,11 @@ def test_config5_large_model(built_lib):
     err = O.rel_l2(out.cpu().numpy(), ref)
     print(f"\n[config5 large, {m.last_lstm_impl()}] cIRM rel-L2 {err:.3e}")
     assert out.shape == (1, 2, 513, 94) and err < MASK_TOL
+    monkeypatch.setenv("FSN_TC5R", "0")                           # the generic kernel stays reachable
+    with torch.no_grad():
+        out_mma = m(_t(mag), _t(real), _t(imag))
+    assert m.last_lstm_impl() == "mma"
+    assert O.rel_l2(out_mma.cpu().numpy(), ref) < MASK_TOL
 
 
 def test_fused_postprocessing_matches_torch(built_lib):
@@ -518,10 +523,10 @@ def test_command_line_tool_matches_reference_pipeline(built_lib, golden, tmp_pat
     assert wavfile.read(out_dir / "odd.wav")[1].shape == (20000,)
 
 
-@pytest.mark.parametrize("L,H,rnn", [(1, 64, "LSTM"), (3, 64, "LSTM"), (3, 128, "GRU"), (4, 64, "LSTM")])
+@pytest.mark.parametrize("L,H,rnn", [(1, 64, "LSTM"), (3, 64, "LSTM"), (3, 128, "GRU"), (4, 64, "LSTM"), (3, 192, "LSTM"), (1, 448, "LSTM")])
 def test_layerwise_tcgen05_vs_oracle(built_lib, monkeypatch, L, H, rnn):
     """Layer-wise tcgen05 path (k_lstm_tc5r.cu: one cuBLAS input-projection GEMM + one recurrent launch per layer) for stacks
-    outside the fused kernel's envelope; opt-in through FSN_TC5R=1.  First / middle / last layer roles, LSTM and GRU cells,
+    outside the fused kernel's envelope (default for hidden % 64 == 0, <= 512; FSN_TC5R=0 disables).  First / middle / last layer roles, LSTM and GRU cells,
     more than one CTA pair (B*F = 5*33 = 165 rows -> 2 tiles) and a half-empty last tile."""
     monkeypatch.setenv("FSN_TC5R", "1")
     cfg = dict(small_cfg(H), sequence_model=rnn)
@@ -555,3 +560,8 @@ def test_layerwise_tcgen05_config5(built_lib, monkeypatch):
     err = O.rel_l2(out.cpu().numpy(), ref)
     print(f"\n[config5 large, layer-wise tcgen05] cIRM rel-L2 {err:.3e}")
     assert out.shape == (1, 2, 513, 94) and err < MASK_TOL
+    monkeypatch.setenv("FSN_TC5R", "0")                           # the generic kernel stays reachable
+    with torch.no_grad():
+        out_mma = m(_t(mag), _t(real), _t(imag))
+    assert m.last_lstm_impl() == "mma"
+    assert O.rel_l2(out_mma.cpu().numpy(), ref) < MASK_TOL
