@@ -376,9 +376,10 @@ def test_config4_causal_fullsubnet_long_clip(built_lib):
     assert not torch.equal(a[..., t0:], b[..., t0:])
 
 
-def test_config5_large_model(built_lib):
+def test_config5_large_model(built_lib, monkeypatch):
     """BASELINE config #5 geometry: num_freqs=513 (n_fft=1024, hop 512 -> T=94 for 3 s), sub-band hidden 512, 3-layer
-    LSTMs (additive num_layers knob; oracle = SequenceModel(num_layers=3) semantics, pinned by tests/golden/lstm3_small)."""
+    LSTMs (additive num_layers knob; oracle = SequenceModel(num_layers=3) semantics, pinned by tests/golden/lstm3_small).
+    Default = layer-wise tcgen05 path (k_lstm_tc5r.cu); FSN_TC5R=0 = generic mma.sync kernel."""
     cfg = O.default_plus_config()
     cfg.update(num_freqs=513, sb_model_hidden_size=512, fb_model_hidden_size=512)
     params = O.make_params_plus(cfg, seed=31, num_layers=3)
@@ -391,6 +392,7 @@ def test_config5_large_model(built_lib):
         out = m(_t(mag), _t(real), _t(imag))
     err = O.rel_l2(out.cpu().numpy(), ref)
     print(f"\n[config5 large, {m.last_lstm_impl()}] cIRM rel-L2 {err:.3e}")
+    assert m.last_lstm_impl() == "tcgen05"
     assert out.shape == (1, 2, 513, 94) and err < MASK_TOL
     monkeypatch.setenv("FSN_TC5R", "0")                           # the generic kernel stays reachable
     with torch.no_grad():
@@ -542,26 +544,3 @@ def test_layerwise_tcgen05_vs_oracle(built_lib, monkeypatch, L, H, rnn):
     print(f"\n[layer-wise tcgen05 L={L} H={H} {rnn}] cIRM {err:.3e}")
     assert torch.equal(out, out2)
     assert err < MASK_TOL
-
-
-def test_layerwise_tcgen05_config5(built_lib, monkeypatch):
-    """BASELINE config #5 geometry (F = 513, H = 512, 3 layers) on the layer-wise tcgen05 path."""
-    monkeypatch.setenv("FSN_TC5R", "1")
-    cfg = O.default_plus_config()
-    cfg.update(num_freqs=513, sb_model_hidden_size=512, fb_model_hidden_size=512)
-    params = O.make_params_plus(cfg, seed=31, num_layers=3)
-    X = O.stft(O.synth_clips(1, seed0=91), n_fft=1024, hop=512, win=1024)
-    mag, real, imag = (np.abs(X)[:, None].astype(np.float32), X.real[:, None].astype(np.float32), X.imag[:, None].astype(np.float32))
-    ref = O.fullsubnet_plus_forward(params, cfg, mag, real, imag, num_layers=3)
-    m = build_plus(cfg, params, num_layers=3)
-    with torch.no_grad():
-        out = m(_t(mag), _t(real), _t(imag))
-    assert m.last_lstm_impl() == "tcgen05"
-    err = O.rel_l2(out.cpu().numpy(), ref)
-    print(f"\n[config5 large, layer-wise tcgen05] cIRM rel-L2 {err:.3e}")
-    assert out.shape == (1, 2, 513, 94) and err < MASK_TOL
-    monkeypatch.setenv("FSN_TC5R", "0")                           # the generic kernel stays reachable
-    with torch.no_grad():
-        out_mma = m(_t(mag), _t(real), _t(imag))
-    assert m.last_lstm_impl() == "mma"
-    assert O.rel_l2(out_mma.cpu().numpy(), ref) < MASK_TOL
