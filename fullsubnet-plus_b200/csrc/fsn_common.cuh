@@ -111,6 +111,26 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
+// Same copy with an L2 eviction-priority hint: evict_first for data that is read exactly once (the per-step input images, 392 MB
+// per launch at B = 64, which otherwise push the 50 MB cell-state scratch out of L2), evict_last for the weight stream that every
+// CTA re-reads every step.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
 // One lane of a fully converged warp (elect.sync).  The tcgen05 issue loops must stay warp-uniform and predicate only
 // the instruction on this: an `if (lane == 0)` region forces every UTCHMMA operand through R2UR moves and serialises the
 // mbarrier polls with the issue -- measured 109 vs 64 cycles per M=128,N=128 MMA (fsn_probe_tcgen05, "probe4").

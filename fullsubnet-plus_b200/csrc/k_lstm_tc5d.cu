@@ -91,8 +91,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wstream) + (size_t)rank * D5_KB;
             const uint8_t* xsrc = reinterpret_cast<const uint8_t*>(a.img) + (size_t)tile * Tp * D5_XIMG;
             int slot = 0; uint32_t ph = 0;
+            const uint64_t pol_x = l2_policy_evict_first(), pol_w = l2_policy_evict_last();
             mbar_arrive_expect_tx(xfull, D5_XIMG);
-            bulk_g2s(ximg, xsrc, D5_XIMG, xfull);
+            bulk_g2s_hint(ximg, xsrc, D5_XIMG, xfull, pol_x);
             constexpr int NKB0 = 1 + KBH, NKB1 = 2 * KBH;           // k-blocks per chunk: x | h0, h0 | h1
             for (int t = 0; t < Tp; ++t) {
                 for (int layer = 0; layer < 2; ++layer) {
@@ -103,7 +104,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                             if (layer == 1 && j == NCH / 2 && half == 0 && t + 1 < Tp) {     // x_{t+1}: layer 0 of step t is long done
                                 mbar_wait(xempty, t & 1);
                                 mbar_arrive_expect_tx(xfull, D5_XIMG);
-                                bulk_g2s(ximg, xsrc + (size_t)(t + 1) * D5_XIMG, D5_XIMG, xfull);
+                                bulk_g2s_hint(ximg, xsrc + (size_t)(t + 1) * D5_XIMG, D5_XIMG, xfull, pol_x);
                             }
                             for (int kb0 = 0; kb0 < nkb; kb0 += 4) {
                                 const int nk = (nkb - kb0 < 4) ? nkb - kb0 : 4;
@@ -112,8 +113,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                                 for (int i = 0; i < nk; ++i) {
                                     int kbs = kb0 + i;                      // layer 1: consumed recurrent part (stream k-blocks KBH..) first
                                     if (layer == 1) kbs = (kbs < KBH) ? KBH + kbs : kbs - KBH;
-                                    bulk_g2s(stages + (size_t)slot * D5_STAGE + i * D5_SUB,
-                                             wsrc + (size_t)(kb_base + kbs) * D5_STAGE_FULL + half * D5_SUB, D5_SUB, &full[slot]);
+                                    bulk_g2s_hint(stages + (size_t)slot * D5_STAGE + i * D5_SUB,
+                                                  wsrc + (size_t)(kb_base + kbs) * D5_STAGE_FULL + half * D5_SUB, D5_SUB, &full[slot], pol_w);
                                 }
                                 if (++slot == nstage) { slot = 0; ph ^= 1; }
                             }
@@ -337,8 +338,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                     if (cg == 0 && t >= a.la && grow < a.rows) {
                         const float o0 = fc0 + fcpart[(128 + r) * 2] + fcpart[(256 + r) * 2] + fcpart[(384 + r) * 2] + fcb0;
                         const float o1 = fc1 + fcpart[(128 + r) * 2 + 1] + fcpart[(256 + r) * 2 + 1] + fcpart[(384 + r) * 2 + 1] + fcb1;
-                        a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)] = o0;
-                        a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)] = o1;
+                        __stcs(&a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)], o0);   // streaming stores: written once
+                        __stcs(&a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)], o1);
                     }
                     asm volatile("bar.sync 2, 512;" ::: "memory");
                 }
