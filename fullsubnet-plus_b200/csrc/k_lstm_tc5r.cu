@@ -368,3 +368,17 @@ void lstm_tc5r_pack_layer(int H, int Kin, int Kpad, const float* w_ih, const flo
 }
 
 }  // namespace fsn
+
+extern "C" int64_t fsn_tc5r_weight_stream_bytes(int32_t H) { return (H % 64 || H < 64 || H > 512) ? -1 : fsn::lstm_tc5r_weight_stream_bytes(H); }
+
+extern "C" int fsn_tc5r_pack_layer(int32_t H, int32_t Kin, int32_t Kpad, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                   int32_t gru, uint16_t* h_stream, uint16_t* h_wih, float* h_bias) {
+    if (H % 64 || H < 64 || H > 512 || Kin < 1 || Kin > Kpad || !w_ih || !w_hh || !b_ih || !b_hh || !h_stream || !h_wih || !h_bias) return FSN_EINVAL;
+    std::vector<uint16_t> st, wp;
+    std::vector<float> bp;
+    fsn::lstm_tc5r_pack_layer(H, Kin, Kpad, w_ih, w_hh, b_ih, b_hh, gru != 0, st, wp, bp);
+    std::memcpy(h_stream, st.data(), st.size() * 2);
+    std::memcpy(h_wih, wp.data(), wp.size() * 2);
+    std::memcpy(h_bias, bp.data(), bp.size() * 4);
+    return FSN_OK;
+}

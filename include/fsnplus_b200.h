@@ -161,6 +161,13 @@ int32_t fsn_tc5_gate_row(int32_t hidden, int32_t chunk, int32_t n);
 int fsn_tc5_pack_weights(int32_t input_size, int32_t hidden, const float* w_ih0, const float* w_hh0, const float* w_ih1,
                          const float* w_hh1, uint16_t* h_dst /* fp16 bits */);
 
+/* Layer-wise tcgen05 path, one layer: recurrent stream (hidden/32 chunks x hidden/64 tiles of 16 KB), the
+ * input-projection matrix for the GEMM ([4 hidden, k_pad] fp16, rows in chunk column order) and the pre-scaled biases
+ * ([4 hidden] in the same order; gru != 0 scales pseudo-gate 3 like a tanh argument).  b_ih / b_hh in the nn.LSTM 4-block layout. */
+int64_t fsn_tc5r_weight_stream_bytes(int32_t hidden);
+int fsn_tc5r_pack_layer(int32_t hidden, int32_t k_in, int32_t k_pad, const float* w_ih, const float* w_hh, const float* b_ih,
+                        const float* b_hh, int32_t gru, uint16_t* h_stream, uint16_t* h_wih, float* h_bias);
+
 /* tcgen05 / TMEM / bulk-copy self-test used by the GPU test-suite (tests/test_gpu_probe.py):
  * runs tiny single-CTA GEMMs through every instruction form the persistent kernel relies on and
  * writes max-abs-errors into h_report[0..n).  Returns the number of entries written or < 0. */

@@ -174,6 +174,35 @@ def test_tc5_weight_stream_layout(built_lib):
     assert built_lib.fsn_tc5_weight_stream_bytes(34, 100) == -1           # unsupported geometry
 
 
+def test_tc5r_layer_packing(built_lib):
+    """Layer-wise tcgen05 path (k_lstm_tc5r.cu): recurrent stream tiles, permuted input-projection matrix and pre-scaled biases
+    of one layer follow the chunk column order n -> fsn_tc5_gate_row (gate q = (n % 32) // 8 of unit 32 j + 8 (n // 32) + n % 8)."""
+    H, Kin, Kpad = 128, 34, 64
+    rng = np.random.default_rng(1)
+    w_ih, w_hh = rng.standard_normal((4 * H, Kin)).astype(np.float32), rng.standard_normal((4 * H, H)).astype(np.float32)
+    b_ih, b_hh = rng.standard_normal(4 * H).astype(np.float32), rng.standard_normal(4 * H).astype(np.float32)
+    NCH, KBH = H // 32, H // 64
+    assert built_lib.fsn_tc5r_weight_stream_bytes(H) == NCH * KBH * 16384
+    assert built_lib.fsn_tc5r_weight_stream_bytes(100) == -1 and built_lib.fsn_tc5r_weight_stream_bytes(576) == -1
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    off = np.array([[built_lib.fsn_sw128_offset(n, k) // 2 for k in range(64)] for n in range(128)])
+    L2E = 1.4426950408889634
+    for gru in (0, 1):
+        stream, wih, bias = np.zeros(NCH * KBH * 8192, np.uint16), np.zeros(4 * H * Kpad, np.uint16), np.zeros(4 * H, np.float32)
+        assert built_lib.fsn_tc5r_pack_layer(H, Kin, Kpad, vp(w_ih), vp(w_hh), vp(b_ih), vp(b_hh), gru, vp(stream), vp(wih), vp(bias)) == 0
+        st, wp = stream.view(np.float16).reshape(NCH, KBH, 8192), wih.view(np.float16).reshape(4 * H, Kpad)
+        for j in range(NCH):
+            rows = np.array([built_lib.fsn_tc5_gate_row(H, j, n) for n in range(128)])
+            for kb in range(KBH):
+                assert np.array_equal(st[j, kb][off], w_hh[rows][:, kb * 64:(kb + 1) * 64].astype(np.float16))
+            assert np.array_equal(wp[j * 128:(j + 1) * 128, :Kin], w_ih[rows].astype(np.float16))
+            assert not wp[j * 128:(j + 1) * 128, Kin:].any()
+            q = (np.arange(128) % 32) // 8
+            scale = np.where((q == 2) | ((q == 3) & (gru == 1)), -2 * L2E, -L2E).astype(np.float32)
+            assert np.allclose(bias[j * 128:(j + 1) * 128], scale * (b_ih[rows] + b_hh[rows]), rtol=1e-6)
+    assert built_lib.fsn_tc5r_pack_layer(100, Kin, Kpad, vp(w_ih), vp(w_hh), vp(b_ih), vp(b_hh), 0, vp(stream), vp(wih), vp(bias)) != 0
+
+
 def test_oracle_is_test_infrastructure_only():
     """Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import oracle/ (the product path has no CPU route)."""
     import os
