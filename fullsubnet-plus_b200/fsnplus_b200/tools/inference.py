@@ -130,9 +130,10 @@ def _rank_world():
 
 
 @torch.no_grad()
-def run(config, checkpoint_path, output_dir, batch_size=64, device=None, log=print):
+def run(config, checkpoint_path, output_dir, batch_size=64, device=None, log=print, model_and_epoch=None):
     """Enhance every file of config["dataset"]["args"]["dataset_dir_list"].  Under torchrun each rank takes every
-    world-size-th batch (files are independent: no collective).  Returns {name: path} of the files this rank wrote."""
+    world-size-th batch (files are independent: no collective).  Returns {name: path} of the files this rank wrote.
+    ``model_and_epoch`` (tests of the host logic) replaces the checkpoint load with a ready ``(callable, epoch)``."""
     rank, world, local_rank = _rank_world()
     if device is None:
         device = f"cuda:{local_rank}"
@@ -143,7 +144,8 @@ def run(config, checkpoint_path, output_dir, batch_size=64, device=None, log=pri
         raise NotImplementedError(f"Not implemented Inferencer type: {itype}")       # base_inferencer.py:135
     files = find_files(config["dataset"]["args"]["dataset_dir_list"])
     ds_sr = config["dataset"]["args"].get("sr", sr)
-    model, epoch = build_model(config["model"], Path(checkpoint_path).expanduser().absolute(), device)
+    model, epoch = model_and_epoch or build_model(config["model"], Path(checkpoint_path).expanduser().absolute(), device)
+    on_gpu = torch.device(device).type == "cuda"
     enhanced_dir = Path(output_dir).expanduser().absolute() / f"enhanced_{str(epoch).zfill(4)}"
     enhanced_dir.mkdir(parents=True, exist_ok=True)
 
@@ -153,8 +155,10 @@ def run(config, checkpoint_path, output_dir, batch_size=64, device=None, log=pri
     for bi, idx in enumerate(batches):
         if bi % world != rank:
             continue
-        noisy = torch.from_numpy(np.stack([clips[i] for i in idx])).pin_memory().to(device, non_blocking=True)
-        torch.cuda.synchronize(device)
+        noisy = torch.from_numpy(np.stack([clips[i] for i in idx]))
+        if on_gpu:
+            noisy = noisy.pin_memory().to(device, non_blocking=True)
+            torch.cuda.synchronize(device)
         t1 = time.time()
         enhanced = H.enhance_batch(model, noisy, n_fft, hop, win, complex_inputs=INFERENCE_TYPES[itype]).cpu().numpy()
         t2 = time.time()

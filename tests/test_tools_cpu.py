@@ -77,3 +77,42 @@ def test_unknown_inferencer_type_and_model_path(tmp_path):
         T.run(T.load_toml(p), tmp_path / "none.tar", tmp_path, device="cpu")
     with pytest.raises(NotImplementedError):
         T.build_model({"path": "some.other.Model", "args": {}}, tmp_path / "none.tar", "cpu")
+
+
+def test_run_host_logic_with_rank_sharding(tmp_path, monkeypatch):
+    """Host logic of run(): length buckets, round-robin batches per rank (RANK / WORLD_SIZE as torchrun sets them), output
+    directory + file names + int16 convention.  The model is a stand-in that predicts a constant compressed cIRM (2, 0), i.e. a
+    positive real gain: the enhanced waveform is a scaled copy of the input, and the gain cancels in the peak normalisation, so
+    the int16 output is predictable from the input file alone."""
+    import torch
+    from scipy.io import wavfile
+    from fsnplus_b200.tools import inference as T
+    rng = np.random.default_rng(3)
+    noisy = tmp_path / "noisy"
+    noisy.mkdir()
+    lens = [4096, 4096, 6000, 4096, 6000, 4096, 4096]
+    for i, n in enumerate(lens):
+        wavfile.write(noisy / f"f{i}.wav", 16000, (rng.standard_normal(n) * 0.05).astype(np.float32))
+    cfg = T.load_toml(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inference_reference.toml"))
+    cfg["dataset"]["args"]["dataset_dir_list"] = [str(noisy)]
+
+    def constant_mask(mag, real, imag):                       # compressed cIRM (2.0, 0): decompresses to a positive real gain
+        m = torch.zeros(mag.size(0), 2, mag.size(2), mag.size(3))
+        m[:, 0] = 2.0
+        return m
+
+    seen = {}
+    for rank in (0, 1):
+        monkeypatch.setenv("RANK", str(rank)); monkeypatch.setenv("WORLD_SIZE", "2"); monkeypatch.setenv("LOCAL_RANK", str(rank))
+        seen[rank] = T.run(cfg, tmp_path / "unused.tar", tmp_path / "out", batch_size=2, device="cpu", log=lambda *a: None,
+                           model_and_epoch=(constant_mask, 12))
+    # batches: [0,1] [3,5] [6] [2,4] -> rank 0 takes batches 0 and 2, rank 1 batches 1 and 3
+    assert sorted(seen[0]) == ["f0", "f1", "f6"] and sorted(seen[1]) == ["f2", "f3", "f4", "f5"]
+    out_dir = tmp_path / "out" / "enhanced_0012"
+    assert sorted(p.name for p in out_dir.iterdir()) == [f"f{i}.wav" for i in range(7)]
+    for i, n in enumerate(lens):
+        rate, pcm = wavfile.read(out_dir / f"f{i}.wav")
+        x = wavfile.read(noisy / f"f{i}.wav")[1]
+        assert rate == 16000 and pcm.dtype == np.int16 and pcm.shape == (n,)
+        want = T.to_int16(x)                                   # a positive gain cancels in the peak normalisation
+        assert np.abs(pcm.astype(int) - want.astype(int)).max() <= 2, i     # STFT -> iSTFT round trip in fp32
