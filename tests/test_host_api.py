@@ -129,6 +129,31 @@ def test_no_cpu_fallback(built_lib):
         assert rc == -2 and b"no CPU fallback" in built_lib.fsn_last_error()
 
 
+def test_create_validates_the_configuration(built_lib):
+    """fsn_model_create rejects bad configurations with FSN_EINVAL (-1) and a message before it ever touches a device."""
+    from fsnplus_b200 import _lib
+    from fsnplus_b200.model import FullSubNet_Plus
+
+    def create(**over):
+        cfg = _lib.FsnConfig.from_buffer_copy(FullSubNet_Plus(**O.default_plus_config())._cfg)
+        for k, v in over.items():
+            setattr(cfg, k, v)
+        h = C.c_void_p()
+        rc = built_lib.fsn_model_create(C.byref(cfg), C.byref(h))
+        if rc == 0:
+            built_lib.fsn_model_destroy(h)
+        return rc, built_lib.fsn_last_error()
+
+    for over, needle in (({"model_kind": 7}, b"model_kind"), ({"num_freqs": 2}, b"geometry"), ({"sb_num_neighbors": 300}, b"reflect"),
+                         ({"num_layers": 5}, b"num_layers"), ({"sb_hidden": 100}, b"multiple of 16"), ({"output_size": 0}, b"output_size"),
+                         ({"norm_type": 9}, b"norm_type"), ({"channel_attention": 4}, b"channel_attention"), ({"rnn_type": 2}, b"rnn_type"),
+                         ({"subband_num": 2}, b"ECA"), ({"channel_attention": _lib.ATTENTION["ECA"], "subband_num": 200}, b"subband_num")):
+        rc, msg = create(**over)
+        assert rc == -1 and needle in msg, (over, rc, msg)
+    rc, msg = create()                                                   # a valid configuration gets as far as the device check
+    assert rc == 0 if torch.cuda.is_available() else (rc == -2 and b"no CPU fallback" in msg)
+
+
 def test_sw128_offsets(built_lib):
     seen = set()
     for r in range(128):
