@@ -180,6 +180,18 @@ def main():
               f"{O.rel_l2(O.fullsubnet_plus_forward(params, bcfg, m, r, i), out):.2e}")
         save(f"plus_small_ECA_sub{sub}", out=out, fb_in=fb_in, seed=5)
 
+    # fb_num_neighbors > 0: the full-band outputs are unfolded too (fullsubnet_plus.py:167-179, fullsubnet.py:90-91)
+    ncfg = dict(scfg, fb_num_neighbors=1)
+    params = O.make_params_plus(ncfg, seed=6)
+    out, fb_in, fb_out = run_plus(ncfg, params, m, r, i)
+    print(f"plus_small[fb_num_neighbors=1]: oracle-vs-reference rel-L2 out={O.rel_l2(O.fullsubnet_plus_forward(params, ncfg, m, r, i), out):.2e}")
+    save("plus_small_fbn1", out=out, seed=6)
+    ncfg = dict(small_fsn_cfg(), fb_num_neighbors=2)
+    params = O.make_params_fsn(ncfg, seed=6)
+    out, fb_out = run_fsn(ncfg, params, m)
+    print(f"fsn_small[fb_num_neighbors=2]: oracle-vs-reference rel-L2 out={O.rel_l2(O.fullsubnet_forward(params, ncfg, m), out):.2e}")
+    save("fsn_small_fbn2", out=out, seed=6)
+
     # sequence_model = "GRU" (sequence_model.py:39-46): FullSubNet+ sub-band GRU, fullsubnet.Model full-band + sub-band GRU
     gcfg = dict(scfg, sequence_model="GRU")
     params = O.make_params_plus(gcfg, seed=8, lstm_scale=2.0)

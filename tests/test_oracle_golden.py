@@ -55,6 +55,17 @@ def test_plus_small_subband_num(golden, sub):
     assert O.rel_l2(st["fb_in"], g["fb_in"]) < TOL
 
 
+def test_fb_num_neighbors(golden):
+    """fb_num_neighbors > 0: the full-band outputs are unfolded as well (fullsubnet_plus.py:167-179, fullsubnet.py:90-91)."""
+    gi = golden("plus_small")
+    cfg = dict(small_plus_cfg(), fb_num_neighbors=1)
+    out = O.fullsubnet_plus_forward(O.make_params_plus(cfg, seed=6), cfg, gi["mag"], gi["real"], gi["imag"])
+    assert O.rel_l2(out, golden("plus_small_fbn1")["out"]) < TOL
+    cfg = dict(small_fsn_cfg("offline_laplace_norm"), fb_num_neighbors=2)
+    out = O.fullsubnet_forward(O.make_params_fsn(cfg, seed=6), cfg, gi["mag"])
+    assert O.rel_l2(out, golden("fsn_small_fbn2")["out"]) < TOL
+
+
 def test_gru_variants(golden):
     """sequence_model = "GRU" (sequence_model.py:39-46) for both model classes, gates pushed towards saturation (x2)."""
     gi = golden("plus_small")
