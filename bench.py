@@ -103,7 +103,7 @@ class CpuReference:
         self.sweep = {}
         if threads is None:
             ncpu = os.cpu_count() or 1
-            cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
+            cands = sorted({c for c in (1, 4, 8, 16, 32, 64, ncpu) if c <= ncpu})   # 1 thread: the scalar figure SURVEY.md 8d asks for
             best, threads = None, cands[0]
             for c in cands:
                 torch.set_num_threads(c)
