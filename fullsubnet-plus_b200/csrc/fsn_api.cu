@@ -33,14 +33,16 @@ static int fail(int code, const char* fmt, ...) {
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
-    int ensure(size_t n, bool zero) {
+    // grow-only; a fresh allocation is zero-filled ON THE STREAM THAT WILL USE IT (a legacy-stream cudaMemset is not ordered
+    // against kernels on a non-blocking stream)
+    int ensure(size_t n, bool zero, cudaStream_t s = nullptr) {
         if (n <= bytes) return 0;
         if (p) cudaFree(p);
         p = nullptr; bytes = 0;
         cudaError_t e = cudaMalloc(&p, n);
         if (e != cudaSuccess) return (int)e;
         bytes = n;
-        if (zero) e = cudaMemset(p, 0, n);
+        if (zero) e = cudaMemsetAsync(p, 0, n, s);
         return (int)e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
@@ -64,26 +66,45 @@ struct fsn_model {
     bool tc5r_ok = false;
     DevBuf r_stream[4], r_wih[4], r_bias[4], r_gin, r_hseq;
     cublasHandle_t cublas = nullptr;
-    // workspaces (grow-only, keyed by the last (B, T))
-    int wsB = 0, wsT = 0;
-    DevBuf fbin, fbout, xa, xb, y1, y2, stats, mu, ximg, cstate, magpad, fbx, hseq, stage_in[3], stage_out;
+    // Front-end workspaces (everything the full-band stage writes and the sub-band LSTM reads), grow-only, keyed by the last
+    // (B, T).  TWO lanes: the pipelined entry points (fsn_model_submit / fsn_model_forward_host_async) run the front end of
+    // batch i+1 in lane (i+1)&1 on the front stream while the sub-band LSTM of batch i still reads lane i&1 on the LSTM stream.
+    struct Lane {
+        int wsB = 0, wsT = 0;
+        DevBuf fbin, fbout, xa, xb, y1, y2, stats, mu, ximg, magpad, fbx, hseq;
+        DevBuf x0, xr;                                 // time-major fb input / relu'd last residual
+        DevBuf tsse_scale, sb_rowsum;
+        DevBuf xn, sigma;                              // pre-normalised inputs / sub-band std for the non-default norm types
+        alignas(64) unsigned char mapX0[128], mapXa[128], mapXb[128], mapXr[128], mapY2[128];
+        cudaEvent_t ev_front = nullptr, ev_lstm = nullptr;   // front end written / LSTM finished reading this lane
+        bool used = false;                             // ev_lstm has been recorded (a pipelined batch ran / may still run in this lane)
+        void release_all() {
+            DevBuf* all[] = {&fbin, &fbout, &xa, &xb, &y1, &y2, &stats, &mu, &ximg, &magpad, &fbx, &hseq, &x0, &xr, &tsse_scale, &sb_rowsum, &xn, &sigma};
+            for (auto* b : all) b->release();
+        }
+    } lane[2];
+    int last_lane = 0;
+    DevBuf cstate, stage_in[3], stage_out;             // LSTM-side scratch (one LSTM runs at a time), host-entry staging
     // tcgen05 TCN (FullSubNet+): folded / padded weights, per-block tensor maps, time-major activations
     bool tcn5 = false;
     int Cp = 0, tcnNT = 0, tcnNtiles = 0, num_sms = 148;
     DevBuf tW1, tW2, tWfc, tS1, tS2b, tBfc;            // [8][3][512][Cp], [8][3][Cp][512], [3][Cp][Cp], [8][3][Cp] x2, [3][Cp]
-    DevBuf x0, xr;                                     // time-major fb input / relu'd last residual
-    DevBuf tsse_scale, sb_rowsum;
     DevBuf ws_h, ws_bar;                               // weight-stationary full-band LSTM: h exchange buffer, grid barrier
-    DevBuf xn, sigma;                                  // pre-normalised inputs / sub-band std for the non-default norm types
     alignas(64) unsigned char mapW1[8][128], mapW2[8][128], mapWfc[128];
-    alignas(64) unsigned char mapX0[128], mapXa[128], mapXb[128], mapXr[128], mapY2[128];
     int64_t launches = 0;
     int last_impl = 0;
-    // async host pipeline: two staging slots, copy-in / copy-out streams, per-slot events
-    cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_h2d[2] = {}, ev_fwd[2] = {}, ev_d2h[2] = {};
+    // tuning knobs, read ONCE at fsn_model_create (never on the forward path): FSN_LSTM_IMPL overrides cfg.lstm_impl,
+    // FSN_NO_WS=1 keeps the full-band LSTM of fullsubnet.Model off the weight-stationary kernel
+    int env_impl = 0;
+    bool env_no_ws = false;
+    // pipelined execution: front-end stream, LSTM stream (higher priority), copy-in / copy-out streams, per-slot events
+    cudaStream_t s_front = nullptr, s_lstm = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_plain = nullptr;   // caller's inputs ready / last plain forward finished
+    bool plain_pending = false;
+    cudaEvent_t ev_h2d[2] = {}, ev_d2h[2] = {};
+    bool d2h_used[2] = {false, false};
     DevBuf a_in[2][3], a_out[2];
-    int64_t nasync = 0;
+    int64_t nsub = 0;
     static const int NEV = 32;
     cudaEvent_t ev0[NEV] = {}, ev1[NEV] = {};
     int64_t nfwd = 0;                                 // forwards whose LSTM events were recorded
@@ -325,6 +346,7 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     if (!cfg || !out) return fail(FSN_EINVAL, "null argument");
     const fsn_config& c = *cfg;
     if (c.model_kind != FSN_KIND_PLUS && c.model_kind != FSN_KIND_FSN) return fail(FSN_EINVAL, "unknown model_kind %d", c.model_kind);
+    if (c.num_freqs > 2048) return fail(FSN_EINVAL, "num_freqs > 2048 is not supported");
     if (c.num_freqs < 4 || c.look_ahead < 0 || c.sb_num_neighbors < 0 || c.fb_num_neighbors < 0) return fail(FSN_EINVAL, "bad geometry");
     if (c.sb_num_neighbors >= c.num_freqs || c.fb_num_neighbors >= c.num_freqs) return fail(FSN_EINVAL, "reflect padding needs neighbors < num_freqs");
     if (c.num_layers < 1 || c.num_layers > 4) return fail(FSN_EINVAL, "num_layers must be 1..4");
@@ -345,6 +367,8 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FSN_ECUDA, "no CUDA device: fsnplus_b200 has no CPU fallback");
     fsn_model* m = new fsn_model();
     m->cfg = c;
+    { const char* e = getenv("FSN_LSTM_IMPL"); if (e && *e) m->env_impl = atoi(e); }
+    { const char* e = getenv("FSN_NO_WS"); m->env_no_ws = e && atoi(e) != 0; }
     build_specs(m);
     for (int i = 0; i < fsn_model::NEV; ++i) { cudaEventCreate(&m->ev0[i]); cudaEventCreate(&m->ev1[i]); }
     { cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev); if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) m->num_sms = prop.multiProcessorCount; }
@@ -355,14 +379,21 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
 
 extern "C" void fsn_model_destroy(fsn_model* m) {
     if (!m) return;
-    DevBuf* all[] = {&m->arena, &m->sb_tc5_stream, &m->sb_tc5_bias, &m->fbin, &m->fbout, &m->xa, &m->xb, &m->y1, &m->y2, &m->stats,
-                     &m->mu, &m->ximg, &m->cstate, &m->magpad, &m->fbx, &m->hseq, &m->stage_in[0], &m->stage_in[1], &m->stage_in[2],
-                     &m->stage_out, &m->tW1, &m->tW2, &m->tWfc, &m->tS1, &m->tS2b, &m->tBfc, &m->x0, &m->xr, &m->xn, &m->sigma, &m->ws_h, &m->ws_bar, &m->tsse_scale, &m->sb_rowsum};
+    cudaDeviceSynchronize();
+    DevBuf* all[] = {&m->arena, &m->sb_tc5_stream, &m->sb_tc5_bias, &m->cstate, &m->stage_in[0], &m->stage_in[1], &m->stage_in[2],
+                     &m->stage_out, &m->tW1, &m->tW2, &m->tWfc, &m->tS1, &m->tS2b, &m->tBfc, &m->ws_h, &m->ws_bar};
     for (auto* b : all) b->release();
+    for (auto& ln : m->lane) {
+        ln.release_all();
+        if (ln.ev_front) cudaEventDestroy(ln.ev_front);
+        if (ln.ev_lstm) cudaEventDestroy(ln.ev_lstm);
+    }
     for (int i = 0; i < 4; ++i) { m->r_stream[i].release(); m->r_wih[i].release(); m->r_bias[i].release(); }
     m->r_gin.release(); m->r_hseq.release();
     if (m->cublas) cublasDestroy(m->cublas);
-    if (m->s_in) { cudaStreamDestroy(m->s_in); cudaStreamDestroy(m->s_out); for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_h2d[i]); cudaEventDestroy(m->ev_fwd[i]); cudaEventDestroy(m->ev_d2h[i]); } }
+    if (m->s_front) { cudaStreamDestroy(m->s_front); cudaStreamDestroy(m->s_lstm); cudaEventDestroy(m->ev_in); }
+    if (m->ev_plain) cudaEventDestroy(m->ev_plain);
+    if (m->s_in) { cudaStreamDestroy(m->s_in); cudaStreamDestroy(m->s_out); for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_h2d[i]); cudaEventDestroy(m->ev_d2h[i]); } }
     for (int i = 0; i < 2; ++i) { m->a_out[i].release(); for (int j = 0; j < 3; ++j) m->a_in[i][j].release(); }
     for (int i = 0; i < fsn_model::NEV; ++i) { if (m->ev0[i]) cudaEventDestroy(m->ev0[i]); if (m->ev1[i]) cudaEventDestroy(m->ev1[i]); }
     for (int i = 0; i < 4; ++i) { m->sb_frag[i].release(); m->sb_bias[i].release(); m->fb_frag[i].release(); m->fb_bias[i].release(); }
@@ -475,87 +506,81 @@ static void fill_ws(fsn_model* m, LstmWsLaunch& w) {
     w.L = c.num_layers; w.H = c.fb_hidden; w.I = c.num_freqs; w.Ipad = (c.num_freqs + 15) / 16 * 16; w.fast = c.fast_math; w.gru = c.rnn_type == FSN_RNN_GRU;
 }
 
-// The layer-wise tcgen05 path (k_lstm_tc5r.cu) serves stacks outside the fused kernel's envelope; FSN_TC5R=0 sends them to the
-// generic mma.sync kernel instead.
-static bool layerwise_enabled() { const char* ev = getenv("FSN_TC5R"); return !ev || atoi(ev) != 0; }
+// lstm_impl = auto: fused two-layer tcgen05 kernel when the geometry fits, else the layer-wise tcgen05 path (k_lstm_tc5r.cu), else
+// the generic mma.sync kernel; lstm_impl = mma forces the generic kernel.
 static int pick_impl(const fsn_model* m) {
-    int impl = m->cfg.lstm_impl;
-    const char* env = getenv("FSN_LSTM_IMPL");
-    if (env && *env) impl = atoi(env);
-    if (impl == FSN_LSTM_AUTO) impl = (m->tc5_ok || (m->tc5r_ok && layerwise_enabled())) ? FSN_LSTM_TCGEN05 : FSN_LSTM_MMA;
+    int impl = m->env_impl ? m->env_impl : m->cfg.lstm_impl;
+    if (impl == FSN_LSTM_AUTO) impl = (m->tc5_ok || m->tc5r_ok) ? FSN_LSTM_TCGEN05 : FSN_LSTM_MMA;
     return impl;
 }
 // tcgen05 requested, but the geometry is outside the fused two-layer kernel: run the layer-wise kernel (k_lstm_tc5r.cu)
-static bool use_layerwise(const fsn_model* m) { return layerwise_enabled() && pick_impl(m) == FSN_LSTM_TCGEN05 && !m->tc5_ok && m->tc5r_ok; }
+static bool use_layerwise(const fsn_model* m) { return pick_impl(m) == FSN_LSTM_TCGEN05 && !m->tc5_ok && m->tc5r_ok; }
 
 
-static int ensure_ws(fsn_model* m, int B, int T) {
+static int ensure_ws(fsn_model* m, fsn_model::Lane& ln, int B, int T, cudaStream_t s, cudaStream_t sl) {
     const fsn_config& c = m->cfg;
     const int F = c.num_freqs, Tp = T + c.look_ahead, Pp = (Tp + 3) & ~3;
     const int nbr = (c.model_kind == FSN_KIND_PLUS) ? 3 : 1;
     const size_t act = (size_t)nbr * B * F * Pp * 4;
-    const int rows = B * F, ntiles = ((rows + 127) / 128 + 1) / 2 * 2;      // whole CTA pairs (k_lstm_tc5p.cu)
+    const int rows = B * F, ntiles = ((rows + 127) / 128 + 1) / 2 * 2;      // whole CTA pairs (k_lstm_tc5d.cu)
+    const bool regeo = (ln.wsB != B || ln.wsT != T);
     int e = 0;
-    e |= m->fbin.ensure(act, true);
-    e |= m->fbout.ensure(act, true);
-    e |= m->mu.ensure((size_t)B * 4, true);
-    e |= m->sigma.ensure((size_t)B * 4, true);
-    e |= m->tsse_scale.ensure((size_t)nbr * B * F * 4, true);
-    e |= m->sb_rowsum.ensure((size_t)B * 4 * F * 2 * 4, true);
-    if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE) e |= m->xn.ensure((size_t)nbr * B * F * Tp * 4, true);
+    e |= ln.fbin.ensure(act, true, s);
+    e |= ln.fbout.ensure(act, true, s);
+    e |= ln.mu.ensure((size_t)B * 4, true, s);
+    e |= ln.sigma.ensure((size_t)B * 4, true, s);
+    e |= ln.tsse_scale.ensure((size_t)nbr * B * F * 4, true, s);
+    e |= ln.sb_rowsum.ensure((size_t)B * 4 * F * 2 * 4, true, s);
+    if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE) e |= ln.xn.ensure((size_t)nbr * B * F * Tp * 4, true, s);
     // images are re-zeroed whenever the geometry changes (rows beyond B*F and k >= I must stay zero)
     const size_t img_bytes = (size_t)ntiles * Tp * 16384;
-    if (m->wsB != B || m->wsT != T) { m->ximg.release(); }
-    e |= m->ximg.ensure(img_bytes, true);
+    if (regeo) { ln.ximg.release(); }
+    e |= ln.ximg.ensure(img_bytes, true, s);
+    // LSTM-side scratch: shared by both lanes (LSTM launches are serialised on the LSTM stream)
     int ra = 0;
     size_t cs = lstm_mma_cstate_bytes(c.num_layers, rows, c.sb_hidden, &ra);
     size_t cs5 = lstm_tc5_cstate_bytes(ntiles, c.sb_hidden);
     if (use_layerwise(m)) {
         const size_t M = (size_t)ntiles * Tp * 128, csr = lstm_tc5r_cstate_bytes(ntiles, c.sb_hidden);
         if (csr > cs5) cs5 = csr;
-        e |= m->r_gin.ensure(M * 4 * c.sb_hidden * 2, false);
-        if (c.num_layers > 1) e |= m->r_hseq.ensure(M * c.sb_hidden * 2, false);
+        e |= m->r_gin.ensure(M * 4 * c.sb_hidden * 2, false, sl);
+        if (c.num_layers > 1) e |= m->r_hseq.ensure(M * c.sb_hidden * 2, false, sl);
     }
-    e |= m->cstate.ensure(cs > cs5 ? cs : cs5, true);
-    if (c.model_kind == FSN_KIND_PLUS && m->tcn5) {
-        const size_t rows = (size_t)3 * B * Tp;
-        const bool regeo = (m->wsB != B || m->wsT != T);
-        if (regeo) { m->x0.release(); m->xa.release(); m->xb.release(); m->xr.release(); m->y1.release(); m->y2.release(); }
-        e |= m->x0.ensure(rows * m->Cp * 4, true);
-        e |= m->xa.ensure(rows * m->Cp * 4, true);
-        e |= m->xb.ensure(rows * m->Cp * 4, true);
-        e |= m->xr.ensure(rows * m->Cp * 4, true);
-        e |= m->y1.ensure(rows * 512 * 4, true);
-        e |= m->y2.ensure(rows * 512 * 4, true);
-        e |= m->stats.ensure((size_t)8 * 2 * 3 * B * 2 * sizeof(double), true);
+    if (c.model_kind == FSN_KIND_FSN) {
+        int ra2 = 0;
+        const size_t csf = lstm_mma_cstate_bytes(c.num_layers, B, c.fb_hidden, &ra2);
+        if (csf > cs) cs = csf;
+    }
+    e |= m->cstate.ensure(cs > cs5 ? cs : cs5, true, sl);
+    if (c.model_kind == FSN_KIND_PLUS) {
+        if (!m->tcn5) return fail(FSN_ESTATE, "the TCN weights were not packed");
+        const size_t trows = (size_t)3 * B * Tp;
+        if (regeo) { ln.x0.release(); ln.xa.release(); ln.xb.release(); ln.xr.release(); ln.y1.release(); ln.y2.release(); }
+        e |= ln.x0.ensure(trows * m->Cp * 4, true, s);
+        e |= ln.xa.ensure(trows * m->Cp * 4, true, s);
+        e |= ln.xb.ensure(trows * m->Cp * 4, true, s);
+        e |= ln.xr.ensure(trows * m->Cp * 4, true, s);
+        e |= ln.y1.ensure(trows * 512 * 4, true, s);
+        e |= ln.y2.ensure(trows * 512 * 4, true, s);
+        e |= ln.stats.ensure((size_t)8 * 2 * 3 * B * 2 * sizeof(double), true, s);
         if (!e && regeo) {
-            if (make_tmap_f32_2d(m->mapX0, m->x0.p, rows, m->Cp, 128) || make_tmap_f32_2d(m->mapXa, m->xa.p, rows, m->Cp, 128) ||
-                make_tmap_f32_2d(m->mapXb, m->xb.p, rows, m->Cp, 128) || make_tmap_f32_2d(m->mapXr, m->xr.p, rows, m->Cp, 128) ||
-                make_tmap_f32_2d(m->mapY2, m->y2.p, rows, 512, 128))
+            if (make_tmap_f32_2d(ln.mapX0, ln.x0.p, trows, m->Cp, 128) || make_tmap_f32_2d(ln.mapXa, ln.xa.p, trows, m->Cp, 128) ||
+                make_tmap_f32_2d(ln.mapXb, ln.xb.p, trows, m->Cp, 128) || make_tmap_f32_2d(ln.mapXr, ln.xr.p, trows, m->Cp, 128) ||
+                make_tmap_f32_2d(ln.mapY2, ln.y2.p, trows, 512, 128))
                 return fail(FSN_ECUDA, "cuTensorMapEncodeTiled failed for the activations");
         }
-    } else if (c.model_kind == FSN_KIND_PLUS) {
-        e |= m->xa.ensure(act, true);
-        e |= m->xb.ensure(act, true);
-        const size_t hid = (size_t)3 * B * 512 * Pp * 4;
-        e |= m->y1.ensure(hid, true);
-        e |= m->y2.ensure(hid, true);
-        e |= m->stats.ensure((size_t)8 * 2 * 3 * B * 2 * sizeof(double), true);
     } else {
         const int Ipad = (F + 15) / 16 * 16, rows_pad = (B + 63) / 64 * 64;
-        e |= m->magpad.ensure((size_t)B * F * Pp * 4, true);
-        e |= m->fbx.ensure((size_t)Tp * rows_pad * Ipad * 2, true);
-        e |= m->hseq.ensure((size_t)B * c.fb_hidden * Pp * 4, true);
-        int ra2 = 0;
-        size_t csf = lstm_mma_cstate_bytes(c.num_layers, B, c.fb_hidden, &ra2);
-        if (csf > m->cstate.bytes) e |= m->cstate.ensure(csf, true);
+        e |= ln.magpad.ensure((size_t)B * F * Pp * 4, true, s);
+        e |= ln.fbx.ensure((size_t)Tp * rows_pad * Ipad * 2, true, s);
+        e |= ln.hseq.ensure((size_t)B * c.fb_hidden * Pp * 4, true, s);
     }
     if (e) return fail(FSN_ECUDA, "workspace allocation failed for B=%d T=%d", B, T);
-    m->wsB = B; m->wsT = T;
+    ln.wsB = B; ln.wsT = T;
     return FSN_OK;
 }
 
-static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s) {
+static int run_sb_lstm(fsn_model* m, fsn_model::Lane& ln, int B, int T, float* d_out, cudaStream_t s) {
     const fsn_config& c = m->cfg;
     const int F = c.num_freqs, Tp = T + c.look_ahead, rows = B * F, ntiles = (rows + 127) / 128;
     const int impl = pick_impl(m);
@@ -571,7 +596,7 @@ static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s)
         const float one = 1.f, zero = 0.f;
         for (int l = 0; l < c.num_layers; ++l) {
             const int K = (l == 0) ? 64 : H;
-            const void* X = (l == 0) ? m->ximg.p : m->r_hseq.p;
+            const void* X = (l == 0) ? ln.ximg.p : m->r_hseq.p;
             // row-major Gin[M, 4H] = X[M, K] * Wp[4H, K]^T  ==  column-major Gin^T[4H, M] = Wp^T(op T) * X^T
             cublasStatus_t st = cublasGemmEx(m->cublas, CUBLAS_OP_T, CUBLAS_OP_N, 4 * H, (int)M, K, &one, m->r_wih[l].p, CUDA_R_16F, K, X, CUDA_R_16F, K,
                                              &zero, m->r_gin.p, CUDA_R_16F, 4 * H, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT_TENSOR_OP);
@@ -587,8 +612,7 @@ static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s)
             a.hseq = static_cast<__half*>(m->r_hseq.p);
             a.cstate = static_cast<float*>(m->cstate.p);
             a.out = d_out; a.F = F; a.la = c.look_ahead;
-            a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU; a.last = (l == c.num_layers - 1);
-            { const char* ev = getenv("FSN_TC5_DEBUG"); a.debug = ev ? atoi(ev) : 0; }
+            a.act = c.sb_act; a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU; a.last = (l == c.num_layers - 1);
             int e = launch_lstm_tc5r(a, s);
             if (e) return fail(FSN_ECUDA, "layer-wise tcgen05 LSTM launch failed (layer %d): %s", l, cudaGetErrorString((cudaError_t)e));
             m->launches++;
@@ -601,16 +625,10 @@ static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s)
         a.fc_w = P(m, "sb_model.fc_output_layer.weight");
         a.fc_b = P(m, "sb_model.fc_output_layer.bias");
         a.H = c.sb_hidden; a.I = m->Isb; a.rows = rows; a.Tp = Tp;
-        a.img = static_cast<const __half*>(m->ximg.p); a.ntiles = ntiles;
+        a.img = static_cast<const __half*>(ln.ximg.p); a.ntiles = ntiles;
         a.cstate = static_cast<float*>(m->cstate.p);
-        a.out = d_out; a.F = F; a.la = c.look_ahead; a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU;
-        { const char* ev = getenv("FSN_TC5_ELECT"); a.elect = ev ? atoi(ev) : 0; }
-        { const char* ev = getenv("FSN_TC5_NSTAGE"); a.nstage_cap = ev ? atoi(ev) : 0; }
-        { const char* ev = getenv("FSN_TC5_DEBUG"); a.debug = ev ? atoi(ev) : 0; }
-        int pair = 2;                                                   // 2: double-buffered pair kernel, 1: pair kernel, 0: single CTA
-        { const char* ev = getenv("FSN_TC5_PAIR"); if (ev) pair = atoi(ev); }
-        if (a.gru && pair == 0) pair = 2;                               // the GRU cell exists in the pair kernels only
-        int e = pair == 2 ? launch_lstm_tc5_dbuf(a, s) : pair == 1 ? launch_lstm_tc5_pair(a, s) : launch_lstm_tc5(a, s);
+        a.out = d_out; a.F = F; a.la = c.look_ahead; a.act = c.sb_act; a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU;
+        int e = launch_lstm_tc5_dbuf(a, s);
         if (e) return fail(FSN_ECUDA, "tcgen05 LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
     } else {
         LstmMmaLaunch a{};
@@ -622,7 +640,7 @@ static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s)
         a.w.fc_b = P(m, "sb_model.fc_output_layer.bias");
         a.L = c.num_layers; a.H = c.sb_hidden; a.I = m->Isb; a.Ipad = 64;
         a.rows = rows; a.Tp = Tp;
-        a.img = static_cast<const __half*>(m->ximg.p); a.ntiles = ntiles;
+        a.img = static_cast<const __half*>(ln.ximg.p); a.ntiles = ntiles;
         a.cstate = static_cast<float*>(m->cstate.p);
         lstm_mma_cstate_bytes(c.num_layers, rows, c.sb_hidden, &a.rows_alloc);
         a.out = d_out; a.O = c.output_size; a.F = F; a.la = c.look_ahead; a.act = c.sb_act;
@@ -634,8 +652,11 @@ static int run_sb_lstm(fsn_model* m, int B, int T, float* d_out, cudaStream_t s)
     return FSN_OK;
 }
 
-extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
-                                 float* d_out, void* stream) {
+// The whole forward.  Front end (norm, attention, full-band model, sub-band statistics + packing) on stream `s` into lane `ln`;
+// the sub-band LSTM on stream `sl` (== s for the plain entry point; the pipelined entry points pass the LSTM stream, ordered
+// after the front end by the lane's ev_front).
+static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                        float* d_out, cudaStream_t s, cudaStream_t sl) {
     if (!m || !d_mag || !d_out) return fail(FSN_EINVAL, "null argument");
     if (!m->finalized) return fail(FSN_ESTATE, "fsn_model_finalize has not been called");
     const fsn_config& c = m->cfg;
@@ -645,18 +666,18 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
     if (c.model_kind == FSN_KIND_PLUS && c.channel_attention == FSN_ATTN_TSSE)
         for (int i = 0; i < 3; ++i)
             if (Tp < c.kersize[i]) return fail(FSN_EINVAL, "sequence shorter than the TSSE kernel size");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int rc = ensure_ws(m, B, T);
+    int rc = ensure_ws(m, ln, B, T, s, sl);
     if (rc) return rc;
     m->launches = 0;
+    m->last_lane = (int)(&ln - m->lane);
 
     SbPackLaunch sp{};
     sp.B = B; sp.F = F; sp.Tp = Tp; sp.Ns = c.sb_num_neighbors; sp.Nf = c.fb_num_neighbors; sp.P = Pp;
-    sp.mu = static_cast<float*>(m->mu.p);
-    sp.sigma = static_cast<float*>(m->sigma.p);
-    sp.rowsum = static_cast<float*>(m->sb_rowsum.p);
+    sp.mu = static_cast<float*>(ln.mu.p);
+    sp.sigma = static_cast<float*>(ln.sigma.p);
+    sp.rowsum = static_cast<float*>(ln.sb_rowsum.p);
     sp.norm_type = c.norm_type;
-    sp.ximg = static_cast<__half*>(m->ximg.p);
+    sp.ximg = static_cast<__half*>(ln.ximg.p);
     sp.plain = use_layerwise(m) ? 1 : 0;                              // the layer-wise path feeds the images to a GEMM as a plain matrix
     sp.ntiles = (B * F + 127) / 128;
 
@@ -680,29 +701,29 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
             ta.p[b].fc1_w = P(m, p + ".fc1.weight"); ta.p[b].fc1_b = P(m, p + ".fc1.bias");
             ta.p[b].fc2_w = P(m, p + ".fc2.weight"); ta.p[b].fc2_b = P(m, p + ".fc2.bias");
         }
-        ta.out = static_cast<float*>(m->fbin.p);
-        ta.scale = static_cast<float*>(m->tsse_scale.p);
-        if (m->tcn5) { ta.out_tm = static_cast<float*>(m->x0.p); ta.Cp = m->Cp; }
+        ta.out = static_cast<float*>(ln.fbin.p);
+        ta.scale = static_cast<float*>(ln.tsse_scale.p);
+        ta.out_tm = static_cast<float*>(ln.x0.p); ta.Cp = m->Cp;
         if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE) {
             NormLaunch na{};
-            na.x[0] = d_mag; na.x[1] = d_real; na.x[2] = d_imag; na.y = static_cast<float*>(m->xn.p);
+            na.x[0] = d_mag; na.x[1] = d_real; na.x[2] = d_imag; na.y = static_cast<float*>(ln.xn.p);
             na.nbranch = 3; na.B = B; na.F = F; na.T = T; na.Tp = Tp; na.type = c.norm_type;
             launch_input_norm(na, s); m->launches++;
-            for (int b = 0; b < 3; ++b) ta.x[b] = static_cast<const float*>(m->xn.p) + (size_t)b * B * F * Tp;
+            for (int b = 0; b < 3; ++b) ta.x[b] = static_cast<const float*>(ln.xn.p) + (size_t)b * B * F * Tp;
             ta.T = Tp; ta.prenorm = 1;                                  // padded frames are part of the normalised signal
         }
         launch_tsse_norm(ta, s); m->launches += 2;
 
         const int Z = 3 * B;
-        double* stats = static_cast<double*>(m->stats.p);
+        double* stats = static_cast<double*>(ln.stats.p);
         CK(cudaMemsetAsync(stats, 0, (size_t)8 * 2 * Z * 2 * sizeof(double), s));
         static const int dil[8] = {1, 2, 5, 9, 1, 2, 5, 9};     // sequence_model.py:47-58
-        if (m->tcn5) {
+        {
             const int Cp = m->Cp;
             GemmTc5Launch g{};
             g.rows_per_branch = B * Tp; g.tiles_m = (B * Tp + 127) / 128; g.nbranch = 3; g.Tp = Tp; g.B = B;
-            const float* curp = static_cast<const float*>(m->x0.p);
-            const unsigned char* curmap = m->mapX0;
+            const float* curp = static_cast<const float*>(ln.x0.p);
+            const unsigned char* curmap = ln.mapX0;
             for (int blk = 0; blk < 8; ++blk) {
                 double* st1 = stats + (size_t)(2 * blk) * Z * 2;
                 double* st2 = stats + (size_t)(2 * blk + 1) * Z * 2;
@@ -710,13 +731,13 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
                 GemmTc5Launch g1 = g;
                 g1.epi = EPI5_PRELU_STATS; g1.Kp = Cp; g1.NT = 256; g1.ntiles_n = 2; g1.Npad = 512;
                 for (int b = 0; b < 3; ++b) { g1.bias[b] = P(m, key(b, "conv1x1.bias")); g1.prelu[b] = P(m, key(b, "prelu1.weight")); }
-                g1.stats_out = st1; g1.Y = static_cast<float*>(m->y1.p); g1.ldY = 512;
+                g1.stats_out = st1; g1.Y = static_cast<float*>(ln.y1.p); g1.ldY = 512;
                 int e = launch_gemm_tc5(curmap, m->mapW1[blk], g1, m->num_sms, s);
                 if (e) return fail(FSN_ECUDA, "TCN GEMM1 launch failed: %s", cudaGetErrorString((cudaError_t)e));
                 m->launches++;
 
                 DwTmLaunch dw{};
-                dw.X = static_cast<const float*>(m->y1.p); dw.Y = static_cast<float*>(m->y2.p);
+                dw.X = static_cast<const float*>(ln.y1.p); dw.Y = static_cast<float*>(ln.y2.p);
                 dw.Z = Z; dw.B = B; dw.C = 512; dw.Tp = Tp; dw.dilation = dil[blk]; dw.tchunk = 48;
                 dw.stats_in = st1; dw.stats_out = st2;
                 for (int b = 0; b < 3; ++b) {
@@ -726,7 +747,7 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
                 }
                 launch_dwconv_tm(dw, s); m->launches++;
 
-                float* nxtp = (blk & 1) ? static_cast<float*>(m->xb.p) : static_cast<float*>(m->xa.p);
+                float* nxtp = (blk & 1) ? static_cast<float*>(ln.xb.p) : static_cast<float*>(ln.xa.p);
                 GemmTc5Launch g2 = g;
                 g2.epi = EPI5_GLN_RES; g2.Kp = 512; g2.NT = m->tcnNT; g2.ntiles_n = m->tcnNtiles; g2.Npad = Cp;
                 for (int b = 0; b < 3; ++b) {
@@ -734,94 +755,51 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
                     g2.s1[b] = static_cast<const float*>(m->tS1.p) + ((size_t)blk * 3 + b) * Cp;
                 }
                 g2.stats_in = st2; g2.count_in = (double)512 * Tp;
-                g2.Xold = curp; g2.Y = nxtp; g2.ldY = Cp; g2.Xrelu = (blk == 7) ? static_cast<float*>(m->xr.p) : nullptr;
-                e = launch_gemm_tc5(m->mapY2, m->mapW2[blk], g2, m->num_sms, s);
+                g2.Xold = curp; g2.Y = nxtp; g2.ldY = Cp; g2.Xrelu = (blk == 7) ? static_cast<float*>(ln.xr.p) : nullptr;
+                e = launch_gemm_tc5(ln.mapY2, m->mapW2[blk], g2, m->num_sms, s);
                 if (e) return fail(FSN_ECUDA, "TCN GEMM2 launch failed: %s", cudaGetErrorString((cudaError_t)e));
                 m->launches++;
                 curp = nxtp;
-                curmap = (blk & 1) ? m->mapXb : m->mapXa;
+                curmap = (blk & 1) ? ln.mapXb : ln.mapXa;
             }
             GemmTc5Launch g3 = g;
             g3.epi = EPI5_OUT; g3.Kp = Cp; g3.NT = m->tcnNT; g3.ntiles_n = m->tcnNtiles; g3.Npad = Cp;
             for (int b = 0; b < 3; ++b) g3.bias[b] = static_cast<const float*>(m->tBfc.p) + (size_t)b * Cp;
-            g3.out = static_cast<float*>(m->fbout.p); g3.F = F; g3.P = Pp; g3.act = c.fb_act;
-            int e = launch_gemm_tc5(m->mapXr, m->mapWfc, g3, m->num_sms, s);
+            g3.out = static_cast<float*>(ln.fbout.p); g3.F = F; g3.P = Pp; g3.act = c.fb_act;
+            int e = launch_gemm_tc5(ln.mapXr, m->mapWfc, g3, m->num_sms, s);
             if (e) return fail(FSN_ECUDA, "TCN output GEMM launch failed: %s", cudaGetErrorString((cudaError_t)e));
             m->launches++;
-        } else {
-        const float* cur = static_cast<const float*>(m->fbin.p);
-        float* nxt = static_cast<float*>(m->xa.p);
-        for (int blk = 0; blk < 8; ++blk) {
-            double* st1 = stats + (size_t)(2 * blk) * Z * 2;
-            double* st2 = stats + (size_t)(2 * blk + 1) * Z * 2;
-            auto key = [&](int b, const char* leaf) { return std::string("fb_model") + sfx[b] + ".sequence_model." + std::to_string(blk) + "." + leaf; };
-            ConvLaunch ca{};
-            ca.X = cur; ca.Y = static_cast<float*>(m->y1.p); ca.Z = Z; ca.zper = B; ca.M = 512; ca.K = F; ca.Tp = Tp; ca.P = Pp;
-            ca.pro = PRO_NONE; ca.epi = EPI_PRELU_STATS; ca.stats_out = st1;
-            for (int b = 0; b < 3; ++b) { ca.W[b] = P(m, key(b, "conv1x1.weight")); ca.bias[b] = P(m, key(b, "conv1x1.bias")); ca.prelu[b] = P(m, key(b, "prelu1.weight")); }
-            launch_conv1x1(ca, s); m->launches++;
-
-            DwLaunch da{};
-            da.X = static_cast<const float*>(m->y1.p); da.Y = static_cast<float*>(m->y2.p);
-            da.Z = Z; da.zper = B; da.C = 512; da.Tp = Tp; da.P = Pp; da.dilation = dil[blk];
-            da.stats_in = st1; da.stats_out = st2;
-            for (int b = 0; b < 3; ++b) {
-                da.gamma[b] = P(m, key(b, "norm1.weight")); da.beta[b] = P(m, key(b, "norm1.bias"));
-                da.w[b] = P(m, key(b, "depthwise_conv.weight")); da.b[b] = P(m, key(b, "depthwise_conv.bias"));
-                da.prelu[b] = P(m, key(b, "prelu2.weight"));
-            }
-            launch_dwconv(da, s); m->launches++;
-
-            ConvLaunch cc{};
-            cc.X = static_cast<const float*>(m->y2.p); cc.Y = nxt; cc.Z = Z; cc.zper = B; cc.M = F; cc.K = 512; cc.Tp = Tp; cc.P = Pp;
-            cc.pro = PRO_GLN; cc.epi = EPI_RESIDUAL; cc.stats_in = st2; cc.count_in = (double)512 * Tp; cc.R = cur;
-            for (int b = 0; b < 3; ++b) {
-                cc.W[b] = P(m, key(b, "sconv.weight")); cc.bias[b] = P(m, key(b, "sconv.bias"));
-                cc.gamma[b] = P(m, key(b, "norm2.weight")); cc.beta[b] = P(m, key(b, "norm2.bias"));
-            }
-            launch_conv1x1(cc, s); m->launches++;
-            cur = nxt;
-            nxt = (nxt == static_cast<float*>(m->xa.p)) ? static_cast<float*>(m->xb.p) : static_cast<float*>(m->xa.p);
-        }
-        ConvLaunch cf{};
-        cf.X = cur; cf.Y = static_cast<float*>(m->fbout.p); cf.Z = Z; cf.zper = B; cf.M = F; cf.K = F; cf.Tp = Tp; cf.P = Pp;
-        cf.pro = PRO_RELU; cf.epi = EPI_ACT; cf.act = c.fb_act;
-        for (int b = 0; b < 3; ++b) {
-            cf.W[b] = P(m, std::string("fb_model") + sfx[b] + ".fc_output_layer.weight");
-            cf.bias[b] = P(m, std::string("fb_model") + sfx[b] + ".fc_output_layer.bias");
-        }
-        launch_conv1x1(cf, s); m->launches++;
         }
 
-        sp.win = static_cast<const float*>(m->fbin.p); sp.Pw = Pp;      // post-attention mag branch (fullsubnet_plus.py:182)
+        sp.win = static_cast<const float*>(ln.fbin.p); sp.Pw = Pp;      // post-attention mag branch (fullsubnet_plus.py:182)
         sp.nfb = 3;
-        for (int b = 0; b < 3; ++b) sp.fb[b] = static_cast<const float*>(m->fbout.p) + (size_t)b * B * F * Pp;
+        for (int b = 0; b < 3; ++b) sp.fb[b] = static_cast<const float*>(ln.fbout.p) + (size_t)b * B * F * Pp;
     } else {
         TsseLaunch ta{};
         ta.x[0] = d_mag; ta.nbranch = 1; ta.B = B; ta.F = F; ta.T = T; ta.Tp = Tp; ta.P = Pp; ta.attention = 0;
-        ta.out = static_cast<float*>(m->fbin.p);
-        ta.scale = static_cast<float*>(m->tsse_scale.p);
+        ta.out = static_cast<float*>(ln.fbin.p);
+        ta.scale = static_cast<float*>(ln.tsse_scale.p);
         if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE) {
             NormLaunch na{};
-            na.x[0] = d_mag; na.y = static_cast<float*>(m->xn.p);
+            na.x[0] = d_mag; na.y = static_cast<float*>(ln.xn.p);
             na.nbranch = 1; na.B = B; na.F = F; na.T = T; na.Tp = Tp; na.type = c.norm_type;
             launch_input_norm(na, s); m->launches++;
-            ta.x[0] = static_cast<const float*>(m->xn.p); ta.T = Tp; ta.prenorm = 1;
+            ta.x[0] = static_cast<const float*>(ln.xn.p); ta.T = Tp; ta.prenorm = 1;
         }
         launch_tsse_norm(ta, s); m->launches += 2;
-        launch_pad_copy(d_mag, static_cast<float*>(m->magpad.p), B, F, T, Pp, s); m->launches++;
+        launch_pad_copy(d_mag, static_cast<float*>(ln.magpad.p), B, F, T, Pp, s); m->launches++;
         const int Ipad = (F + 15) / 16 * 16, rows_pad = (B + 63) / 64 * 64;
-        launch_fb_pack(static_cast<const float*>(m->fbin.p), static_cast<__half*>(m->fbx.p), B, F, Tp, Pp, rows_pad, Ipad, s); m->launches++;
-        if (lstm_ws_supported(c.num_layers, c.fb_hidden, Ipad, B, m->num_sms) && !getenv("FSN_NO_WS")) {
+        launch_fb_pack(static_cast<const float*>(ln.fbin.p), static_cast<__half*>(ln.fbx.p), B, F, Tp, Pp, rows_pad, Ipad, s); m->launches++;
+        if (lstm_ws_supported(c.num_layers, c.fb_hidden, Ipad, B, m->num_sms) && !m->env_no_ws) {
             const size_t hb = (size_t)c.num_layers * 2 * 64 * c.fb_hidden * 2;
-            if (m->ws_h.ensure(hb, false) || m->ws_bar.ensure(64, true)) return fail(FSN_ECUDA, "allocation failed");
+            if (m->ws_h.ensure(hb, false, s) || m->ws_bar.ensure(64, true, s)) return fail(FSN_ECUDA, "allocation failed");
             CK(cudaMemsetAsync(m->ws_h.p, 0, hb, s));
             LstmWsLaunch w{};
             fill_ws(m, w);
             w.rows = B; w.rows_pad = rows_pad; w.Tp = Tp;
-            w.x = static_cast<const __half*>(m->fbx.p); w.hbuf = static_cast<__half*>(m->ws_h.p); w.cbuf = nullptr;
+            w.x = static_cast<const __half*>(ln.fbx.p); w.hbuf = static_cast<__half*>(m->ws_h.p); w.cbuf = nullptr;
             w.barrier = static_cast<unsigned int*>(m->ws_bar.p);
-            w.hseq = static_cast<float*>(m->hseq.p); w.P = Pp; w.resume = 0; w.t0 = 0;
+            w.hseq = static_cast<float*>(ln.hseq.p); w.P = Pp; w.resume = 0; w.t0 = 0;
             int e = launch_lstm_ws(w, s);
             if (e) return fail(FSN_ECUDA, "weight-stationary full-band LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
             m->launches++;
@@ -832,34 +810,106 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
             a.w.bias[l] = static_cast<const float*>(m->fb_bias[l].p);
         }
         a.L = c.num_layers; a.H = c.fb_hidden; a.I = F; a.Ipad = Ipad; a.rows = B; a.Tp = Tp;
-        a.xplain = static_cast<const __half*>(m->fbx.p); a.rows_pad = rows_pad;
+        a.xplain = static_cast<const __half*>(ln.fbx.p); a.rows_pad = rows_pad;
         a.cstate = static_cast<float*>(m->cstate.p);
         lstm_mma_cstate_bytes(c.num_layers, B, c.fb_hidden, &a.rows_alloc);
-        a.hseq = static_cast<float*>(m->hseq.p); a.P = Pp; a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU;
+        a.hseq = static_cast<float*>(ln.hseq.p); a.P = Pp; a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU;
         int e = launch_lstm_mma(a, s);
         if (e) return fail(FSN_ECUDA, "full-band LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
         m->launches++;
         }
         ConvLaunch cf{};
-        cf.X = static_cast<const float*>(m->hseq.p); cf.Y = static_cast<float*>(m->fbout.p);
-        cf.Z = B; cf.zper = B; cf.M = F; cf.K = c.fb_hidden; cf.Tp = Tp; cf.P = Pp;
-        cf.pro = PRO_NONE; cf.epi = EPI_ACT; cf.act = c.fb_act;
-        cf.W[0] = P(m, "fb_model.fc_output_layer.weight"); cf.bias[0] = P(m, "fb_model.fc_output_layer.bias");
+        cf.X = static_cast<const float*>(ln.hseq.p); cf.Y = static_cast<float*>(ln.fbout.p);
+        cf.Z = B; cf.M = F; cf.K = c.fb_hidden; cf.Tp = Tp; cf.P = Pp; cf.act = c.fb_act;
+        cf.W = P(m, "fb_model.fc_output_layer.weight"); cf.bias = P(m, "fb_model.fc_output_layer.bias");
         launch_conv1x1(cf, s); m->launches++;
 
-        sp.win = static_cast<const float*>(m->magpad.p); sp.Pw = Pp;    // raw padded magnitude (fullsubnet.py:94)
+        sp.win = static_cast<const float*>(ln.magpad.p); sp.Pw = Pp;    // raw padded magnitude (fullsubnet.py:94)
         sp.nfb = 1;
-        sp.fb[0] = static_cast<const float*>(m->fbout.p);
+        sp.fb[0] = static_cast<const float*>(ln.fbout.p);
     }
     launch_sb_stats(sp, s); m->launches += 2;
     launch_sb_pack(sp, s); m->launches++;
+    if (sl != s) {                                                      // pipelined: the LSTM stream picks the lane up when the front end is done
+        CK(cudaEventRecord(ln.ev_front, s));
+        CK(cudaStreamWaitEvent(sl, ln.ev_front, 0));
+    }
     const int evi = (int)(m->nfwd % fsn_model::NEV);
-    cudaEventRecord(m->ev0[evi], s);
-    rc = run_sb_lstm(m, B, T, d_out, s);
-    cudaEventRecord(m->ev1[evi], s);
+    cudaEventRecord(m->ev0[evi], sl);
+    rc = run_sb_lstm(m, ln, B, T, d_out, sl);
+    cudaEventRecord(m->ev1[evi], sl);
     if (rc) return rc;
     m->nfwd++;
     CK(cudaGetLastError());
+    return FSN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pipelined execution: internal streams, lanes
+// ---------------------------------------------------------------------------------------------
+static int ensure_pipeline(fsn_model* m) {
+    if (m->s_front) return FSN_OK;
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));                     // hi = numerically lowest = highest priority
+    CK(cudaStreamCreateWithPriority(&m->s_front, cudaStreamNonBlocking, lo));
+    CK(cudaStreamCreateWithPriority(&m->s_lstm, cudaStreamNonBlocking, hi));   // the LSTM's CTA pairs win the SMs when both are pending
+    CK(cudaEventCreateWithFlags(&m->ev_in, cudaEventDisableTiming));
+    for (auto& ln : m->lane) {
+        CK(cudaEventCreateWithFlags(&ln.ev_front, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ln.ev_lstm, cudaEventDisableTiming));
+    }
+    return FSN_OK;
+}
+
+// one pipelined batch: inputs are ready once `ready` (an event, may be null) has fired; returns the lane used
+static int submit_impl(fsn_model* m, cudaEvent_t ready, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                       float* d_out, int* lane_out) {
+    int rc = ensure_pipeline(m);
+    if (rc) return rc;
+    const bool overlap = (m->cfg.model_kind == FSN_KIND_PLUS);           // fullsubnet.Model: its full-band LSTM is a cooperative launch and
+    const int slot = overlap ? (int)(m->nsub & 1) : 0;                   // shares the LSTM scratch -> one lane, one stream, no overlap
+    fsn_model::Lane& ln = m->lane[slot];
+    cudaStream_t sf = overlap ? m->s_front : m->s_lstm;
+    if (ready) CK(cudaStreamWaitEvent(sf, ready, 0));
+    if (m->plain_pending) { CK(cudaStreamWaitEvent(sf, m->ev_plain, 0)); CK(cudaStreamWaitEvent(m->s_lstm, m->ev_plain, 0)); }
+    if (ln.used) CK(cudaStreamWaitEvent(sf, ln.ev_lstm, 0));              // the LSTM that read this lane has finished
+    rc = forward_impl(m, ln, d_mag, d_real, d_imag, B, T, d_out, sf, m->s_lstm);
+    if (rc) return rc;
+    CK(cudaEventRecord(ln.ev_lstm, m->s_lstm));
+    ln.used = true;
+    m->nsub++;
+    if (lane_out) *lane_out = slot;
+    return FSN_OK;
+}
+
+extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                                 float* d_out, void* stream) {
+    if (!m) return fail(FSN_EINVAL, "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (auto& ln : m->lane)                                             // batches still in flight in the pipeline share the scratch buffers
+        if (ln.used) CK(cudaStreamWaitEvent(s, ln.ev_lstm, 0));
+    int rc = forward_impl(m, m->lane[0], d_mag, d_real, d_imag, B, T, d_out, s, s);
+    if (rc) return rc;
+    if (!m->ev_plain) CK(cudaEventCreateWithFlags(&m->ev_plain, cudaEventDisableTiming));
+    CK(cudaEventRecord(m->ev_plain, s));
+    m->plain_pending = true;
+    return FSN_OK;
+}
+
+extern "C" int fsn_model_submit(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                                float* d_out, void* stream) {
+    if (!m) return fail(FSN_EINVAL, "null argument");
+    int rc = ensure_pipeline(m);
+    if (rc) return rc;
+    CK(cudaEventRecord(m->ev_in, static_cast<cudaStream_t>(stream)));    // everything enqueued on the caller's stream so far (the inputs)
+    return submit_impl(m, m->ev_in, d_mag, d_real, d_imag, B, T, d_out, nullptr);
+}
+
+extern "C" int fsn_model_wait(fsn_model* m, void* stream) {
+    if (!m) return fail(FSN_EINVAL, "null model");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (auto& ln : m->lane)
+        if (ln.used) CK(cudaStreamWaitEvent(s, ln.ev_lstm, 0));
     return FSN_OK;
 }
 
@@ -888,23 +938,26 @@ extern "C" int fsn_model_forward_host(fsn_model* m, const float* h_mag, const fl
 extern "C" int fsn_model_forward_host_async(fsn_model* m, const float* h_mag, const float* h_real, const float* h_imag, int32_t B, int32_t T,
                                             float* h_out, void* stream) {
     if (!m || !h_mag || !h_out) return fail(FSN_EINVAL, "null argument");
+    (void)stream;                                                        // host buffers carry no stream order; the work runs on internal streams
     const fsn_config& c = m->cfg;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = ensure_pipeline(m);
+    if (rc) return rc;
     if (!m->s_in) {
         CK(cudaStreamCreateWithFlags(&m->s_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             CK(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&m->ev_fwd[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&m->ev_d2h[i], cudaEventDisableTiming));
         }
     }
-    const int slot = (int)(m->nasync & 1);
-    const bool reuse = m->nasync >= 2;
+    const bool overlap = (c.model_kind == FSN_KIND_PLUS);
+    const int slot = overlap ? (int)(m->nsub & 1) : 0;                   // staging slot == lane
+    fsn_model::Lane& ln = m->lane[slot];
     const size_t in_bytes = (size_t)B * c.num_freqs * T * 4, out_bytes = (size_t)B * c.output_size * c.num_freqs * T * 4;
     const float* hin[3] = {h_mag, h_real, h_imag};
     const int nin = (c.model_kind == FSN_KIND_PLUS) ? 3 : 1;
-    if (reuse) CK(cudaStreamWaitEvent(m->s_in, m->ev_fwd[slot], 0));          // the forward that read this input slot is done
+    // the front end that read this input slot: it finished before the lane's LSTM did
+    if (ln.used) CK(cudaStreamWaitEvent(m->s_in, ln.ev_lstm, 0));
     for (int i = 0; i < nin; ++i) {
         if (!hin[i]) return fail(FSN_EINVAL, "missing input %d", i);
         if (m->a_in[slot][i].bytes < in_bytes) {
@@ -918,42 +971,44 @@ extern "C" int fsn_model_forward_host_async(fsn_model* m, const float* h_mag, co
         CK(cudaDeviceSynchronize());
         if (m->a_out[slot].ensure(out_bytes, false)) return fail(FSN_ECUDA, "staging allocation failed");
     }
-    CK(cudaStreamWaitEvent(s, m->ev_h2d[slot], 0));
-    if (reuse) CK(cudaStreamWaitEvent(s, m->ev_d2h[slot], 0));                // the copy-out that read this output slot is done
-    int rc = fsn_model_forward(m, static_cast<const float*>(m->a_in[slot][0].p), static_cast<const float*>(m->a_in[slot][1].p),
-                               static_cast<const float*>(m->a_in[slot][2].p), B, T, static_cast<float*>(m->a_out[slot].p), stream);
+    if (m->d2h_used[slot]) CK(cudaStreamWaitEvent(m->s_lstm, m->ev_d2h[slot], 0));   // the copy-out that read this output slot is done
+    int used = 0;
+    rc = submit_impl(m, m->ev_h2d[slot], static_cast<const float*>(m->a_in[slot][0].p), static_cast<const float*>(m->a_in[slot][1].p),
+                     static_cast<const float*>(m->a_in[slot][2].p), B, T, static_cast<float*>(m->a_out[slot].p), &used);
     if (rc) return rc;
-    CK(cudaEventRecord(m->ev_fwd[slot], s));
-    CK(cudaStreamWaitEvent(m->s_out, m->ev_fwd[slot], 0));
+    CK(cudaStreamWaitEvent(m->s_out, ln.ev_lstm, 0));
     CK(cudaMemcpyAsync(h_out, m->a_out[slot].p, out_bytes, cudaMemcpyDeviceToHost, m->s_out));
     CK(cudaEventRecord(m->ev_d2h[slot], m->s_out));
-    m->nasync++;
+    m->d2h_used[slot] = true;
     return FSN_OK;
 }
 
 extern "C" int fsn_model_sync_host(fsn_model* m) {
     if (!m) return fail(FSN_EINVAL, "null model");
-    if (m->s_in) { CK(cudaStreamSynchronize(m->s_in)); CK(cudaStreamSynchronize(m->s_out)); }
+    if (m->s_in) { CK(cudaStreamSynchronize(m->s_in)); }
+    if (m->s_lstm) { CK(cudaStreamSynchronize(m->s_front)); CK(cudaStreamSynchronize(m->s_lstm)); }
+    if (m->s_out) { CK(cudaStreamSynchronize(m->s_out)); }
     return FSN_OK;
 }
 
 extern "C" int fsn_model_get_stage(fsn_model* m, const char* name, float* d_dst, int64_t numel, void* stream) {
     if (!m || !name || !d_dst) return fail(FSN_EINVAL, "null argument");
-    if (!m->wsB) return fail(FSN_ESTATE, "no forward has run yet");
+    fsn_model::Lane& ln = m->lane[m->last_lane];
+    if (!ln.wsB) return fail(FSN_ESTATE, "no forward has run yet");
     const fsn_config& c = m->cfg;
-    const int F = c.num_freqs, Tp = m->wsT + c.look_ahead, Pp = (Tp + 3) & ~3, B = m->wsB;
+    const int F = c.num_freqs, Tp = ln.wsT + c.look_ahead, Pp = (Tp + 3) & ~3, B = ln.wsB;
     const int nbr = (c.model_kind == FSN_KIND_PLUS) ? 3 : 1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const std::string n(name);
     if (n == "fb_in" || n == "fb_out") {
         if (numel != (int64_t)nbr * B * F * Tp) return fail(FSN_EINVAL, "%s needs %lld elements", name, (long long)nbr * B * F * Tp);
-        const void* src = (n == "fb_in") ? m->fbin.p : m->fbout.p;
+        const void* src = (n == "fb_in") ? ln.fbin.p : ln.fbout.p;
         CK(cudaMemcpy2DAsync(d_dst, (size_t)Tp * 4, src, (size_t)Pp * 4, (size_t)Tp * 4, (size_t)nbr * B * F, cudaMemcpyDeviceToDevice, s));
         return FSN_OK;
     }
     if (n == "sb_mu") {
         if (numel != B) return fail(FSN_EINVAL, "sb_mu needs %d elements", B);
-        CK(cudaMemcpyAsync(d_dst, m->mu.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(d_dst, ln.mu.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
         return FSN_OK;
     }
     return fail(FSN_EINVAL, "unknown stage %s", name);
@@ -994,7 +1049,7 @@ extern "C" int fsn_stream_create(fsn_model* m, int32_t B, fsn_stream** out) {
     e |= st->c_sb.ensure(lstm_mma_cstate_bytes(c.num_layers, rows, c.sb_hidden, &st->ra_sb), true);
     e |= st->h_fb.ensure((size_t)c.num_layers * st->ra_fb * c.fb_hidden * 2, true);
     e |= st->h_sb.ensure((size_t)c.num_layers * st->ra_sb * c.sb_hidden * 2, true);
-    st->use_ws = lstm_ws_supported(c.num_layers, c.fb_hidden, st->Ipad, B, m->num_sms) && !getenv("FSN_NO_WS");
+    st->use_ws = lstm_ws_supported(c.num_layers, c.fb_hidden, st->Ipad, B, m->num_sms) && !m->env_no_ws;
     if (st->use_ws) {
         e |= st->ws_h.ensure((size_t)c.num_layers * 2 * 64 * c.fb_hidden * 2, true);
         e |= st->ws_c.ensure((size_t)c.num_layers * 64 * c.fb_hidden * 4, true);
@@ -1043,9 +1098,8 @@ extern "C" int fsn_stream_step(fsn_stream* st, const float* d_mag, float* d_mask
     if (e) return fail(FSN_ECUDA, "full-band LSTM step failed: %s", cudaGetErrorString((cudaError_t)e));
     ConvLaunch cf{};
     cf.X = static_cast<const float*>(st->hseq.p); cf.Y = static_cast<float*>(st->fbout.p);
-    cf.Z = B; cf.zper = B; cf.M = F; cf.K = c.fb_hidden; cf.Tp = 1; cf.P = 4;
-    cf.pro = PRO_NONE; cf.epi = EPI_ACT; cf.act = c.fb_act;
-    cf.W[0] = P(m, "fb_model.fc_output_layer.weight"); cf.bias[0] = P(m, "fb_model.fc_output_layer.bias");
+    cf.Z = B; cf.M = F; cf.K = c.fb_hidden; cf.Tp = 1; cf.P = 4; cf.act = c.fb_act;
+    cf.W = P(m, "fb_model.fc_output_layer.weight"); cf.bias = P(m, "fb_model.fc_output_layer.bias");
     launch_conv1x1(cf, s);
     StreamPackLaunch pa{d_mag, static_cast<const float*>(st->fbout.p), 4, static_cast<double*>(st->cum_sb.p), static_cast<__half*>(st->ximg.p),
                         B, F, c.sb_num_neighbors, c.fb_num_neighbors, n, c.norm_type};
@@ -1091,11 +1145,3 @@ extern "C" float fsn_model_last_lstm_ms(fsn_model* m) {
     return fsn_model_lstm_ms_history(m, &ms, 1) == 1 ? ms : -1.f;
 }
 extern "C" int fsn_model_last_lstm_impl(const fsn_model* m) { return m ? m->last_impl : 0; }
-
-extern "C" int fsn_probe_tcgen05(float* h_report, int32_t n) {
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FSN_ECUDA, "no CUDA device");
-    int rc = run_probe_tcgen05(h_report, n);
-    if (rc < 0) return fail(FSN_ECUDA, "probe failed (rc=%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
-    return rc;
-}

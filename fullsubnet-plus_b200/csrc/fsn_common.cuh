@@ -32,6 +32,14 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_
 template <bool FAST> __device__ __forceinline__ float sigm(float x) { return FAST ? sigmoid_fast(x) : sigmoid_acc(x); }
 template <bool FAST> __device__ __forceinline__ float tanh_(float x) { return FAST ? tanh_approx(x) : tanh_acc(x); }
 
+// output activation of SequenceModel (sequence_model.py:84-93, 120-121); codes = FSN_ACT_* of include/fsnplus_b200.h
+__device__ __forceinline__ float apply_act(float y, int act) {
+    if (act == 1) return fmaxf(y, 0.f);
+    if (act == 2) return tanhf(y);
+    if (act == 3) return fminf(fmaxf(y, 0.f), 6.f);
+    return y;
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);

@@ -35,40 +35,15 @@ void launch_tsse_norm(const TsseLaunch& a, cudaStream_t s);
 struct NormLaunch { const float* x[3]; float* y; int nbranch, B, F, T, Tp, type; };
 void launch_input_norm(const NormLaunch& a, cudaStream_t s);
 
-enum { PRO_NONE = 0, PRO_GLN = 1, PRO_RELU = 2 };
-enum { EPI_NONE = 0, EPI_PRELU_STATS = 1, EPI_RESIDUAL = 2, EPI_ACT = 3 };
-struct ConvLaunch {
-    const float* X;      // [Z, K, P]
-    const float* W[3];   // per group [M, K]
-    const float* bias[3];
-    float* Y;            // [Z, M, P]
-    int Z, zper;         // group g = z / zper
-    int M, K, Tp, P;
-    int pro, epi;
-    const double* stats_in;   // [Z, 2] (sum, sumsq) of X          (PRO_GLN)
-    const float* gamma[3];    // [K]
-    const float* beta[3];
-    double* stats_out;        // [Z, 2] accumulated over Y          (EPI_PRELU_STATS)
-    const float* prelu[3];    // [1]
-    const float* R;           // residual [Z, M, P]                 (EPI_RESIDUAL)
-    int act;                  // FSN_ACT_*                          (EPI_ACT)
-    double count_in;          // elements per sample in the GLN statistics (K * Tp)
+struct ConvLaunch {          // Y[z] = act(W X[z] + b): output Linear of the full-band LSTM (fullsubnet.Model)
+    const float* X;          // [Z, K, P]
+    const float* W;          // [M, K]
+    const float* bias;       // [M]
+    float* Y;                // [Z, M, P]
+    int Z, M, K, Tp, P;
+    int act;                 // FSN_ACT_*
 };
 void launch_conv1x1(const ConvLaunch& a, cudaStream_t s);
-
-struct DwLaunch {
-    const float* X;  // [Z, C, P] (post-PReLU1)
-    float* Y;        // [Z, C, P] (post-PReLU2)
-    int Z, zper, C, Tp, P, dilation;
-    const double* stats_in;
-    double* stats_out;
-    const float* gamma[3];
-    const float* beta[3];
-    const float* w[3];      // [C, 3]
-    const float* b[3];      // [C]
-    const float* prelu[3];  // [1]
-};
-void launch_dwconv(const DwLaunch& a, cudaStream_t s);
 
 struct SbPackLaunch {
     const float* win;        // [B, F, Pw] window source (post-attention mag branch, or raw padded mag)
@@ -142,7 +117,7 @@ struct LstmWsLaunch {
 bool lstm_ws_supported(int L, int H, int Ipad, int rows, int num_sms);
 int launch_lstm_ws(const LstmWsLaunch& a, cudaStream_t s);
 
-// ---- k_lstm_tc5.cu ---------------------------------------------------------------------------
+// ---- k_lstm_tc5d.cu --------------------------------------------------------------------------
 struct LstmTc5Launch {
     const __half* wstream;    // packed weight stream (fsn_tc5_pack_weights)
     const float* bias;        // [2][4H] permuted to the stream's gate-column order
@@ -153,17 +128,13 @@ struct LstmTc5Launch {
     const __half* img; int ntiles;   // [ntiles, Tp, 16 KB]
     float* cstate;            // [ntiles][2 layers][H/16 chunks][4][128][4] fp32
     float* out; int F, la;
+    int act;                  // FSN_ACT_* applied to the Linear output (sb_output_activate_function, sequence_model.py:120-121)
     int fast;
-    int gru;                  // 1: pseudo-gate GRU cell (pair kernel only)
-    int elect;                // tuning knob: 1 = one elected mbarrier arrive per epilogue warp, 0 = every thread arrives
-    int nstage_cap;           // tuning knob: cap on the weight ring depth (0 = as many as fit)
-    int debug;                // timing experiments only (results invalid): 1 = skip the cell update, 2 = MMA issuer ignores accempty
+    int gru;                  // 1: pseudo-gate GRU cell
 };
 size_t lstm_tc5_cstate_bytes(int ntiles, int H);
 bool lstm_tc5_supported(int L, int H, int I, int O);
-int launch_lstm_tc5(const LstmTc5Launch& a, cudaStream_t s);
-int launch_lstm_tc5_pair(const LstmTc5Launch& a, cudaStream_t s);   // k_lstm_tc5p.cu: cta_group::2 version (2-CTA clusters)
-int launch_lstm_tc5_dbuf(const LstmTc5Launch& a, cudaStream_t s);   // k_lstm_tc5d.cu: pair kernel with two 64-column accumulators (default)
+int launch_lstm_tc5_dbuf(const LstmTc5Launch& a, cudaStream_t s);   // k_lstm_tc5d.cu: CTA-pair kernel with two 64-column accumulators
 
 // ---- k_lstm_tc5r.cu: single-layer recurrent kernel (time-batched input projection) for stacks outside the fused kernel's envelope
 struct LstmTc5rLaunch {
@@ -176,7 +147,8 @@ struct LstmTc5rLaunch {
     __half* hseq;             // [ntiles_pad * Tp * 128, H] fp16 output sequence (not the last layer)
     float* cstate;            // [ntiles_pad][H/32][4][2][128][4] fp32
     float* out; int F, la;    // last layer: mask [B, 2, F, Tp - la]
-    int fast, gru, last, debug;
+    int act;                  // FSN_ACT_* on the Linear output (last layer)
+    int fast, gru, last;
 };
 bool lstm_tc5r_supported(int H, int O);
 size_t lstm_tc5r_cstate_bytes(int ntiles, int H);
@@ -209,8 +181,5 @@ struct DwTmLaunch {
     const float* gamma[3]; const float* beta[3]; const float* w[3]; const float* b[3]; const float* prelu[3];
 };
 void launch_dwconv_tm(const DwTmLaunch& a, cudaStream_t s);
-
-// ---- k_probe.cu ------------------------------------------------------------------------------
-int run_probe_tcgen05(float* h_report, int n);
 
 }  // namespace fsn

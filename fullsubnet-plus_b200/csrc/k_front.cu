@@ -1,7 +1,6 @@
 // Full-band front end of the FullSubNet+/FullSubNet forward on sm_100a:
 //   * utterance Laplace norm + TSSE ("MulCA") channel attention     (K1 + K2 of SURVEY.md 2a)
-//   * TCN blocks as TF32 tensor-core 1x1 convolutions with the PReLU / gLN statistics / residual
-//     fused into their prologue and epilogue, plus the dilated depth-wise convolution            (K3)
+//   * the output Linear of fullsubnet.Model's full-band LSTM (the TCN of FullSubNet+ is in k_gemm_tc5.cu)  (K3)
 //   * utterance mean of the (never materialised) unfolded sub-band input and the fp16 packing of the
 //     per-step LSTM input tiles                                                                  (K4)
 #include "fsn_common.cuh"
@@ -245,34 +244,20 @@ void launch_input_norm(const NormLaunch& a, cudaStream_t s) {
 }
 
 // =============================================================================================
-// K3a: 1x1 convolution Y[z] = W[g] * pro(X[z]) + b as a TF32 tensor-core GEMM (mma.sync m16n8k8),
-// 64x64x32 tiles, 4 warps.  Prologue: gLN apply (statistics from the producer's epilogue) or ReLU.
-// Epilogue: PReLU + gLN statistics of the output, residual add, or output activation.
-// reference: causal_conv.py:96-108 (TCNBlock.forward), sequence_model.py:106-112.
+// Output Linear of the full-band LSTM of fullsubnet.Model (fullsubnet.py:86, sequence_model.py:118-121):
+// Y[z] = act(W * X[z] + b) on the [Z, K, P] layout as a TF32 tensor-core GEMM (mma.sync m16n8k8), 64x64x32 tiles, 4 warps.
+// (The TCN's 1x1 convolutions run on tcgen05, k_gemm_tc5.cu; this small GEMM is latency-bound: Z <= 64, K = 512, M = 257.)
 // =============================================================================================
-template <int PRO, int EPI>
 __global__ void __launch_bounds__(128) conv1x1_tf32_kernel(ConvLaunch a) {
     __shared__ uint32_t Ws[64][36];
     __shared__ uint32_t Xs[32][72];
-    __shared__ double red[8];
-    const int z = blockIdx.z, g = z / a.zper;
+    const int z = blockIdx.z;
     const int m0 = blockIdx.y * 64, t0 = blockIdx.x * 64;
     const int M = a.M, K = a.K, Tp = a.Tp, P = a.P;
-    const float* W = a.W[g];
+    const float* W = a.W;
     const float* X = a.X + (size_t)z * K * P;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 1, wn = warp & 1;
-
-    float mean = 0.f, rstd = 1.f;
-    if (PRO == PRO_GLN) {
-        double su = a.stats_in[2 * z], sq = a.stats_in[2 * z + 1];
-        double mu = su / a.count_in;
-        double var = sq / a.count_in - mu * mu;
-        mean = (float)mu;
-        rstd = (float)(1.0 / sqrt((var > 0 ? var : 0) + 1e-8));
-    }
-    const float* gam = (PRO == PRO_GLN) ? a.gamma[g] : nullptr;
-    const float* bet = (PRO == PRO_GLN) ? a.beta[g] : nullptr;
 
     float acc[2][4][4];
 #pragma unroll
@@ -292,12 +277,7 @@ __global__ void __launch_bounds__(128) conv1x1_tf32_kernel(ConvLaunch a) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             int e = tid + 128 * j, kk = e >> 6, tt = e & 63;
-            float v = 0.f;
-            if (k0 + kk < K && t0 + tt < Tp) {
-                v = X[(size_t)(k0 + kk) * P + t0 + tt];
-                if (PRO == PRO_GLN) v = fmaf((v - mean) * rstd, gam[k0 + kk], bet[k0 + kk]);
-                if (PRO == PRO_RELU) v = fmaxf(v, 0.f);
-            }
+            float v = (k0 + kk < K && t0 + tt < Tp) ? X[(size_t)(k0 + kk) * P + t0 + tt] : 0.f;
             Xs[kk][tt] = f2tf32(v);
         }
         __syncthreads();
@@ -324,10 +304,7 @@ __global__ void __launch_bounds__(128) conv1x1_tf32_kernel(ConvLaunch a) {
         __syncthreads();
     }
 
-    const float* bias = a.bias[g];
     float* Y = a.Y + (size_t)z * M * P;
-    const float slope = (EPI == EPI_PRELU_STATS) ? a.prelu[g][0] : 0.f;
-    double lsum = 0.0, lsq = 0.0;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -336,88 +313,12 @@ __global__ void __launch_bounds__(128) conv1x1_tf32_kernel(ConvLaunch a) {
             for (int q = 0; q < 4; ++q) {
                 int row = m0 + wm * 32 + mt * 16 + (lane >> 2) + ((q & 2) ? 8 : 0);
                 int col = t0 + wn * 32 + nt * 8 + 2 * (lane & 3) + (q & 1);
-                if (row < M && col < Tp) {
-                    float y = acc[mt][nt][q] + bias[row];
-                    if (EPI == EPI_PRELU_STATS) {
-                        y = (y >= 0.f) ? y : slope * y;
-                        lsum += (double)y; lsq += (double)y * (double)y;
-                    }
-                    if (EPI == EPI_RESIDUAL) y += a.R[(size_t)z * M * P + (size_t)row * P + col];
-                    if (EPI == EPI_ACT) {
-                        if (a.act == FSN_ACT_RELU) y = fmaxf(y, 0.f);
-                        else if (a.act == FSN_ACT_TANH) y = tanhf(y);
-                        else if (a.act == FSN_ACT_RELU6) y = fminf(fmaxf(y, 0.f), 6.f);
-                    }
-                    Y[(size_t)row * P + col] = y;
-                }
+                if (row < M && col < Tp) Y[(size_t)row * P + col] = apply_act(acc[mt][nt][q] + a.bias[row], a.act);
             }
-    if (EPI == EPI_PRELU_STATS) {
-        lsum = warp_sum_d(lsum); lsq = warp_sum_d(lsq);
-        if (lane == 0) { red[warp] = lsum; red[4 + warp] = lsq; }
-        __syncthreads();
-        if (tid == 0) {
-            atomicAdd(&a.stats_out[2 * z], red[0] + red[1] + red[2] + red[3]);
-            atomicAdd(&a.stats_out[2 * z + 1], red[4] + red[5] + red[6] + red[7]);
-        }
-    }
 }
 
 void launch_conv1x1(const ConvLaunch& a, cudaStream_t s) {
-    dim3 grid((a.Tp + 63) / 64, (a.M + 63) / 64, a.Z), block(128);
-#define FSN_CONV_CASE(P_, E_) \
-    if (a.pro == P_ && a.epi == E_) { conv1x1_tf32_kernel<P_, E_><<<grid, block, 0, s>>>(a); return; }
-    FSN_CONV_CASE(PRO_NONE, EPI_PRELU_STATS)
-    FSN_CONV_CASE(PRO_GLN, EPI_RESIDUAL)
-    FSN_CONV_CASE(PRO_RELU, EPI_ACT)
-    FSN_CONV_CASE(PRO_NONE, EPI_ACT)
-    FSN_CONV_CASE(PRO_NONE, EPI_NONE)
-#undef FSN_CONV_CASE
-}
-
-// =============================================================================================
-// K3b: gLN1 apply -> depth-wise conv (k=3, dilation d, zero padding d in the normalised domain)
-//      -> PReLU2, accumulating the gLN2 statistics.  reference: causal_conv.py:100-106.
-// =============================================================================================
-__global__ void __launch_bounds__(256) dwconv_kernel(DwLaunch a) {
-    __shared__ double red[16];
-    const int z = blockIdx.z, g = z / a.zper;
-    const int C = a.C, Tp = a.Tp, P = a.P, d = a.dilation;
-    const double cnt = (double)C * (double)Tp;
-    const double mu = a.stats_in[2 * z] / cnt;
-    const double var = a.stats_in[2 * z + 1] / cnt - mu * mu;
-    const float mean = (float)mu, rstd = (float)(1.0 / sqrt((var > 0 ? var : 0) + 1e-8));
-    const float slope = a.prelu[g][0];
-    const int c0 = blockIdx.x * 8;
-    double lsum = 0.0, lsq = 0.0;
-    for (int e = threadIdx.x; e < 8 * Tp; e += blockDim.x) {
-        const int c = c0 + e / Tp, t = e % Tp;
-        if (c >= C) break;
-        const float* xr = a.X + ((size_t)z * C + c) * P;
-        const float ga = a.gamma[g][c] * rstd, be = a.beta[g][c] - mean * rstd * a.gamma[g][c];
-        float acc = a.b[g][c];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            int tt = t + (j - 1) * d;
-            if (tt >= 0 && tt < Tp) acc = fmaf(a.w[g][c * 3 + j], fmaf(xr[tt], ga, be), acc);
-        }
-        acc = (acc >= 0.f) ? acc : slope * acc;
-        a.Y[((size_t)z * C + c) * P + t] = acc;
-        lsum += (double)acc; lsq += (double)acc * (double)acc;
-    }
-    lsum = warp_sum_d(lsum); lsq = warp_sum_d(lsq);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { red[warp] = lsum; red[8 + warp] = lsq; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s1 = 0, s2 = 0;
-        for (int i = 0; i < 8; ++i) { s1 += red[i]; s2 += red[8 + i]; }
-        atomicAdd(&a.stats_out[2 * z], s1);
-        atomicAdd(&a.stats_out[2 * z + 1], s2);
-    }
-}
-
-void launch_dwconv(const DwLaunch& a, cudaStream_t s) {
-    dwconv_kernel<<<dim3((a.C + 7) / 8, 1, a.Z), 256, 0, s>>>(a);
+    conv1x1_tf32_kernel<<<dim3((a.Tp + 63) / 64, (a.M + 63) / 64, a.Z), 128, 0, s>>>(a);
 }
 
 // =============================================================================================

@@ -1,6 +1,5 @@
-// CTA-pair persistent tcgen05 LSTM with DOUBLE-BUFFERED accumulators (the default sub-band kernel; k_lstm_tc5p.cu is the
-// single-accumulator pair kernel it grew out of, k_lstm_tc5.cu the single-CTA design; reference: sequence_model.py:113-122,
-// fullsubnet_plus.py:205-208).
+// CTA-pair persistent tcgen05 LSTM with DOUBLE-BUFFERED accumulators: the sub-band kernel (its single-CTA and
+// single-accumulator predecessors live in the git history only).  reference: sequence_model.py:113-122, fullsubnet_plus.py:205-208.
 //
 // Why: TMEM is full (h0 192 + h1 192 + one 128-column accumulator = 512 columns), so the pair kernel serialises
 // "MMA chunk j -> drain chunk j -> MMA chunk j+1": ncu shows the tensor pipe 77 % active, the rest is 24 drain bubbles of
@@ -19,6 +18,8 @@
 #include "fsn_kernels.h"
 #include "../../include/fsnplus_b200.h"
 
+#include <cstring>
+
 namespace fsn {
 
 constexpr int D5_KB = 8192;         // one k-block of my half-tile in the packed stream: 64 of the 128 gate columns x 64 k x fp16
@@ -31,6 +32,9 @@ constexpr int D5_THREADS = (D5_EPI_WARPS + 2) * 32;
 constexpr int D5_MAX_SMEM = 227 * 1024;
 
 struct D5Plan { int nstage; size_t total; };
+bool lstm_tc5_supported(int L, int H, int I, int O) { return L == 2 && H % 64 == 0 && H >= 64 && H <= 384 && I <= 64 && O == 2; }
+size_t lstm_tc5_cstate_bytes(int ntiles, int H) { return (size_t)ntiles * 2 * H * 128 * sizeof(float); }
+
 static inline D5Plan d5_plan(int H) {
     D5Plan p;
     const size_t fixed = D5_XIMG + (size_t)128 * H * 2 /*park*/ + (size_t)2 * 4 * H * 4 /*pre-scaled biases*/ + 4 * 128 * 2 * 4 + 64 * 8;
@@ -172,7 +176,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                     for (int j = 0; j < NCH; ++j) {
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
-                            if (!(a.debug & 2)) mbar_wait(&accempty[half], (accuse & 1) ^ 1);
+                            mbar_wait(&accempty[half], (accuse & 1) ^ 1);
                             tc5_fence_after();
                             d = tmem + acc_col + 64 * half;
 #pragma unroll
@@ -282,7 +286,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                         else { cnext[0] = np[0]; cnext[1] = np[128]; }
                     }
 
-                    if (a.debug & 1) continue;                     // timing experiment: drain only, no cell update
                     const float L2E = 1.4426950408889634f;
                     uint32_t hp[4];
                     float cn[8];
@@ -338,8 +341,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                     if (cg == 0 && t >= a.la && grow < a.rows) {
                         const float o0 = fc0 + fcpart[(128 + r) * 2] + fcpart[(256 + r) * 2] + fcpart[(384 + r) * 2] + fcb0;
                         const float o1 = fc1 + fcpart[(128 + r) * 2 + 1] + fcpart[(256 + r) * 2 + 1] + fcpart[(384 + r) * 2 + 1] + fcb1;
-                        __stcs(&a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)], o0);   // streaming stores: written once
-                        __stcs(&a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)], o1);
+                        __stcs(&a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)], apply_act(o0, a.act));   // streaming stores: written once
+                        __stcs(&a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)], apply_act(o1, a.act));
                     }
                     asm volatile("bar.sync 2, 512;" ::: "memory");
                 }
@@ -356,7 +359,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
 int launch_lstm_tc5_dbuf(const LstmTc5Launch& a, cudaStream_t s) {
     if (!lstm_tc5_supported(2, a.H, a.I, 2)) return (int)cudaErrorInvalidValue;
     D5Plan p = d5_plan(a.H);
-    if (a.nstage_cap > 0 && a.nstage_cap < p.nstage) { p.total -= (size_t)(p.nstage - a.nstage_cap) * D5_STAGE; p.nstage = a.nstage_cap; }
     if (p.nstage < 2) return (int)cudaErrorInvalidValue;
     const int grid = (a.ntiles + 1) / 2 * 2;                        // whole pairs; the buffers cover the padded tile
     cudaError_t e = cudaErrorInvalidValue;
@@ -379,3 +381,54 @@ int launch_lstm_tc5_dbuf(const LstmTc5Launch& a, cudaStream_t s) {
 }
 
 }  // namespace fsn
+
+// ---------------------------------------------------------------------------------------------
+// Host-side packing of the weight stream (exposed through the C ABI for CPU layout tests).
+// Stream order per time step: layer 0, chunk j = 0..H/32-1: [x block][H/64 hidden blocks];
+//                             layer 1, chunk j:              [H/64 blocks of W_ih1][H/64 blocks of W_hh1].
+// Stage = 128 gate columns (fsn_tc5_gate_row) x 64 k, K-major, SWIZZLE_128B.
+// ---------------------------------------------------------------------------------------------
+static inline uint16_t d5_h_bits(float f) {
+    __half h = __float2half_rn(f);
+    uint16_t b;
+    std::memcpy(&b, &h, 2);
+    return b;
+}
+
+extern "C" int64_t fsn_tc5_weight_stream_bytes(int32_t I, int32_t H) {
+    if (H % 64 || I > 64) return -1;
+    const int NCH = H / 32, KBH = H / 64;
+    return (int64_t)(NCH * (1 + KBH) + NCH * 2 * KBH) * fsn::D5_STAGE_FULL;
+}
+
+// Gate column n (0..127) of chunk j <-> weight row: n = cg*32 + q*8 + u, q in (i,f,g,o), hidden unit 32 j + 8 cg + u.
+extern "C" int32_t fsn_tc5_gate_row(int32_t H, int32_t j, int32_t n) { return ((n % 32) / 8) * H + 32 * j + 8 * (n / 32) + (n % 8); }
+
+extern "C" int fsn_tc5_pack_weights(int32_t I, int32_t H, const float* w_ih0, const float* w_hh0, const float* w_ih1,
+                                    const float* w_hh1, uint16_t* dst) {
+    if (H % 64 || I > 64) return FSN_EINVAL;
+    const int NCH = H / 32, KBH = H / 64;
+    size_t s = 0;
+    auto stage = [&](auto&& getw) {
+        uint8_t* img = reinterpret_cast<uint8_t*>(dst) + s * fsn::D5_STAGE_FULL;
+        for (int n = 0; n < 128; ++n)
+            for (int k = 0; k < 64; ++k) {
+                uint16_t b = d5_h_bits(getw(n, k));
+                std::memcpy(img + fsn::sw128_offset(n, k), &b, 2);
+            }
+        ++s;
+    };
+    for (int j = 0; j < NCH; ++j) {
+        auto row = [&](int n) { return fsn_tc5_gate_row(H, j, n); };
+        stage([&](int n, int k) { return k < I ? w_ih0[(size_t)row(n) * I + k] : 0.f; });
+        for (int kb = 0; kb < KBH; ++kb) stage([&](int n, int k) { return w_hh0[(size_t)row(n) * H + kb * 64 + k]; });
+    }
+    for (int j = 0; j < NCH; ++j) {
+        auto row = [&](int n) { return fsn_tc5_gate_row(H, j, n); };
+        for (int kb = 0; kb < KBH; ++kb) stage([&](int n, int k) { return w_ih1[(size_t)row(n) * H + kb * 64 + k]; });
+        for (int kb = 0; kb < KBH; ++kb) stage([&](int n, int k) { return w_hh1[(size_t)row(n) * H + kb * 64 + k]; });
+    }
+    return FSN_OK;
+}
+
+extern "C" uint32_t fsn_sw128_offset(uint32_t row, uint32_t k) { return fsn::sw128_offset(row, k); }

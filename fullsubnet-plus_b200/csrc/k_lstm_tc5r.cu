@@ -122,7 +122,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
                 for (int j = 0; j < NCH; ++j) {
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        if (!(a.debug & 2)) mbar_wait(&accempty[half], (accuse & 1) ^ 1);
+                        mbar_wait(&accempty[half], (accuse & 1) ^ 1);
                         tc5_fence_after();
                         d = tmem + acc_col + 64 * half;
 #pragma unroll
@@ -280,8 +280,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
                 if (cg == 0 && t >= a.la && grow < a.rows) {
                     const float o0 = fc0 + fcpart[(128 + r) * 2] + fcpart[(256 + r) * 2] + fcpart[(384 + r) * 2] + fcb0;
                     const float o1 = fc1 + fcpart[(128 + r) * 2 + 1] + fcpart[(256 + r) * 2 + 1] + fcpart[(384 + r) * 2 + 1] + fcb1;
-                    a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)] = o0;
-                    a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)] = o1;
+                    a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)] = apply_act(o0, a.act);
+                    a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)] = apply_act(o1, a.act);
                 }
                 asm volatile("bar.sync 2, 512;" ::: "memory");
             }

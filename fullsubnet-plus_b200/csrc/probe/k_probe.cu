@@ -2,9 +2,9 @@
 // LSTM kernel relies on (SS and TS tcgen05.mma with SWIZZLE_128B K-major tiles staged by cp.async.bulk,
 // tcgen05.st as the A-operand writer, tcgen05.ld 32x32b as the accumulator reader, tcgen05.commit ->
 // mbarrier), checked against a host computation, plus issue-rate measurements of the four MMA shapes the
-// design discussion in DESIGN.md quotes.  Exposed as fsn_probe_tcgen05() and run by tests/test_gpu_probe.py.
-#include "fsn_common.cuh"
-#include "fsn_kernels.h"
+// design discussion in DESIGN.md quotes.  TEST-ONLY target: built into tests/libfsn_probe.so (not the product library),
+// exposed as fsn_probe_tcgen05() and run by tests/test_gpu_probe.py.
+#include "../fsn_common.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -332,7 +332,7 @@ static float h_val(uint16_t b) { __half h; std::memcpy(&h, &b, 2); return __half
 
 #define PROBE_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = -(int)e_ - 1000; goto done; } } while (0)
 
-int run_probe_tcgen05(float* report, int n) {
+static int run_probe_tcgen05(float* report, int n) {
     if (n < 40) return -1;
     int rc = 0;
     std::vector<uint16_t> A(128 * 64), B(256 * 64);
@@ -507,3 +507,10 @@ done:
 }
 
 }  // namespace fsn
+
+// writes max-abs-errors / cycle counts into h_report[0..n); returns the number of entries written or < 0
+extern "C" int fsn_probe_tcgen05(float* h_report, int32_t n) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -1;
+    return fsn::run_probe_tcgen05(h_report, n);
+}

@@ -140,6 +140,7 @@ class _B200Model(nn.Module):
         self._handle = None
         self._handle_device = None
         self._pushed_version = None
+        self._inflight, self._inflight_host = [], []
 
     # -- handle management ---------------------------------------------------------------------
     def _param_version(self):
@@ -202,27 +203,88 @@ class _B200Model(nn.Module):
             _lib.check(lib.fsn_model_forward(self._handle, ptr(ins[0]), ptr(ins[1]), ptr(ins[2]), B, T, ptr(out), stream))
         return out
 
+    def submit(self, mag, real=None, imag=None, out=None):
+        """Pipelined forward for STREAMS of batches (C ABI: fsn_model_submit): same inputs as forward(), returns the output tensor
+        immediately; it is valid on the current stream after ``wait()``.  The full-band front end of this batch runs while the
+        sub-band LSTM of the previously submitted batch is still running (two internal streams, two workspace lanes).  The inputs
+        must not be modified before ``wait()``; references to them are held until then."""
+        assert mag.dim() == 4
+        B, Cn, F, T = mag.shape
+        assert Cn == 1
+        if self.training:
+            raise NotImplementedError("fsnplus_b200 implements the inference (eval) forward only; call .eval()")
+        if not mag.is_cuda:
+            raise RuntimeError("fsnplus_b200 has no CPU fallback: move the model and its inputs to a B200 (cuda) device")
+        if F != self._cfg.num_freqs:
+            raise ValueError(f"expected {self._cfg.num_freqs} frequency bins, got {F}")
+        ins = [x.detach().to(dtype=torch.float32).contiguous() if x is not None else None for x in (mag, real, imag)]
+        with torch.cuda.device(mag.device):
+            lib = self._ensure_handle(mag.device)
+            if out is None:
+                out = torch.empty((B, self._cfg.output_size, F, T), dtype=torch.float32, device=mag.device)
+            ptr = lambda x: C.c_void_p(x.data_ptr()) if x is not None else C.c_void_p()
+            stream = C.c_void_p(torch.cuda.current_stream(mag.device).cuda_stream)
+            _lib.check(lib.fsn_model_submit(self._handle, ptr(ins[0]), ptr(ins[1]), ptr(ins[2]), B, T, ptr(out), stream))
+        self._inflight.append((ins, out))
+        return out
+
+    def wait(self):
+        """Make the current stream wait for every ``submit()`` issued so far (does not block the host)."""
+        if self._handle is not None:
+            with torch.cuda.device(self._handle_device):
+                stream = C.c_void_p(torch.cuda.current_stream(self._handle_device).cuda_stream)
+                _lib.check(_lib.load_library().fsn_model_wait(self._handle, stream))
+                # the tensors may now be freed: torch's caching allocator orders reuse on the current stream, which waits for them
+                for ins, out in self._inflight:
+                    for t in ins + [out]:
+                        if t is not None and t.is_cuda:
+                            t.record_stream(torch.cuda.current_stream(self._handle_device))
+        self._inflight = []
+
+    @staticmethod
+    def _check_host(name, t, shape):
+        if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+            raise ValueError(f"forward_host: {name} must be a contiguous CPU float32 tensor of shape {tuple(shape)}, got "
+                             f"{type(t).__name__} {getattr(t, 'device', '')} {getattr(t, 'dtype', '')} {tuple(getattr(t, 'shape', ()))}")
+
     def forward_host(self, mag, real=None, imag=None, out=None, device="cuda:0", pipelined=False):
         """Same forward through the HOST-buffer entry point of the C ABI (H2D + forward + D2H in one call).
         ``mag/real/imag``: CPU float32 tensors [B, 1, F, T] (pinned for best bandwidth); returns a CPU tensor.
-        ``pipelined=True`` uses the double-buffered async entry point (copies overlap the previous/next forward);
-        the returned tensor is valid after ``sync_host()``."""
+        ``pipelined=True`` uses the double-buffered async entry point (copies and the front end of the next batch overlap the
+        sub-band LSTM of the previous one); it needs PINNED buffers, the returned tensor is valid after ``sync_host()`` and the
+        inputs/outputs are kept referenced until then."""
+        if mag.dim() != 4:
+            raise ValueError("forward_host: mag must be [B, 1, F, T]")
         B, _, F, T = mag.shape
+        shape = (B, 1, self._cfg.num_freqs, T)
+        self._check_host("mag", mag, shape)
+        if self._kind == _lib.KIND_PLUS:
+            self._check_host("real", real, shape)
+            self._check_host("imag", imag, shape)
+        else:
+            real = imag = None
+        if out is None:
+            out = torch.empty((B, self._cfg.output_size, F, T), dtype=torch.float32).pin_memory()
+        self._check_host("out", out, (B, self._cfg.output_size, F, T))
+        if pipelined and not all(t.is_pinned() for t in (mag, real, imag, out) if t is not None):
+            raise ValueError("forward_host(pipelined=True) needs pinned host tensors (the copies are asynchronous)")
         dev = torch.device(device)
         with torch.cuda.device(dev):
             lib = self._ensure_handle(dev)
-            if out is None:
-                out = torch.empty((B, self._cfg.output_size, F, T), dtype=torch.float32).pin_memory()
             ptr = lambda x: C.c_void_p(x.data_ptr()) if x is not None else C.c_void_p()
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             fn = lib.fsn_model_forward_host_async if pipelined else lib.fsn_model_forward_host
             _lib.check(fn(self._handle, ptr(mag), ptr(real), ptr(imag), B, T, ptr(out), stream))
+        if pipelined:
+            self._inflight_host.append((mag, real, imag, out))     # the async copies read / write these after the call returns
         return out
 
     def sync_host(self):
-        """Wait for every forward_host(..., pipelined=True) issued so far (their outputs are then valid)."""
+        """Wait for every forward_host(..., pipelined=True) / submit() issued so far (their outputs are then valid)."""
         if self._handle is not None:
             _lib.check(_lib.load_library().fsn_model_sync_host(self._handle))
+        self._inflight_host = []
+        self._inflight = []
 
     # -- introspection used by tests / bench -----------------------------------------------------
     def last_lstm_impl(self):

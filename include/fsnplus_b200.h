@@ -113,10 +113,23 @@ int fsn_model_forward(fsn_model* m, const float* d_mag, const float* d_real, con
 int fsn_model_forward_host(fsn_model* m, const float* h_mag, const float* h_real, const float* h_imag, int32_t B, int32_t T,
                            float* h_out, void* stream);
 
-/* Pipelined variant for streams of batches: returns as soon as the work is enqueued.  Inputs are copied on an internal
- * copy stream into one of two device staging slots, the forward runs on `stream`, the mask is copied back on a second
- * copy stream -- so the H2D of batch i+1 and the D2H of batch i-1 overlap the forward of batch i.  The host buffers must be
- * pinned and must stay untouched (h_out unread) until fsn_model_sync_host() returns. */
+/* Pipelined variants for STREAMS OF BATCHES (the reference's inferencer loop, base_inferencer.py:133-160, issues one forward
+ * after the other; the outputs of a batch are only needed when its files are written).  The forward is split at the one point
+ * where it changes character: the full-band front end (norm, attention, TCN / full-band LSTM, sub-band statistics + packing) is
+ * bandwidth/latency-bound and occupies the whole GPU for a short time, the sub-band LSTM is tensor-bound and occupies 130 of the
+ * 148 SMs for a long time.  Both entry points run the front end of batch i+1 on an internal stream, into the second of two
+ * workspace lanes, WHILE the sub-band LSTM of batch i runs on another internal stream: the front end fills the idle SMs.
+ *
+ * fsn_model_submit: device buffers.  The inputs must be complete in `stream` order at the time of the call and stay untouched,
+ * d_out unread, until fsn_model_wait(m, stream) has been called (it makes `stream` wait for every submitted batch; it does not
+ * block the host) or fsn_model_sync_host(m) has returned.  A plain fsn_model_forward on any stream first waits for the pipeline.
+ *
+ * fsn_model_forward_host_async: pinned host buffers; additionally the H2D copy of batch i+1 and the D2H copy of batch i-1
+ * overlap on two copy streams.  `stream` is ignored (host memory carries no stream order).  The host buffers must stay
+ * untouched (h_out unread) until fsn_model_sync_host() returns. */
+int fsn_model_submit(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                     float* d_out, void* stream);
+int fsn_model_wait(fsn_model* m, void* stream);
 int fsn_model_forward_host_async(fsn_model* m, const float* h_mag, const float* h_real, const float* h_imag, int32_t B, int32_t T,
                                  float* h_out, void* stream);
 int fsn_model_sync_host(fsn_model* m);
@@ -167,11 +180,6 @@ int fsn_tc5_pack_weights(int32_t input_size, int32_t hidden, const float* w_ih0,
 int64_t fsn_tc5r_weight_stream_bytes(int32_t hidden);
 int fsn_tc5r_pack_layer(int32_t hidden, int32_t k_in, int32_t k_pad, const float* w_ih, const float* w_hh, const float* b_ih,
                         const float* b_hh, int32_t gru, uint16_t* h_stream, uint16_t* h_wih, float* h_bias);
-
-/* tcgen05 / TMEM / bulk-copy self-test used by the GPU test-suite (tests/test_gpu_probe.py):
- * runs tiny single-CTA GEMMs through every instruction form the persistent kernel relies on and
- * writes max-abs-errors into h_report[0..n).  Returns the number of entries written or < 0. */
-int fsn_probe_tcgen05(float* h_report, int32_t n);
 
 #ifdef __cplusplus
 }

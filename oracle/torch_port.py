@@ -27,9 +27,25 @@ class TorchPort:
                                if k.startswith(pre + ".sequence_model.")})
             self.lstm[pre] = m.eval()
 
-    @staticmethod
-    def norm(x):                                    # base_model.py:210-225
-        return x / (x.mean(dim=(1, 2, 3), keepdim=True) + 1e-5)
+    def norm(self, x):                              # base_model.py:318-330 (norm_wrapper) on [B, C, F, T]
+        kind = self.cfg.get("norm_type", "offline_laplace_norm")
+        if kind == "offline_laplace_norm":          # :210-225
+            return x / (x.mean(dim=(1, 2, 3), keepdim=True) + 1e-5)
+        if kind == "offline_gaussian_norm":         # :260-275
+            return (x - x.mean(dim=(1, 2, 3), keepdim=True)) / (x.std(dim=(1, 2, 3), keepdim=True) + 1e-5)
+        B, C, Fq, T = x.shape
+        eps = torch.finfo(torch.float32).eps        # audio_zen/constant.py:8
+        xr = x.reshape(B * C, Fq, T)
+        cnt = torch.arange(Fq, Fq * T + 1, Fq, dtype=x.dtype).reshape(1, T)
+        csum = torch.cumsum(xr.sum(dim=1), dim=-1)
+        cmean = csum / cnt
+        if kind == "cumulative_laplace_norm":       # :227-258
+            return (xr / (cmean.reshape(B * C, 1, T) + eps)).reshape(B, C, Fq, T)
+        if kind == "cumulative_layer_norm":         # :277-316
+            cpow = torch.cumsum((xr * xr).sum(dim=1), dim=-1)
+            cstd = torch.sqrt((cpow - 2 * cmean * csum) / cnt + cmean ** 2 + eps)
+            return ((xr - cmean[:, None, :]) / cstd[:, None, :]).reshape(B, C, Fq, T)
+        raise NotImplementedError(kind)
 
     @staticmethod
     def unfold(x, n):                               # base_model.py:15-47

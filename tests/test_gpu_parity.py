@@ -376,10 +376,10 @@ def test_config4_causal_fullsubnet_long_clip(built_lib):
     assert not torch.equal(a[..., t0:], b[..., t0:])
 
 
-def test_config5_large_model(built_lib, monkeypatch):
+def test_config5_large_model(built_lib):
     """BASELINE config #5 geometry: num_freqs=513 (n_fft=1024, hop 512 -> T=94 for 3 s), sub-band hidden 512, 3-layer
     LSTMs (additive num_layers knob; oracle = SequenceModel(num_layers=3) semantics, pinned by tests/golden/lstm3_small).
-    Default = layer-wise tcgen05 path (k_lstm_tc5r.cu); FSN_TC5R=0 = generic mma.sync kernel."""
+    Default = layer-wise tcgen05 path (k_lstm_tc5r.cu); lstm_impl="mma" = generic mma.sync kernel."""
     cfg = O.default_plus_config()
     cfg.update(num_freqs=513, sb_model_hidden_size=512, fb_model_hidden_size=512)
     params = O.make_params_plus(cfg, seed=31, num_layers=3)
@@ -394,7 +394,7 @@ def test_config5_large_model(built_lib, monkeypatch):
     print(f"\n[config5 large, {m.last_lstm_impl()}] cIRM rel-L2 {err:.3e}")
     assert m.last_lstm_impl() == "tcgen05"
     assert out.shape == (1, 2, 513, 94) and err < MASK_TOL
-    monkeypatch.setenv("FSN_TC5R", "0")                           # the generic kernel stays reachable
+    m = build_plus(cfg, params, num_layers=3, lstm_impl="mma")     # the generic kernel stays reachable
     with torch.no_grad():
         out_mma = m(_t(mag), _t(real), _t(imag))
     assert m.last_lstm_impl() == "mma"
@@ -526,11 +526,10 @@ def test_command_line_tool_matches_reference_pipeline(built_lib, golden, tmp_pat
 
 
 @pytest.mark.parametrize("L,H,rnn", [(1, 64, "LSTM"), (3, 64, "LSTM"), (3, 128, "GRU"), (4, 64, "LSTM"), (3, 192, "LSTM"), (1, 448, "LSTM")])
-def test_layerwise_tcgen05_vs_oracle(built_lib, monkeypatch, L, H, rnn):
+def test_layerwise_tcgen05_vs_oracle(built_lib, L, H, rnn):
     """Layer-wise tcgen05 path (k_lstm_tc5r.cu: one cuBLAS input-projection GEMM + one recurrent launch per layer) for stacks
-    outside the fused kernel's envelope (default for hidden % 64 == 0, <= 512; FSN_TC5R=0 disables).  First / middle / last layer roles, LSTM and GRU cells,
+    outside the fused kernel's envelope (default for hidden % 64 == 0, <= 512).  First / middle / last layer roles, LSTM and GRU cells,
     more than one CTA pair (B*F = 5*33 = 165 rows -> 2 tiles) and a half-empty last tile."""
-    monkeypatch.setenv("FSN_TC5R", "1")
     cfg = dict(small_cfg(H), sequence_model=rnn)
     params = O.make_params_plus(cfg, seed=40 + L, num_layers=L, lstm_scale=2.0)
     mag, real, imag = small_inputs(5, 33, 26, 12)

@@ -7,9 +7,12 @@ pytestmark = pytest.mark.gpu
 
 
 def test_tcgen05_probe(built_lib):
+    import os
+    probe = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfsn_probe.so"))   # test-only target, built by build()
+    probe.fsn_probe_tcgen05.argtypes = [C.POINTER(C.c_float), C.c_int32]
     rep = (C.c_float * 48)()
-    n = built_lib.fsn_probe_tcgen05(rep, 48)
-    assert n == 43, built_lib.fsn_last_error()
+    n = probe.fsn_probe_tcgen05(rep, 48)
+    assert n == 43, n
     err_ss, err_ts, err_mix = list(rep)[:3]
     labels = [f"N{N}/{'TS' if ts else 'SS'}/acc{a}" for N in (64, 128, 192, 256) for ts in (1, 0) for a in (1, 2) if not (a == 2 and N > 128)]
     print(f"\nprobe: err ss={err_ss:.2e} ts={err_ts:.2e} mix={err_mix:.2e}")

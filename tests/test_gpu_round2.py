@@ -1,0 +1,282 @@
+"""GPU parity tests added in round 2 (all run through the C ABI via the Python mirror of the reference API).
+
+  * the three tests that were collected last and marked xfail-until-run in round 1 (they XPASSed on the driver's B200): now plain;
+  * sb_output_activate_function on every sub-band kernel (reference sequence_model.py:84-93,120-121);
+  * BASELINE config #4 at its stated size: 30 s clip (T = 1876), fullsubnet.Model + cumulative_laplace_norm, normal and x3 weights,
+    truth = float64 torch port (pinned to the reference goldens for every norm_type, tests/test_oracle_golden.py);
+  * the streaming step API at the DEFAULT geometry (F = 257, H = 512 / 384: weight-stationary full-band kernel + generic step kernel);
+  * 64 DISTINCT clips in one batch against the per-clip CPU port;
+  * the pipelined entry points (fsn_model_submit / _wait, forward_host pipelined): batches in flight, results identical to forward().
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fsn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+MASK_TOL = 1e-3
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+def _small(H):
+    c = O.default_plus_config()
+    c.update(num_freqs=33, sb_num_neighbors=3, sb_model_hidden_size=H)
+    return c
+
+
+def _plus(cfg, params, **kw):
+    from fsnplus_b200.model import FullSubNet_Plus
+    m = FullSubNet_Plus(**cfg, **kw)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    return m.to(DEV).eval()
+
+
+def _fsn(cfg, params, **kw):
+    from fsnplus_b200.model import Model
+    m = Model(**cfg, **kw)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    return m.to(DEV).eval()
+
+
+def _inputs(B, F, T, seed):
+    rng = np.random.default_rng(seed)
+    real = rng.standard_normal((B, 1, F, T)) * 0.05 + 0.004
+    imag = rng.standard_normal((B, 1, F, T)) * 0.05 - 0.003
+    mag = np.sqrt(real ** 2 + imag ** 2)
+    return mag.astype(np.float32), real.astype(np.float32), imag.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# formerly tests/test_gpu_zz_pending.py
+# ---------------------------------------------------------------------------------------------------------------------
+def test_plus_fb_num_neighbors_golden(built_lib, golden):
+    """fb_num_neighbors > 0: the full-band outputs are unfolded like the sub-band window (fullsubnet_plus.py:167-179)."""
+    gi, g = golden("plus_small"), golden("plus_small_fbn1")
+    cfg = dict(_small(32), fb_num_neighbors=1)
+    m = _plus(cfg, O.make_params_plus(cfg, seed=6))
+    with torch.no_grad():
+        out = m(_t(gi["mag"]), _t(gi["real"]), _t(gi["imag"]))
+    err = O.rel_l2(out.cpu().numpy(), g["out"])
+    print(f"\n[FullSubNet+ fb_num_neighbors=1] cIRM {err:.3e}")
+    assert err < MASK_TOL
+
+
+def test_fsn_fb_num_neighbors_golden(built_lib, golden):
+    gi, g = golden("plus_small"), golden("fsn_small_fbn2")
+    cfg = O.default_fsn_config()
+    cfg.update(num_freqs=33, sb_num_neighbors=3, sb_model_hidden_size=32, fb_model_hidden_size=48, fb_num_neighbors=2)
+    m = _fsn(cfg, O.make_params_fsn(cfg, seed=6))
+    with torch.no_grad():
+        out = m(_t(gi["mag"]))
+    err = O.rel_l2(out.cpu().numpy(), g["out"])
+    print(f"\n[fullsubnet.Model fb_num_neighbors=2] cIRM {err:.3e}")
+    assert err < MASK_TOL
+
+
+def test_layerwise_path_under_fullsubnet_model_with_cumulative_norm(built_lib):
+    """Layer-wise tcgen05 path (k_lstm_tc5r.cu) fed by the cumulative packer's unswizzled store."""
+    cfg = O.default_fsn_config()
+    cfg.update(num_freqs=33, sb_num_neighbors=3, sb_model_hidden_size=64, fb_model_hidden_size=48, norm_type="cumulative_laplace_norm")
+    params = O.make_params_fsn(cfg, seed=23, num_layers=3)
+    rng = np.random.default_rng(4)
+    mag = np.abs(rng.standard_normal((5, 1, 33, 24)) * 0.05 + 0.01).astype(np.float32)
+    ref = O.fullsubnet_forward(params, cfg, mag, num_layers=3)
+    m = _fsn(cfg, params, num_layers=3)
+    with torch.no_grad():
+        out = m(_t(mag))
+    assert m.last_lstm_impl() == "tcgen05"
+    err = O.rel_l2(out.cpu().numpy(), ref)
+    print(f"\n[fullsubnet.Model, 3 x 64 sub-band, cumulative_laplace_norm, layer-wise tcgen05] cIRM {err:.3e}")
+    assert err < MASK_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sb_output_activate_function on every sub-band kernel
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("act", ["Tanh", "ReLU", "ReLU6"])
+@pytest.mark.parametrize("path", ["fused", "layerwise", "mma"])
+def test_sb_output_activation(built_lib, act, path):
+    """The reference applies sb_output_activate_function to the Linear output (sequence_model.py:120-121); the shipped configs use
+    false, so round 1's tcgen05 epilogues silently skipped it.  Fused two-layer kernel (H = 64), layer-wise kernel (3 layers) and
+    the generic mma.sync kernel (H = 32) against the oracle."""
+    H, L, impl = {"fused": (64, 2, "tcgen05"), "layerwise": (64, 3, "tcgen05"), "mma": (32, 2, "mma")}[path]
+    cfg = dict(_small(H), sb_output_activate_function=act)
+    params = O.make_params_plus(cfg, seed=50, num_layers=L, lstm_scale=2.0)
+    params["sb_model.fc_output_layer.weight"] = params["sb_model.fc_output_layer.weight"] * 4.0     # outputs on both sides of 0 and beyond 1
+    mag, real, imag = _inputs(3, 33, 19, 21)
+    ref = O.fullsubnet_plus_forward(params, cfg, mag, real, imag, num_layers=L)
+    plain = O.fullsubnet_plus_forward(params, dict(cfg, sb_output_activate_function=False), mag, real, imag, num_layers=L)
+    assert O.rel_l2(plain, ref) > 0.05                                   # the activation matters on this fixture
+    m = _plus(cfg, params, num_layers=L, lstm_impl=impl)
+    with torch.no_grad():
+        out = m(_t(mag), _t(real), _t(imag))
+    assert m.last_lstm_impl() == impl
+    err = O.rel_l2(out.cpu().numpy(), ref)
+    print(f"\n[sb_act={act} {path}] cIRM {err:.3e}")
+    assert err < MASK_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config #4 at its stated size
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scale", [1.0, 3.0])
+def test_config4_30s_clip_parity(built_lib, scale):
+    """fullsubnet.Model + cumulative_laplace_norm, look_ahead 2, one 30 s clip (T = 1876), against the float64 CPU port; scale 3
+    multiplies every LSTM weight by 3 (saturated gates, like a trained network) -- the long-clip worst case for fp16 h
+    re-quantisation.  Also reports the error of the last second alone (drift would show there)."""
+    from oracle.torch_port import TorchPort
+    cfg = O.default_fsn_config()
+    cfg["norm_type"] = "cumulative_laplace_norm"
+    params = O.make_params_fsn(cfg, seed=21, lstm_scale=scale)
+    mag = np.abs(O.stft(O.synth_clips(1, num_samples=480000, seed0=78)))[:, None].astype(np.float32)
+    assert mag.shape == (1, 1, 257, 1876)
+    ref = TorchPort(params, cfg, "fsn", dtype=torch.float64).forward(torch.from_numpy(mag)).numpy()
+    m = _fsn(cfg, params)
+    with torch.no_grad():
+        out = m(_t(mag)).cpu().numpy()
+    err, tail = O.rel_l2(out, ref), O.rel_l2(out[..., -63:], ref[..., -63:])
+    print(f"\n[config4 30 s, lstm x{scale}] cIRM rel-L2 {err:.3e} (last second {tail:.3e})")
+    assert np.isfinite(out).all()
+    assert err < MASK_TOL and tail < 2 * MASK_TOL
+
+
+def test_config4_30s_clip_plus_offline(built_lib):
+    """FullSubNet+ cannot stream (TSSE pools over all time); SURVEY 8d asks for its offline number on the same 30 s clip."""
+    from oracle.torch_port import TorchPort
+    cfg = O.default_plus_config()
+    params = O.make_params_plus(cfg, seed=0)
+    X = O.stft(O.synth_clips(1, num_samples=480000, seed0=78))
+    mag, real, imag = (np.abs(X)[:, None].astype(np.float32), X.real[:, None].astype(np.float32), X.imag[:, None].astype(np.float32))
+    ref = TorchPort(params, cfg, "plus", dtype=torch.float64).forward(*(torch.from_numpy(x) for x in (mag, real, imag))).numpy()
+    m = _plus(cfg, params)
+    with torch.no_grad():
+        out = m(_t(mag), _t(real), _t(imag)).cpu().numpy()
+    err = O.rel_l2(out, ref)
+    print(f"\n[FullSubNet+ 30 s offline] cIRM rel-L2 {err:.3e}")
+    assert err < MASK_TOL
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_streaming_step_api_default_geometry(built_lib, B):
+    """The path scripts/bench_stream.py and `bench.py --config 4` time: F = 257, full-band H = 512 (weight-stationary kernel),
+    sub-band H = 384 (generic step kernel), cumulative_laplace_norm, frame by frame; against the oracle and the offline forward."""
+    from fsnplus_b200.streaming import StreamingFullSubNet
+    cfg = O.default_fsn_config()
+    cfg["norm_type"] = "cumulative_laplace_norm"
+    params = O.make_params_fsn(cfg, seed=33)
+    T = 40
+    mag = np.abs(O.stft(O.synth_clips(B, num_samples=256 * (T - 1), seed0=500)))[:, None].astype(np.float32)
+    assert mag.shape == (B, 1, 257, T)
+    ref = O.fullsubnet_forward(params, cfg, mag)
+    m = _fsn(cfg, params)
+    with torch.no_grad():
+        offline = m(_t(mag))
+    st = StreamingFullSubNet(m, batch_size=B, device=DEV)
+    x, frames = _t(mag), []
+    for t in range(T):
+        y = st.step(x[:, 0, :, t])
+        assert (y is None) == (t < cfg["look_ahead"])
+        if y is not None:
+            frames.append(y)
+    frames += st.flush()
+    st.close()
+    got = torch.stack(frames, dim=-1).cpu().numpy()
+    e_off, e_ref, e_offline = O.rel_l2(got, offline.cpu().numpy()), O.rel_l2(got, ref), O.rel_l2(offline.cpu().numpy(), ref)
+    print(f"\n[streaming default geometry B={B}] step vs offline {e_off:.2e}; step vs oracle {e_ref:.3e}; offline vs oracle {e_offline:.3e}")
+    assert e_ref < MASK_TOL and e_offline < MASK_TOL and e_off < MASK_TOL
+
+
+def test_batch_of_64_distinct_clips_vs_cpu_port(built_lib):
+    """BASELINE config #2's batch with 64 DIFFERENT clips (seeds 1000..1063, SNR -5..20 dB, levels -35..-15 dBFS): every sample
+    of the batched GPU forward against the per-clip fp32 CPU port (the reference's ATen op sequence, one clip per call)."""
+    from oracle.torch_port import TorchPort
+    cfg = O.default_plus_config()
+    params = O.make_params_plus(cfg, seed=0)
+    X = O.stft(O.synth_clips(64))
+    mag, real, imag = (np.abs(X)[:, None].astype(np.float32), X.real[:, None].astype(np.float32), X.imag[:, None].astype(np.float32))
+    m = _plus(cfg, params)
+    with torch.no_grad():
+        out = m(_t(mag), _t(real), _t(imag)).cpu().numpy()
+    port = TorchPort(params, cfg, "plus")
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    errs = []
+    for i in range(64):
+        ref = port.forward(*(torch.from_numpy(x[i:i + 1]) for x in (mag, real, imag))).numpy()
+        errs.append(O.rel_l2(out[i:i + 1], ref))
+    print(f"\n[64 distinct clips] cIRM rel-L2 vs CPU port: max {max(errs):.3e}  median {np.median(errs):.3e}")
+    assert max(errs) < MASK_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# pipelined entry points
+# ---------------------------------------------------------------------------------------------------------------------
+def test_submit_wait_matches_forward(built_lib, golden):
+    """fsn_model_submit / fsn_model_wait: five batches in flight through the two lanes (front end of batch i+1 overlapping the
+    sub-band LSTM of batch i), default geometry, different batch contents; every result must be bit-identical to forward()
+    up to the order of the fp64 atomics of the gLN statistics."""
+    g = golden("plus_default")
+    cfg = O.default_plus_config()
+    m = _plus(cfg, O.make_params_plus(cfg, seed=0))
+    B = 6
+    rng = np.random.default_rng(5)
+    batches = []
+    for k in range(5):
+        scale = rng.uniform(0.3, 3.0, size=(B, 1, 1, 1)).astype(np.float32)
+        shift = rng.integers(0, 188, size=B)
+        mk = lambda x: _t(np.stack([np.roll(x[0], int(s), axis=-1) for s in shift]) * scale)
+        batches.append((mk(g["mag"]), mk(g["real"]), mk(g["imag"])))
+    with torch.no_grad():
+        want = [m(*b) for b in batches]
+        torch.cuda.synchronize()
+        outs = [m.submit(*b) for b in batches]
+        m.wait()
+        torch.cuda.synchronize()
+        for k in range(5):
+            assert O.rel_l2(outs[k].cpu().numpy(), want[k].cpu().numpy()) < 1e-5, k
+        # a plain forward right after pipelined work, and pipelined work right after a plain forward
+        o1 = m.submit(*batches[0])
+        o2 = m(*batches[1])
+        o3 = m.submit(*batches[2])
+        m.wait()
+        torch.cuda.synchronize()
+        for o, k in ((o1, 0), (o2, 1), (o3, 2)):
+            assert O.rel_l2(o.cpu().numpy(), want[k].cpu().numpy()) < 1e-5, k
+
+
+def test_submit_fullsubnet_model_single_lane(built_lib):
+    """fullsubnet.Model through the pipelined API (one lane, no overlap: its full-band LSTM is a cooperative launch)."""
+    cfg = O.default_fsn_config()
+    cfg.update(num_freqs=33, sb_num_neighbors=3, sb_model_hidden_size=64, fb_model_hidden_size=48)
+    m = _fsn(cfg, O.make_params_fsn(cfg, seed=4))
+    xs = [_t(_inputs(3, 33, 22, s)[0]) for s in (1, 2, 3)]
+    with torch.no_grad():
+        want = [m(x) for x in xs]
+        outs = [m.submit(x) for x in xs]
+        m.wait()
+    torch.cuda.synchronize()
+    for a, b in zip(outs, want):
+        assert torch.equal(a, b)
+
+
+def test_forward_host_pipelined_default_geometry(built_lib, golden):
+    """Host-buffer pipelined entry point at the default geometry, four batches, against forward()."""
+    g = golden("plus_default")
+    cfg = O.default_plus_config()
+    m = _plus(cfg, O.make_params_plus(cfg, seed=0))
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    hb = [tuple(pin(np.repeat(g[k], 4, axis=0) * s) for k in ("mag", "real", "imag")) for s in (1.0, 0.5, 2.0, 1.5)]
+    with torch.no_grad():
+        want = [m(*(x.to(DEV) for x in b)).cpu() for b in hb]
+    outs = [m.forward_host(*b, device=DEV, pipelined=True) for b in hb]
+    m.sync_host()
+    for a, b in zip(outs, want):
+        assert O.rel_l2(a.numpy(), b.numpy()) < 1e-5
+    with pytest.raises(ValueError):
+        m.forward_host(hb[0][0].double(), hb[0][1], hb[0][2], device=DEV)
+    with pytest.raises(ValueError):
+        m.forward_host(torch.from_numpy(np.ascontiguousarray(g["mag"])), hb[0][1][:1], hb[0][2][:1], device=DEV, pipelined=True)   # not pinned

@@ -166,3 +166,17 @@ def test_torch_port_matches_reference(golden):
     fcfg = O.default_fsn_config()
     out = TorchPort(O.make_params_fsn(fcfg, seed=1), fcfg, "fsn").forward(t("mag")).numpy()
     assert O.rel_l2(out, gf["out"]) < 1e-4
+
+
+@pytest.mark.parametrize("norm", ["offline_laplace_norm", "cumulative_laplace_norm", "offline_gaussian_norm", "cumulative_layer_norm"])
+def test_torch_port_fp64_all_norms_pinned(golden, norm):
+    """The torch port in float64 is the truth of the long-clip GPU parity tests (the numpy oracle needs minutes for a 30 s clip):
+    pin it to the reference goldens for every norm_type at the fp64 noise floor."""
+    import torch
+    from oracle.torch_port import TorchPort
+    g = golden(f"fsn_small_{norm}")
+    c = O.default_fsn_config()
+    c.update(num_freqs=33, sb_num_neighbors=3, sb_model_hidden_size=32, fb_model_hidden_size=48, norm_type=norm)
+    port = TorchPort(O.make_params_fsn(c, seed=4), c, "fsn", dtype=torch.float64)
+    out = port.forward(torch.from_numpy(g["mag"])).numpy()
+    assert O.rel_l2(out, g["out"]) < 1e-6          # goldens are stored in float32
