@@ -905,6 +905,14 @@ extern "C" int fsn_model_submit(fsn_model* m, const float* d_mag, const float* d
     return submit_impl(m, m->ev_in, d_mag, d_real, d_imag, B, T, d_out, nullptr);
 }
 
+extern "C" int fsn_model_last_lane(const fsn_model* m) { return m ? m->last_lane : 0; }
+
+extern "C" int fsn_model_wait_lane(fsn_model* m, int32_t lane, void* stream) {
+    if (!m || lane < 0 || lane > 1) return fail(FSN_EINVAL, "bad argument");
+    if (m->lane[lane].used) CK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), m->lane[lane].ev_lstm, 0));
+    return FSN_OK;
+}
+
 extern "C" int fsn_model_wait(fsn_model* m, void* stream) {
     if (!m) return fail(FSN_EINVAL, "null model");
     cudaStream_t s = static_cast<cudaStream_t>(stream);

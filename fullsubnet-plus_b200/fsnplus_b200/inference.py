@@ -108,3 +108,98 @@ def enhance_sharded(model, noisy_all, group=None, **kw):
     lo, hi = shard_range(noisy_all.size(0), rank, world)
     local = enhance_batch(model, noisy_all[lo:hi], **kw) if hi > lo else noisy_all.new_zeros((0, noisy_all.size(1)))
     return all_gather_enhanced(local, noisy_all.size(0), group)
+
+
+class EnhancePipeline:
+    """Enhancement of a STREAM of equal-shape batches with everything overlapped (what the reference's inferencer loop,
+    base_inferencer.py:133-160, does one clip at a time):
+
+        push(i):   [optional H2D of pinned host spectra on a copy stream] -> model.submit(batch i)      (front end of batch i runs
+                   while the sub-band LSTM of batch i-1 is still running, see fsn_model_submit)
+                   then, on a side stream, for batch i-1: decompress_cIRM x noisy spectrum (fused kernel) -> torch.istft ->
+                   ONE all-gather of the enhanced waveforms over the process group (world > 1) [-> D2H into pinned host memory]
+        flush():   post-process the last batch and synchronise; returns the list of results in push order.
+
+    The collective therefore runs on the side stream underneath the NEXT batch's forward, never on the
+    critical path.  Results: device tensors [world * B, L] (gathered) or [B, L]; with ``to_host=True`` this rank's shard in
+    pinned host memory.  Result buffers are double-buffered: a result is valid until two pushes later (copy it if kept longer).
+    """
+
+    def __init__(self, model, length, n_fft=512, hop_length=256, win_length=512, complex_inputs=True, gather=True, to_host=False,
+                 keep_results=True, group=None):
+        self.model, self.length, self.stft_args = model, length, (n_fft, hop_length, win_length)
+        self.complex_inputs, self.to_host, self.keep, self.group = complex_inputs, to_host, keep_results, group
+        self.world = dist.get_world_size(group) if (gather and dist.is_available() and dist.is_initialized()) else 1
+        self.dev = next(model.parameters()).device
+        self.post, self.copy = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        self.pending = None                       # (lane, X, mask, slot) of the batch whose LSTM may still be running
+        self.n = 0
+        two = lambda: [None, None]
+        self.masks, self.post_done, self.stage, self.host_out, self.gathered = two(), two(), two(), two(), two()
+        self.results = []
+
+    def _finish(self, item):
+        lane, X, mask, slot = item
+        with torch.cuda.stream(self.post):
+            self.model.wait_lane(lane, self.post)                       # the sub-band LSTM of that batch has written `mask`
+            enh = istft(apply_cirm(mask, X), *self.stft_args, length=self.length)
+            res = enh
+            if self.world > 1:
+                if self.gathered[slot] is None:
+                    self.gathered[slot] = torch.empty((self.world * enh.size(0), enh.size(1)), dtype=enh.dtype, device=self.dev)
+                dist.all_gather_into_tensor(self.gathered[slot], enh.contiguous(), group=self.group)
+                res = self.gathered[slot]
+            if self.to_host:
+                if self.host_out[slot] is None:
+                    self.host_out[slot] = torch.empty(tuple(enh.shape), dtype=enh.dtype).pin_memory()
+                self.host_out[slot].copy_(enh, non_blocking=True)       # this rank's shard -> pinned host memory
+                res = self.host_out[slot]
+            ev = torch.cuda.Event()
+            ev.record(self.post)
+            self.post_done[slot] = ev
+            X.record_stream(self.post)
+        if self.keep:
+            self.results.append(res)
+
+    def push(self, X=None, host=None):
+        """One batch: ``X`` complex64 [B, F, T] on the device, or ``host`` = (mag, real, imag) pinned CPU float32 [B, 1, F, T]
+        (the C ABI's host-buffer layout; X is rebuilt on the device from real / imag)."""
+        slot = self.n & 1
+        main = torch.cuda.current_stream(self.dev)
+        if self.post_done[slot] is not None:
+            main.wait_event(self.post_done[slot])                       # mask / staging buffers of this slot are free again
+        if host is not None:
+            with torch.cuda.stream(self.copy):
+                if self.post_done[slot] is not None:
+                    self.copy.wait_event(self.post_done[slot])
+                if self.stage[slot] is None:
+                    self.stage[slot] = [torch.empty(tuple(h.shape), dtype=torch.float32, device=self.dev) for h in host]
+                for d, h in zip(self.stage[slot], host):
+                    d.copy_(h, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy)
+            main.wait_event(ev)
+            mag = self.stage[slot][0]
+            real, imag = (self.stage[slot][1], self.stage[slot][2]) if self.complex_inputs else (None, None)
+            X = torch.complex(self.stage[slot][1][:, 0], self.stage[slot][2][:, 0])
+        else:
+            mag = X.abs().unsqueeze(1)
+            real, imag = (X.real.unsqueeze(1).contiguous(), X.imag.unsqueeze(1).contiguous()) if self.complex_inputs else (None, None)
+        B, F, T = X.shape
+        if self.masks[slot] is None or self.masks[slot].shape[0] != B or self.masks[slot].shape[-1] != T:
+            self.masks[slot] = torch.empty((B, 2, F, T), dtype=torch.float32, device=self.dev)
+        self.model.submit(mag, real, imag, out=self.masks[slot])
+        item = (self.model.last_lane, X, self.masks[slot], slot)
+        if self.pending is not None:
+            self._finish(self.pending)
+        self.pending = item
+        self.n += 1
+
+    def flush(self):
+        if self.pending is not None:
+            self._finish(self.pending)
+            self.pending = None
+        self.post.synchronize()
+        self.model.wait()
+        out, self.results = self.results, []
+        return out

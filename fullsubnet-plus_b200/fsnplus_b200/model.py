@@ -226,7 +226,15 @@ class _B200Model(nn.Module):
             stream = C.c_void_p(torch.cuda.current_stream(mag.device).cuda_stream)
             _lib.check(lib.fsn_model_submit(self._handle, ptr(ins[0]), ptr(ins[1]), ptr(ins[2]), B, T, ptr(out), stream))
         self._inflight.append((ins, out))
+        self.last_lane = int(lib.fsn_model_last_lane(self._handle))     # ticket for wait_lane()
         return out
+
+    def wait_lane(self, lane, stream=None):
+        """Make ``stream`` (default: the current stream) wait for the batch most recently submitted into workspace lane ``lane``
+        (``self.last_lane`` right after its ``submit()``); valid until the next submit into the same lane, i.e. two submits later."""
+        with torch.cuda.device(self._handle_device):
+            st = stream if stream is not None else torch.cuda.current_stream(self._handle_device)
+            _lib.check(_lib.load_library().fsn_model_wait_lane(self._handle, int(lane), C.c_void_p(st.cuda_stream)))
 
     def wait(self):
         """Make the current stream wait for every ``submit()`` issued so far (does not block the host)."""

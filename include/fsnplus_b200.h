@@ -130,6 +130,10 @@ int fsn_model_forward_host(fsn_model* m, const float* h_mag, const float* h_real
 int fsn_model_submit(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
                      float* d_out, void* stream);
 int fsn_model_wait(fsn_model* m, void* stream);
+/* Finer-grained completion for consumers that post-process batch i while batch i+1 runs: the workspace lane (0 / 1) the LAST
+ * fsn_model_submit used, and a wait on the batch most recently submitted into one lane (valid until the next submit into it). */
+int fsn_model_last_lane(const fsn_model* m);
+int fsn_model_wait_lane(fsn_model* m, int32_t lane, void* stream);
 int fsn_model_forward_host_async(fsn_model* m, const float* h_mag, const float* h_real, const float* h_imag, int32_t B, int32_t T,
                                  float* h_out, void* stream);
 int fsn_model_sync_host(fsn_model* m);

@@ -82,7 +82,15 @@ class TorchPort:
         return {None: o, False: o, "ReLU": F.relu(o), "Tanh": torch.tanh(o), "ReLU6": F.relu6(o)}[name]
 
     def seq_lstm(self, x, pre, actname):            # sequence_model.py:113-122
-        o, _ = self.lstm[pre](x.permute(0, 2, 1).contiguous())
+        xt = x.permute(0, 2, 1).contiguous()
+        if xt.shape[1] <= 512:
+            o, _ = self.lstm[pre](xt)
+        else:                                       # long clips: same recurrence in time chunks with the state carried (ATen's CPU
+            outs, st = [], None                     # LSTM slows down super-linearly with the sequence length)
+            for t0 in range(0, xt.shape[1], 256):
+                oc, st = self.lstm[pre](xt[:, t0:t0 + 256].contiguous(), st)
+                outs.append(oc)
+            o = torch.cat(outs, dim=1)
         o = self.act(F.linear(o, self.p[f"{pre}.fc_output_layer.weight"], self.p[f"{pre}.fc_output_layer.bias"]), actname)
         return o.permute(0, 2, 1).contiguous()
 
