@@ -106,7 +106,8 @@ struct fsn_model {
     DevBuf a_in[2][3], a_out[2];
     int64_t nsub = 0;
     static const int NEV = 32;
-    cudaEvent_t ev0[NEV] = {}, ev1[NEV] = {};
+    cudaEvent_t ev0[NEV] = {}, ev1[NEV] = {};               // sub-band LSTM start / end
+    cudaEvent_t evf0[NEV] = {}, evf1[NEV] = {};             // front end start / end (same ring index)
     int64_t nfwd = 0;                                 // forwards whose LSTM events were recorded
 };
 
@@ -370,7 +371,7 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     { const char* e = getenv("FSN_LSTM_IMPL"); if (e && *e) m->env_impl = atoi(e); }
     { const char* e = getenv("FSN_NO_WS"); m->env_no_ws = e && atoi(e) != 0; }
     build_specs(m);
-    for (int i = 0; i < fsn_model::NEV; ++i) { cudaEventCreate(&m->ev0[i]); cudaEventCreate(&m->ev1[i]); }
+    for (int i = 0; i < fsn_model::NEV; ++i) { cudaEventCreate(&m->ev0[i]); cudaEventCreate(&m->ev1[i]); cudaEventCreate(&m->evf0[i]); cudaEventCreate(&m->evf1[i]); }
     { cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev); if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) m->num_sms = prop.multiProcessorCount; }
     if (m->Isb > 64) { delete m; return fail(FSN_EINVAL, "sub-band input size %d > 64 not supported", m->Isb); }
     *out = m;
@@ -395,7 +396,12 @@ extern "C" void fsn_model_destroy(fsn_model* m) {
     if (m->ev_plain) cudaEventDestroy(m->ev_plain);
     if (m->s_in) { cudaStreamDestroy(m->s_in); cudaStreamDestroy(m->s_out); for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_h2d[i]); cudaEventDestroy(m->ev_d2h[i]); } }
     for (int i = 0; i < 2; ++i) { m->a_out[i].release(); for (int j = 0; j < 3; ++j) m->a_in[i][j].release(); }
-    for (int i = 0; i < fsn_model::NEV; ++i) { if (m->ev0[i]) cudaEventDestroy(m->ev0[i]); if (m->ev1[i]) cudaEventDestroy(m->ev1[i]); }
+    for (int i = 0; i < fsn_model::NEV; ++i) {
+        if (m->ev0[i]) cudaEventDestroy(m->ev0[i]);
+        if (m->ev1[i]) cudaEventDestroy(m->ev1[i]);
+        if (m->evf0[i]) cudaEventDestroy(m->evf0[i]);
+        if (m->evf1[i]) cudaEventDestroy(m->evf1[i]);
+    }
     for (int i = 0; i < 4; ++i) { m->sb_frag[i].release(); m->sb_bias[i].release(); m->fb_frag[i].release(); m->fb_bias[i].release(); }
     delete m;
 }
@@ -670,6 +676,8 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
     if (rc) return rc;
     m->launches = 0;
     m->last_lane = (int)(&ln - m->lane);
+    const int evi = (int)(m->nfwd % fsn_model::NEV);
+    cudaEventRecord(m->evf0[evi], s);
 
     SbPackLaunch sp{};
     sp.B = B; sp.F = F; sp.Tp = Tp; sp.Ns = c.sb_num_neighbors; sp.Nf = c.fb_num_neighbors; sp.P = Pp;
@@ -830,11 +838,11 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
     }
     launch_sb_stats(sp, s); m->launches += 2;
     launch_sb_pack(sp, s); m->launches++;
+    cudaEventRecord(m->evf1[evi], s);
     if (sl != s) {                                                      // pipelined: the LSTM stream picks the lane up when the front end is done
         CK(cudaEventRecord(ln.ev_front, s));
         CK(cudaStreamWaitEvent(sl, ln.ev_front, 0));
     }
-    const int evi = (int)(m->nfwd % fsn_model::NEV);
     cudaEventRecord(m->ev0[evi], sl);
     rc = run_sb_lstm(m, ln, B, T, d_out, sl);
     cudaEventRecord(m->ev1[evi], sl);
@@ -1145,6 +1153,24 @@ extern "C" int fsn_model_lstm_ms_history(fsn_model* m, float* h_ms, int32_t n) {
         float ms = -1.f;
         if (cudaEventSynchronize(m->ev1[evi]) != cudaSuccess || cudaEventElapsedTime(&ms, m->ev0[evi], m->ev1[evi]) != cudaSuccess) ms = -1.f;
         h_ms[i] = ms;
+    }
+    return n;
+}
+// [front start, front end, LSTM start, LSTM end] in ms relative to the front start of the oldest reported forward
+extern "C" int fsn_model_timeline(fsn_model* m, float* h_ms4, int32_t n) {
+    if (!m || !h_ms4 || n < 1) return 0;
+    int64_t avail = m->nfwd < fsn_model::NEV ? m->nfwd : fsn_model::NEV;
+    if (n > avail) n = (int32_t)avail;
+    if (n < 1) return 0;
+    const int base = (int)((m->nfwd - n) % fsn_model::NEV);
+    for (int i = 0; i < n; ++i) {
+        const int evi = (int)((m->nfwd - n + i) % fsn_model::NEV);
+        cudaEvent_t ev[4] = {m->evf0[evi], m->evf1[evi], m->ev0[evi], m->ev1[evi]};
+        for (int k = 0; k < 4; ++k) {
+            float ms = -1.f;
+            if (cudaEventSynchronize(ev[k]) != cudaSuccess || cudaEventElapsedTime(&ms, m->evf0[base], ev[k]) != cudaSuccess) ms = -1.f;
+            h_ms4[4 * i + k] = ms;
+        }
     }
     return n;
 }

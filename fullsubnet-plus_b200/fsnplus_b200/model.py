@@ -306,6 +306,12 @@ class _B200Model(nn.Module):
         k = _lib.load_library().fsn_model_lstm_ms_history(self._handle, buf, n) if self._handle else 0
         return [float(buf[i]) for i in range(k)]
 
+    def timeline(self, n=32):
+        """[(front start, front end, LSTM start, LSTM end)] in ms for the last n forwards, relative to the first one's front start."""
+        buf = (C.c_float * (4 * n))()
+        k = _lib.load_library().fsn_model_timeline(self._handle, buf, n) if self._handle else 0
+        return [tuple(float(buf[4 * i + j]) for j in range(4)) for i in range(k)]
+
     def last_launch_count(self):
         return int(_lib.load_library().fsn_model_last_launch_count(self._handle)) if self._handle else 0
 

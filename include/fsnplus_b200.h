@@ -165,6 +165,10 @@ int64_t fsn_model_last_launch_count(const fsn_model* m);
 float fsn_model_last_lstm_ms(fsn_model* m);
 /* Same for the last n forwards (n <= 32, oldest first); returns how many were written.  Synchronises. */
 int fsn_model_lstm_ms_history(fsn_model* m, float* h_ms, int32_t n);
+/* Device timeline of the last n forwards (n <= 32, oldest first): 4 floats each = front-end start, front-end end, sub-band
+ * LSTM start, LSTM end in ms relative to the oldest one's front-end start (CUDA events on the streams the phases run on).  With
+ * the pipelined entry points the front end of batch i+1 lies inside the LSTM interval of batch i.  Returns the count; synchronises. */
+int fsn_model_timeline(fsn_model* m, float* h_ms4, int32_t n);
 /* Which LSTM implementation the last forward used for the sub-band model (FSN_LSTM_MMA / _TCGEN05). */
 int fsn_model_last_lstm_impl(const fsn_model* m);
 
