@@ -746,7 +746,7 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
 
                 DwTmLaunch dw{};
                 dw.X = static_cast<const float*>(ln.y1.p); dw.Y = static_cast<float*>(ln.y2.p);
-                dw.Z = Z; dw.B = B; dw.C = 512; dw.Tp = Tp; dw.dilation = dil[blk]; dw.tchunk = 48;
+                dw.Z = Z; dw.B = B; dw.C = 512; dw.Tp = Tp; dw.dilation = dil[blk]; dw.tchunk = 48; dw.causal = c.tcn_causal ? 1 : 0;
                 dw.stats_in = st1; dw.stats_out = st2;
                 for (int b = 0; b < 3; ++b) {
                     dw.gamma[b] = P(m, key(b, "norm1.weight")); dw.beta[b] = P(m, key(b, "norm1.bias"));

@@ -177,6 +177,7 @@ int launch_gemm_tc5(const void* mapA, const void* mapB, GemmTc5Launch a, int num
 struct DwTmLaunch {
     const float* X; float* Y;                  // [Z * Tp, C]
     int Z, B, C, Tp, dilation, tchunk;
+    int causal;                                // 1: taps t-2d, t-d, t (TCNBlock(causal=True)); 0: t-d, t, t+d
     const double* stats_in; double* stats_out;
     const float* gamma[3]; const float* beta[3]; const float* w[3]; const float* b[3]; const float* prelu[3];
 };

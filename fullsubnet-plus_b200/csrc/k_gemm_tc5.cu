@@ -287,7 +287,7 @@ int launch_gemm_tc5(const void* mapA, const void* mapB, GemmTc5Launch a, int num
     return (int)cudaGetLastError();
 }
 
-// gLN1 apply -> depth-wise conv (k=3, dilation d, zero padding in the normalised domain) -> PReLU2 + gLN2 statistics,
+// gLN1 apply -> depth-wise conv (k=3, dilation d, zero padding in the normalised domain; causal or symmetric taps) -> PReLU2 + gLN2 statistics,
 // on the time-major [rows, C] layout.  reference: causal_conv.py:100-106.  One CTA = one sample x 64 channels x all
 // frames: the slab (T' x 64 floats, 48 KB for T' = 190) is staged once in shared memory with the gLN already applied,
 // so every input element is read exactly once from HBM/L2 and the three taps come from shared memory.
@@ -325,9 +325,11 @@ __global__ void __launch_bounds__(256) dwconv_tm_kernel(DwTmLaunch a) {
     float ls = 0.f, lq = 0.f;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = tr; t < Tp; t += 16) {
-        const float4 m = reinterpret_cast<const float4*>(slab + t * DW_CH)[cq];
-        const float4 l = (t - d >= 0) ? reinterpret_cast<const float4*>(slab + (t - d) * DW_CH)[cq] : zero;
-        const float4 r = (t + d < Tp) ? reinterpret_cast<const float4*>(slab + (t + d) * DW_CH)[cq] : zero;
+        // taps (w0, w1, w2): non-causal (t-d, t, t+d); causal (t-2d, t-d, t) -- padding 2d + chomp, causal_conv.py:74-75,104-105
+        const int tl = a.causal ? t - 2 * d : t - d, tm = a.causal ? t - d : t, tr2 = a.causal ? t : t + d;
+        const float4 m = (tm >= 0) ? reinterpret_cast<const float4*>(slab + tm * DW_CH)[cq] : zero;
+        const float4 l = (tl >= 0) ? reinterpret_cast<const float4*>(slab + tl * DW_CH)[cq] : zero;
+        const float4 r = (tr2 < Tp) ? reinterpret_cast<const float4*>(slab + tr2 * DW_CH)[cq] : zero;
         float o[4] = {fmaf(w0.x, l.x, fmaf(w1.x, m.x, fmaf(w2.x, r.x, bb.x))), fmaf(w0.y, l.y, fmaf(w1.y, m.y, fmaf(w2.y, r.y, bb.y))),
                       fmaf(w0.z, l.z, fmaf(w1.z, m.z, fmaf(w2.z, r.z, bb.z))), fmaf(w0.w, l.w, fmaf(w1.w, m.w, fmaf(w2.w, r.w, bb.w)))};
 #pragma unroll

@@ -118,7 +118,7 @@ class _B200Model(nn.Module):
 
     def _setup(self, num_freqs, look_ahead, sb_num_neighbors, fb_num_neighbors, fb_hidden, sb_hidden, num_layers,
                output_size, fb_act, sb_act, norm_type, kersize, lstm_impl, fast_math, channel_attention="TSSE",
-               rnn="LSTM", subband_num=1):
+               rnn="LSTM", subband_num=1, tcn_causal=False):
         if norm_type not in _lib.NORM:
             raise NotImplementedError("You must set up a type of Norm. e.g. offline_laplace_norm, "
                                       "cumulative_laplace_norm, forgetting_norm, etc.")       # base_model.py:328-329
@@ -136,6 +136,7 @@ class _B200Model(nn.Module):
         cfg.channel_attention = _lib.ATTENTION[channel_attention]
         cfg.rnn_type = _lib.RNN[rnn]
         cfg.subband_num = int(subband_num)
+        cfg.tcn_causal = int(bool(tcn_causal))
         self._cfg = cfg
         self._handle = None
         self._handle_device = None
@@ -331,7 +332,9 @@ class FullSubNet_Plus(_B200Model):
                  fb_output_activate_function, sb_output_activate_function, fb_model_hidden_size, sb_model_hidden_size,
                  channel_attention_model="SE", norm_type="offline_laplace_norm", num_groups_in_drop_band=2,
                  output_size=2, subband_num=1, kersize=[3, 5, 10], weight_init=True,
-                 num_layers=2, lstm_impl="auto", fast_math=True):
+                 num_layers=2, lstm_impl="auto", fast_math=True, causal_tcn=False):
+        """Reference keywords (fullsubnet_plus.py:17-34) + additive ones: num_layers (LSTM depth), lstm_impl, fast_math,
+        causal_tcn (TCNBlock(causal=True) in the full-band models, causal_conv.py:74-75,104-105; parameters unchanged)."""
         super().__init__()
         assert sequence_model in ("GRU", "LSTM", "TCN"), f"{self.__class__.__name__} only support GRU, LSTM and TCN."
         if sequence_model == "TCN":
@@ -361,7 +364,8 @@ class FullSubNet_Plus(_B200Model):
         self.output_size = output_size
         self._setup(num_freqs, look_ahead, sb_num_neighbors, fb_num_neighbors, fb_model_hidden_size, sb_model_hidden_size,
                     num_layers, output_size, fb_output_activate_function, sb_output_activate_function, norm_type, kersize,
-                    lstm_impl, fast_math, channel_attention_model, sequence_model, subband_num if self._subband_runs else 1)
+                    lstm_impl, fast_math, channel_attention_model, sequence_model, subband_num if self._subband_runs else 1, causal_tcn)
+        self.causal_tcn = bool(causal_tcn)
         if weight_init:
             self.apply(_reference_weight_init)
 

@@ -80,6 +80,9 @@ typedef struct fsn_config {
     int32_t rnn_type;         /* FSN_RNN_*   sequence_model           (:35)                      */
     int32_t subband_num;      /* 0 or 1: off; > 1 needs FSN_ATTN_ECA (the only attention whose
                                  reference forward runs in that mode, fullsubnet_plus.py:146-163) */
+    int32_t tcn_causal;       /* 0: TCNBlock(causal=False), what SequenceModel("TCN") builds (sequence_model.py:47-58);
+                                 1: TCNBlock(causal=True) in the three full-band models (causal_conv.py:74-75,104-105):
+                                 depth-wise taps t-2d, t-d, t instead of t-d, t, t+d.  Additive knob */
 } fsn_config;
 
 typedef struct fsn_model fsn_model;

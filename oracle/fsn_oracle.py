@@ -352,15 +352,17 @@ def gln(x, g, b):
     return (x - mu) / np.sqrt(var + GLN_EPS) * g[None, :, None] + b[None, :, None]
 
 
-def tcn_block(x, p, q, d):
-    """TCNBlock.forward, causal=False, skip connection (causal_conv.py:96-108).  x [B, C, T]."""
+def tcn_block(x, p, q, d, causal=False):
+    """TCNBlock.forward with the skip connection (causal_conv.py:96-108).  x [B, C, T].  causal=False (what SequenceModel builds,
+    sequence_model.py:47-58): symmetric zero padding d, taps t-d, t, t+d.  causal=True (causal_conv.py:74-75,104-105): padding 2d
+    on both sides and the last 2d outputs chomped, i.e. taps t-2d, t-d, t."""
     dt = x.dtype
     w1 = p[f"{q}.conv1x1.weight"].astype(dt)[:, :, 0]
     y = np.einsum("oc,bct->bot", w1, x) + p[f"{q}.conv1x1.bias"].astype(dt)[None, :, None]
     y = gln(prelu(y, p[f"{q}.prelu1.weight"].astype(dt)[0]),
             p[f"{q}.norm1.weight"].astype(dt), p[f"{q}.norm1.bias"].astype(dt))
     T = y.shape[2]
-    yp = np.pad(y, ((0, 0), (0, 0), (d, d)))                               # padding = d (zeros)
+    yp = np.pad(y, ((0, 0), (0, 0), (2 * d, 0) if causal else (d, d)))     # zeros; causal: left 2d (right pad + chomp cancel)
     wd = p[f"{q}.depthwise_conv.weight"].astype(dt)[:, 0, :]
     z = np.zeros_like(y)
     for j in range(3):
@@ -386,10 +388,10 @@ def activation(x, name):
     raise NotImplementedError(name)
 
 
-def seq_tcn(x, p, prefix, act):
+def seq_tcn(x, p, prefix, act, causal=False):
     """SequenceModel.forward, TCN branch (sequence_model.py:106-112).  x [B, F, T]."""
     for i, d in enumerate(TCN_DILATIONS):
-        x = tcn_block(x, p, f"{prefix}.sequence_model.{i}", d)
+        x = tcn_block(x, p, f"{prefix}.sequence_model.{i}", d, causal)
     x = np.maximum(x, 0.0)                                                  # nn.ReLU at sequence_model.py:57
     w = p[f"{prefix}.fc_output_layer.weight"].astype(x.dtype)
     b = p[f"{prefix}.fc_output_layer.bias"].astype(x.dtype)
@@ -488,7 +490,7 @@ def fullsubnet_plus_forward(p, cfg, mag, real, imag, dtype=np.float64, num_layer
             xi = norm(x).reshape(B, F, T)                                               # :144,157,162
             xi = channel_attention(xi, p, f"channel_attention{s}", cfg)                     # :145,158,163
         fb_in.append(xi)
-        fb_out.append(seq_tcn(xi, p, f"fb_model{s}", cfg["fb_output_activate_function"])
+        fb_out.append(seq_tcn(xi, p, f"fb_model{s}", cfg["fb_output_activate_function"], cfg.get("causal_tcn", False))
                       .reshape(B, 1, F, T))                                             # :154,159,164
     unf = [unfold(o, nfb).reshape(B, F, 2 * nfb + 1, T) for o in fb_out]                 # :167-179
     mag_unf = unfold(fb_in[0].reshape(B, 1, F, T), ns).reshape(B, F, 2 * ns + 1, T)      # :182-185

@@ -71,7 +71,10 @@ class TorchPort:
             q = f"{pre}.sequence_model.{i}"
             y = F.conv1d(x, p[f"{q}.conv1x1.weight"], p[f"{q}.conv1x1.bias"])
             y = F.group_norm(F.prelu(y, p[f"{q}.prelu1.weight"]), 1, p[f"{q}.norm1.weight"], p[f"{q}.norm1.bias"], 1e-8)
-            y = F.conv1d(y, p[f"{q}.depthwise_conv.weight"], p[f"{q}.depthwise_conv.bias"], padding=d, dilation=d, groups=y.shape[1])
+            if self.cfg.get("causal_tcn", False):       # TCNBlock(causal=True): padding 2d, chomp 2d (causal_conv.py:74-75,104-105)
+                y = F.conv1d(y, p[f"{q}.depthwise_conv.weight"], p[f"{q}.depthwise_conv.bias"], padding=2 * d, dilation=d, groups=y.shape[1])[:, :, :-2 * d]
+            else:
+                y = F.conv1d(y, p[f"{q}.depthwise_conv.weight"], p[f"{q}.depthwise_conv.bias"], padding=d, dilation=d, groups=y.shape[1])
             y = F.group_norm(F.prelu(y, p[f"{q}.prelu2.weight"]), 1, p[f"{q}.norm2.weight"], p[f"{q}.norm2.bias"], 1e-8)
             x = x + F.conv1d(y, p[f"{q}.sconv.weight"], p[f"{q}.sconv.bias"])
         o = F.linear(F.relu(x).permute(0, 2, 1), p[f"{pre}.fc_output_layer.weight"], p[f"{pre}.fc_output_layer.bias"])

@@ -53,7 +53,7 @@ def hooks(model, names):
 
 def run_plus(cfg, params, mag, real, imag):
     """Reference forward, B=1 per call, float64. Returns out [B,2,F,T] + stage captures."""
-    model = load(FullSubNet_Plus(**cfg), params)
+    model = load(causal_plus(cfg) if cfg.get("causal_tcn") else FullSubNet_Plus(**cfg), params)
     names = ["channel_attention", "channel_attention_real", "channel_attention_imag",
              "fb_model", "fb_model_real", "fb_model_imag"]
     outs, fb_in, fb_out = [], [], []
@@ -68,6 +68,20 @@ def run_plus(cfg, params, mag, real, imag):
         fb_in.append(np.stack([cap[n][0].reshape(-1, Tq)[:Fq] for n in names[:3]]))
         fb_out.append(np.stack([cap[n][0] for n in names[3:]]))
     return np.concatenate(outs), np.stack(fb_in, 1), np.stack(fb_out, 1)      # [B,2,F,T], [3,B,F,T'], [3,B,F,T']
+
+
+def causal_plus(cfg):
+    """The reference FullSubNet_Plus with every full-band TCNBlock rebuilt as TCNBlock(causal=True) (causal_conv.py:67-117; the
+    constructor of SequenceModel("TCN") never passes causal, so the variant is assembled from the reference's own block class;
+    parameter names and shapes are unchanged)."""
+    from audio_zen.model.module.causal_conv import TCNBlock
+    kw = {k: v for k, v in cfg.items() if k != "causal_tcn"}
+    model = FullSubNet_Plus(**kw)
+    for sfx in ("", "_real", "_imag"):
+        seq = getattr(model, "fb_model" + sfx).sequence_model
+        for i, d in enumerate((1, 2, 5, 9, 1, 2, 5, 9)):
+            seq[i] = TCNBlock(in_channels=cfg["num_freqs"], out_channels=cfg["num_freqs"], dilation=d, causal=True)
+    return model
 
 
 def run_fsn(cfg, params, mag):
@@ -225,5 +239,23 @@ def main():
     save("lstm3_small", x=x, out=y, seed=12)
 
 
+def main_causal():
+    """Round 2: the causal FullSubNet+ variant: TCNBlock(causal=True) in all three full-band models."""
+    ccfg = dict(small_plus_cfg(), causal_tcn=True)
+    m, r, i = small_inputs(3, 33, 20, 7)
+    params = O.make_params_plus(ccfg, seed=14)
+    out, fb_in, fb_out = run_plus(ccfg, params, m, r, i)
+    st = {}
+    oo = O.fullsubnet_plus_forward(params, ccfg, m, r, i, stages=st)
+    print(f"plus_small[causal TCN]: oracle-vs-reference rel-L2 out={O.rel_l2(oo, out):.2e} fb_out={O.rel_l2(st['fb_out'], fb_out):.2e}")
+    nc = O.fullsubnet_plus_forward(params, dict(ccfg, causal_tcn=False), m, r, i)
+    print(f"   (non-causal output differs by {O.rel_l2(nc, out):.2e})")
+    save("plus_small_causal", out=out, fb_out=fb_out, seed=14)
+
+
 if __name__ == "__main__":
-    main()
+    if "causal" in sys.argv[1:]:
+        main_causal()
+    else:
+        main()
+        main_causal()

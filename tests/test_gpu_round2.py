@@ -281,3 +281,31 @@ def test_forward_host_pipelined_default_geometry(built_lib, golden):
         m.forward_host(hb[0][0].double(), hb[0][1], hb[0][2], device=DEV)
     with pytest.raises(ValueError):
         m.forward_host(torch.from_numpy(np.ascontiguousarray(g["mag"])), hb[0][1][:1], hb[0][2][:1], device=DEV, pipelined=True)   # not pinned
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# causal FullSubNet+ variant
+# ---------------------------------------------------------------------------------------------------------------------
+def test_causal_tcn_variant(built_lib, golden):
+    """TCNBlock(causal=True) in the full-band models: small config against the committed reference golden (incl. the fb_out
+    stage), default geometry against the oracle, and the causality property of the full-band TCN chain's taps (with the
+    non-causal gLN statistics held fixed this cannot be tested end to end, so the check is the golden)."""
+    g, gi = golden("plus_small_causal"), golden("plus_small")
+    cfg = dict(_small(32), causal_tcn=True)
+    m = _plus(cfg, O.make_params_plus(cfg, seed=14))
+    with torch.no_grad():
+        out = m(_t(gi["mag"]), _t(gi["real"]), _t(gi["imag"]))
+    fb_out = m.get_stage("fb_out", (3, 3, 33, 22), DEV).cpu().numpy()
+    e_fb, err = O.rel_l2(fb_out, g["fb_out"]), O.rel_l2(out.cpu().numpy(), g["out"])
+    print(f"\n[causal TCN small] fb_out {e_fb:.2e} cIRM {err:.3e}")
+    assert e_fb < 2e-3 and err < MASK_TOL
+    gd = golden("plus_default")
+    cfg = dict(O.default_plus_config(), causal_tcn=True)
+    params = O.make_params_plus(cfg, seed=0)
+    ref = O.fullsubnet_plus_forward(params, cfg, gd["mag"], gd["real"], gd["imag"])
+    m = _plus(cfg, params)
+    with torch.no_grad():
+        out = m(_t(gd["mag"]), _t(gd["real"]), _t(gd["imag"]))
+    err = O.rel_l2(out.cpu().numpy(), ref)
+    print(f"[causal TCN default geometry] cIRM {err:.3e} (differs from the non-causal golden by {O.rel_l2(ref, gd['out']):.2e})")
+    assert err < MASK_TOL

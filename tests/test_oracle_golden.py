@@ -180,3 +180,18 @@ def test_torch_port_fp64_all_norms_pinned(golden, norm):
     port = TorchPort(O.make_params_fsn(c, seed=4), c, "fsn", dtype=torch.float64)
     out = port.forward(torch.from_numpy(g["mag"])).numpy()
     assert O.rel_l2(out, g["out"]) < 1e-6          # goldens are stored in float32
+
+
+def test_plus_small_causal_tcn(golden):
+    """Causal FullSubNet+ variant: TCNBlock(causal=True) (causal_conv.py:74-75,104-105) in the three full-band
+    models; golden from the reference's own block class (tests/golden/make_golden.py: causal_plus)."""
+    g, gi = golden("plus_small_causal"), golden("plus_small")
+    cfg = dict(small_plus_cfg(), causal_tcn=True)
+    st = {}
+    out = O.fullsubnet_plus_forward(O.make_params_plus(cfg, seed=14), cfg, gi["mag"], gi["real"], gi["imag"], stages=st)
+    assert O.rel_l2(out, g["out"]) < TOL and O.rel_l2(st["fb_out"], g["fb_out"]) < TOL
+    import torch
+    from oracle.torch_port import TorchPort
+    port = TorchPort(O.make_params_plus(cfg, seed=14), cfg, "plus", dtype=torch.float64)
+    outs = np.concatenate([port.forward(*(torch.from_numpy(gi[k][b:b + 1]) for k in ("mag", "real", "imag"))).numpy() for b in range(3)])
+    assert O.rel_l2(outs, g["out"]) < TOL
