@@ -73,18 +73,20 @@ struct fsn_model {
         int wsB = 0, wsT = 0;
         DevBuf fbin, fbout, xa, xb, y1, y2, stats, mu, ximg, magpad, fbx, hseq;
         DevBuf x0, xr;                                 // time-major fb input / relu'd last residual
+        DevBuf fbo;                                    // time-major full-band outputs [(branch, b, t), Cp] (fused-unfold path)
+        bool fbo_valid = false;                        // the last forward of this lane wrote fbo instead of fbout
         DevBuf tsse_scale, sb_rowsum;
         DevBuf xn, sigma;                              // pre-normalised inputs / sub-band std for the non-default norm types
         alignas(64) unsigned char mapX0[128], mapXa[128], mapXb[128], mapXr[128], mapY2[128];
         cudaEvent_t ev_front = nullptr, ev_lstm = nullptr;   // front end written / LSTM finished reading this lane
         bool used = false;                             // ev_lstm has been recorded (a pipelined batch ran / may still run in this lane)
         void release_all() {
-            DevBuf* all[] = {&fbin, &fbout, &xa, &xb, &y1, &y2, &stats, &mu, &ximg, &magpad, &fbx, &hseq, &x0, &xr, &tsse_scale, &sb_rowsum, &xn, &sigma};
+            DevBuf* all[] = {&fbin, &fbout, &xa, &xb, &y1, &y2, &stats, &mu, &ximg, &magpad, &fbx, &hseq, &x0, &xr, &fbo, &tsse_scale, &sb_rowsum, &xn, &sigma};
             for (auto* b : all) b->release();
         }
     } lane[2];
     int last_lane = 0;
-    DevBuf cstate, stage_in[3], stage_out;             // LSTM-side scratch (one LSTM runs at a time), host-entry staging
+    DevBuf cstate, mask_tmp, stage_in[3], stage_out;   // LSTM-side scratch (one LSTM runs at a time), host-entry staging
     // tcgen05 TCN (FullSubNet+): folded / padded weights, per-block tensor maps, time-major activations
     bool tcn5 = false;
     int Cp = 0, tcnNT = 0, tcnNtiles = 0, num_sms = 148;
@@ -96,7 +98,7 @@ struct fsn_model {
     // tuning knobs, read ONCE at fsn_model_create (never on the forward path): FSN_LSTM_IMPL overrides cfg.lstm_impl,
     // FSN_NO_WS=1 keeps the full-band LSTM of fullsubnet.Model off the weight-stationary kernel
     int env_impl = 0;
-    bool env_no_ws = false;
+    bool env_no_ws = false, env_no_xfuse = false;      // FSN_NO_XFUSE=1: packed sub-band images instead of the fused unfold (A/B only)
     // pipelined execution: front-end stream, LSTM stream (higher priority), copy-in / copy-out streams, per-slot events
     cudaStream_t s_front = nullptr, s_lstm = nullptr, s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in = nullptr, ev_plain = nullptr;   // caller's inputs ready / last plain forward finished
@@ -370,6 +372,7 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     m->cfg = c;
     { const char* e = getenv("FSN_LSTM_IMPL"); if (e && *e) m->env_impl = atoi(e); }
     { const char* e = getenv("FSN_NO_WS"); m->env_no_ws = e && atoi(e) != 0; }
+    { const char* e = getenv("FSN_NO_XFUSE"); m->env_no_xfuse = e && atoi(e) != 0; }
     build_specs(m);
     for (int i = 0; i < fsn_model::NEV; ++i) { cudaEventCreate(&m->ev0[i]); cudaEventCreate(&m->ev1[i]); cudaEventCreate(&m->evf0[i]); cudaEventCreate(&m->evf1[i]); }
     { cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev); if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) m->num_sms = prop.multiProcessorCount; }
@@ -381,7 +384,7 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
 extern "C" void fsn_model_destroy(fsn_model* m) {
     if (!m) return;
     cudaDeviceSynchronize();
-    DevBuf* all[] = {&m->arena, &m->sb_tc5_stream, &m->sb_tc5_bias, &m->cstate, &m->stage_in[0], &m->stage_in[1], &m->stage_in[2],
+    DevBuf* all[] = {&m->arena, &m->sb_tc5_stream, &m->sb_tc5_bias, &m->cstate, &m->mask_tmp, &m->stage_in[0], &m->stage_in[1], &m->stage_in[2],
                      &m->stage_out, &m->tW1, &m->tW2, &m->tWfc, &m->tS1, &m->tS2b, &m->tBfc, &m->ws_h, &m->ws_bar};
     for (auto* b : all) b->release();
     for (auto& ln : m->lane) {
@@ -519,6 +522,12 @@ static int pick_impl(const fsn_model* m) {
     if (impl == FSN_LSTM_AUTO) impl = (m->tc5_ok || m->tc5r_ok) ? FSN_LSTM_TCGEN05 : FSN_LSTM_MMA;
     return impl;
 }
+// Fused unfold: the two-layer tcgen05 kernel builds its input tiles itself (k_lstm_tc5d.cu, x-tile builders) from the window source
+// and the full-band outputs -- for the per-utterance norms; the per-frame cumulative norms keep the packed images.
+static bool use_xfuse(const fsn_model* m) {
+    return pick_impl(m) == FSN_LSTM_TCGEN05 && m->tc5_ok && !m->env_no_xfuse &&
+           (m->cfg.norm_type == FSN_NORM_OFFLINE_LAPLACE || m->cfg.norm_type == FSN_NORM_OFFLINE_GAUSSIAN);
+}
 // tcgen05 requested, but the geometry is outside the fused two-layer kernel: run the layer-wise kernel (k_lstm_tc5r.cu)
 static bool use_layerwise(const fsn_model* m) { return pick_impl(m) == FSN_LSTM_TCGEN05 && !m->tc5_ok && m->tc5r_ok; }
 
@@ -541,7 +550,7 @@ static int ensure_ws(fsn_model* m, fsn_model::Lane& ln, int B, int T, cudaStream
     // images are re-zeroed whenever the geometry changes (rows beyond B*F and k >= I must stay zero)
     const size_t img_bytes = (size_t)ntiles * Tp * 16384;
     if (regeo) { ln.ximg.release(); }
-    e |= ln.ximg.ensure(img_bytes, true, s);
+    if (!use_xfuse(m)) e |= ln.ximg.ensure(img_bytes, true, s);
     // LSTM-side scratch: shared by both lanes (LSTM launches are serialised on the LSTM stream)
     int ra = 0;
     size_t cs = lstm_mma_cstate_bytes(c.num_layers, rows, c.sb_hidden, &ra);
@@ -569,6 +578,7 @@ static int ensure_ws(fsn_model* m, fsn_model::Lane& ln, int B, int T, cudaStream
         e |= ln.y1.ensure(trows * 512 * 4, true, s);
         e |= ln.y2.ensure(trows * 512 * 4, true, s);
         e |= ln.stats.ensure((size_t)8 * 2 * 3 * B * 2 * sizeof(double), true, s);
+        if (use_xfuse(m)) e |= ln.fbo.ensure(trows * m->Cp * 4, true, s);
         if (!e && regeo) {
             if (make_tmap_f32_2d(ln.mapX0, ln.x0.p, trows, m->Cp, 128) || make_tmap_f32_2d(ln.mapXa, ln.xa.p, trows, m->Cp, 128) ||
                 make_tmap_f32_2d(ln.mapXb, ln.xb.p, trows, m->Cp, 128) || make_tmap_f32_2d(ln.mapXr, ln.xr.p, trows, m->Cp, 128) ||
@@ -586,7 +596,10 @@ static int ensure_ws(fsn_model* m, fsn_model::Lane& ln, int B, int T, cudaStream
     return FSN_OK;
 }
 
-static int run_sb_lstm(fsn_model* m, fsn_model::Lane& ln, int B, int T, float* d_out, cudaStream_t s) {
+// d_enh != null: write the enhanced spectrum (decompress_cIRM x noisy) instead of the mask -- fused into the epilogue of the tcgen05
+// kernels, a separate pass over a scratch mask for the generic kernel
+static int run_sb_lstm(fsn_model* m, fsn_model::Lane& ln, int B, int T, float* d_out, const XSrc& xs, const float* d_real, const float* d_imag,
+                       float* d_enh, cudaStream_t s) {
     const fsn_config& c = m->cfg;
     const int F = c.num_freqs, Tp = T + c.look_ahead, rows = B * F, ntiles = (rows + 127) / 128;
     const int impl = pick_impl(m);
@@ -619,6 +632,7 @@ static int run_sb_lstm(fsn_model* m, fsn_model::Lane& ln, int B, int T, float* d
             a.cstate = static_cast<float*>(m->cstate.p);
             a.out = d_out; a.F = F; a.la = c.look_ahead;
             a.act = c.sb_act; a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU; a.last = (l == c.num_layers - 1);
+            a.nreal = d_real; a.nimag = d_imag; a.enh = reinterpret_cast<float2*>(d_enh);
             int e = launch_lstm_tc5r(a, s);
             if (e) return fail(FSN_ECUDA, "layer-wise tcgen05 LSTM launch failed (layer %d): %s", l, cudaGetErrorString((cudaError_t)e));
             m->launches++;
@@ -632,6 +646,8 @@ static int run_sb_lstm(fsn_model* m, fsn_model::Lane& ln, int B, int T, float* d
         a.fc_b = P(m, "sb_model.fc_output_layer.bias");
         a.H = c.sb_hidden; a.I = m->Isb; a.rows = rows; a.Tp = Tp;
         a.img = static_cast<const __half*>(ln.ximg.p); a.ntiles = ntiles;
+        a.xs = xs;
+        a.nreal = d_real; a.nimag = d_imag; a.enh = reinterpret_cast<float2*>(d_enh);
         a.cstate = static_cast<float*>(m->cstate.p);
         a.out = d_out; a.F = F; a.la = c.look_ahead; a.act = c.sb_act; a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU;
         int e = launch_lstm_tc5_dbuf(a, s);
@@ -651,8 +667,13 @@ static int run_sb_lstm(fsn_model* m, fsn_model::Lane& ln, int B, int T, float* d
         lstm_mma_cstate_bytes(c.num_layers, rows, c.sb_hidden, &a.rows_alloc);
         a.out = d_out; a.O = c.output_size; a.F = F; a.la = c.look_ahead; a.act = c.sb_act;
         a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU;
+        if (d_enh) {                                                    // generic kernel: mask into a scratch buffer, then one fused post-processing pass
+            if (m->mask_tmp.ensure((size_t)B * 2 * F * T * 4, false, s)) return fail(FSN_ECUDA, "allocation failed");
+            a.out = static_cast<float*>(m->mask_tmp.p);
+        }
         int e = launch_lstm_mma(a, s);
         if (e) return fail(FSN_ECUDA, "mma LSTM launch failed: %s", cudaGetErrorString((cudaError_t)e));
+        if (d_enh) { launch_apply_cirm_planar(a.out, d_real, d_imag, reinterpret_cast<float2*>(d_enh), B, F, T, s); m->launches++; }
     }
     m->launches++;
     return FSN_OK;
@@ -662,8 +683,10 @@ static int run_sb_lstm(fsn_model* m, fsn_model::Lane& ln, int B, int T, float* d
 // the sub-band LSTM on stream `sl` (== s for the plain entry point; the pipelined entry points pass the LSTM stream, ordered
 // after the front end by the lane's ev_front).
 static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
-                        float* d_out, cudaStream_t s, cudaStream_t sl) {
-    if (!m || !d_mag || !d_out) return fail(FSN_EINVAL, "null argument");
+                        float* d_out, float* d_enh, cudaStream_t s, cudaStream_t sl) {
+    if (!m || !d_mag || (!d_out && !d_enh)) return fail(FSN_EINVAL, "null argument");
+    if (d_enh && (!d_real || !d_imag)) return fail(FSN_EINVAL, "the enhanced-spectrum output needs the noisy real and imaginary planes");
+    if (d_enh && m->cfg.output_size != 2) return fail(FSN_EINVAL, "the enhanced-spectrum output needs output_size 2 (a complex mask)");
     if (!m->finalized) return fail(FSN_ESTATE, "fsn_model_finalize has not been called");
     const fsn_config& c = m->cfg;
     if (B < 1 || T < 1) return fail(FSN_EINVAL, "bad batch/frames");
@@ -679,6 +702,9 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
     const int evi = (int)(m->nfwd % fsn_model::NEV);
     cudaEventRecord(m->evf0[evi], s);
 
+    const bool xfuse = use_xfuse(m);
+    ln.fbo_valid = xfuse && c.model_kind == FSN_KIND_PLUS;
+    XSrc xs{};
     SbPackLaunch sp{};
     sp.B = B; sp.F = F; sp.Tp = Tp; sp.Ns = c.sb_num_neighbors; sp.Nf = c.fb_num_neighbors; sp.P = Pp;
     sp.mu = static_cast<float*>(ln.mu.p);
@@ -774,6 +800,7 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
             g3.epi = EPI5_OUT; g3.Kp = Cp; g3.NT = m->tcnNT; g3.ntiles_n = m->tcnNtiles; g3.Npad = Cp;
             for (int b = 0; b < 3; ++b) g3.bias[b] = static_cast<const float*>(m->tBfc.p) + (size_t)b * Cp;
             g3.out = static_cast<float*>(ln.fbout.p); g3.F = F; g3.P = Pp; g3.act = c.fb_act;
+            if (xfuse) { g3.out_tm = static_cast<float*>(ln.fbo.p); g3.ldY = Cp; }
             int e = launch_gemm_tc5(ln.mapXr, m->mapWfc, g3, m->num_sms, s);
             if (e) return fail(FSN_ECUDA, "TCN output GEMM launch failed: %s", cudaGetErrorString((cudaError_t)e));
             m->launches++;
@@ -782,6 +809,14 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
         sp.win = static_cast<const float*>(ln.fbin.p); sp.Pw = Pp;      // post-attention mag branch (fullsubnet_plus.py:182)
         sp.nfb = 3;
         for (int b = 0; b < 3; ++b) sp.fb[b] = static_cast<const float*>(ln.fbout.p) + (size_t)b * B * F * Pp;
+        if (xfuse) {                                                        // time-major views: window = x0 (branch 0), outputs = fbo
+            const long long rowsB = (long long)Tp * m->Cp;
+            for (int b = 0; b < 3; ++b) sp.fb[b] = static_cast<const float*>(ln.fbo.p) + (size_t)b * B * rowsB;
+            sp.fb_sb = rowsB; sp.fb_sf = 1; sp.fb_st = m->Cp;
+            xs.win = static_cast<const float*>(ln.x0.p); xs.win_sb = rowsB; xs.win_sf = 1; xs.win_st = m->Cp;
+            for (int b = 0; b < 3; ++b) xs.fb[b] = sp.fb[b];
+            xs.fb_sb = rowsB; xs.fb_sf = 1; xs.fb_st = m->Cp;
+        }
     } else {
         TsseLaunch ta{};
         ta.x[0] = d_mag; ta.nbranch = 1; ta.B = B; ta.F = F; ta.T = T; ta.Tp = Tp; ta.P = Pp; ta.attention = 0;
@@ -835,16 +870,25 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
         sp.win = static_cast<const float*>(ln.magpad.p); sp.Pw = Pp;    // raw padded magnitude (fullsubnet.py:94)
         sp.nfb = 1;
         sp.fb[0] = static_cast<const float*>(ln.fbout.p);
+        if (xfuse) {                                                        // frequency-major views of the padded magnitude / the full-band output
+            xs.win = sp.win; xs.win_sb = (long long)F * Pp; xs.win_sf = Pp; xs.win_st = 1;
+            xs.fb[0] = sp.fb[0]; xs.fb_sb = (long long)F * Pp; xs.fb_sf = Pp; xs.fb_st = 1;
+        }
     }
-    launch_sb_stats(sp, s); m->launches += 2;
-    launch_sb_pack(sp, s); m->launches++;
+    launch_sb_stats(sp, s); m->launches += (sp.fb_st > 1) ? 3 : 2;
+    if (xfuse) {
+        xs.nfb = sp.nfb; xs.Ns = sp.Ns; xs.Nf = sp.Nf; xs.mu = sp.mu; xs.sigma = sp.sigma;
+        xs.gauss = (c.norm_type == FSN_NORM_OFFLINE_GAUSSIAN) ? 1 : 0;
+    } else {
+        launch_sb_pack(sp, s); m->launches++;
+    }
     cudaEventRecord(m->evf1[evi], s);
     if (sl != s) {                                                      // pipelined: the LSTM stream picks the lane up when the front end is done
         CK(cudaEventRecord(ln.ev_front, s));
         CK(cudaStreamWaitEvent(sl, ln.ev_front, 0));
     }
     cudaEventRecord(m->ev0[evi], sl);
-    rc = run_sb_lstm(m, ln, B, T, d_out, sl);
+    rc = run_sb_lstm(m, ln, B, T, d_out, xs, d_real, d_imag, d_enh, sl);
     cudaEventRecord(m->ev1[evi], sl);
     if (rc) return rc;
     m->nfwd++;
@@ -871,7 +915,7 @@ static int ensure_pipeline(fsn_model* m) {
 
 // one pipelined batch: inputs are ready once `ready` (an event, may be null) has fired; returns the lane used
 static int submit_impl(fsn_model* m, cudaEvent_t ready, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
-                       float* d_out, int* lane_out) {
+                       float* d_out, float* d_enh, int* lane_out) {
     int rc = ensure_pipeline(m);
     if (rc) return rc;
     const bool overlap = (m->cfg.model_kind == FSN_KIND_PLUS);           // fullsubnet.Model: its full-band LSTM is a cooperative launch and
@@ -881,7 +925,7 @@ static int submit_impl(fsn_model* m, cudaEvent_t ready, const float* d_mag, cons
     if (ready) CK(cudaStreamWaitEvent(sf, ready, 0));
     if (m->plain_pending) { CK(cudaStreamWaitEvent(sf, m->ev_plain, 0)); CK(cudaStreamWaitEvent(m->s_lstm, m->ev_plain, 0)); }
     if (ln.used) CK(cudaStreamWaitEvent(sf, ln.ev_lstm, 0));              // the LSTM that read this lane has finished
-    rc = forward_impl(m, ln, d_mag, d_real, d_imag, B, T, d_out, sf, m->s_lstm);
+    rc = forward_impl(m, ln, d_mag, d_real, d_imag, B, T, d_out, d_enh, sf, m->s_lstm);
     if (rc) return rc;
     CK(cudaEventRecord(ln.ev_lstm, m->s_lstm));
     ln.used = true;
@@ -890,13 +934,13 @@ static int submit_impl(fsn_model* m, cudaEvent_t ready, const float* d_mag, cons
     return FSN_OK;
 }
 
-extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
-                                 float* d_out, void* stream) {
+static int forward_plain(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                         float* d_out, float* d_enh, void* stream) {
     if (!m) return fail(FSN_EINVAL, "null argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     for (auto& ln : m->lane)                                             // batches still in flight in the pipeline share the scratch buffers
         if (ln.used) CK(cudaStreamWaitEvent(s, ln.ev_lstm, 0));
-    int rc = forward_impl(m, m->lane[0], d_mag, d_real, d_imag, B, T, d_out, s, s);
+    int rc = forward_impl(m, m->lane[0], d_mag, d_real, d_imag, B, T, d_out, d_enh, s, s);
     if (rc) return rc;
     if (!m->ev_plain) CK(cudaEventCreateWithFlags(&m->ev_plain, cudaEventDisableTiming));
     CK(cudaEventRecord(m->ev_plain, s));
@@ -904,13 +948,34 @@ extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* 
     return FSN_OK;
 }
 
-extern "C" int fsn_model_submit(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
-                                float* d_out, void* stream) {
+static int submit_plain(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                        float* d_out, float* d_enh, void* stream) {
     if (!m) return fail(FSN_EINVAL, "null argument");
     int rc = ensure_pipeline(m);
     if (rc) return rc;
     CK(cudaEventRecord(m->ev_in, static_cast<cudaStream_t>(stream)));    // everything enqueued on the caller's stream so far (the inputs)
-    return submit_impl(m, m->ev_in, d_mag, d_real, d_imag, B, T, d_out, nullptr);
+    return submit_impl(m, m->ev_in, d_mag, d_real, d_imag, B, T, d_out, d_enh, nullptr);
+}
+
+extern "C" int fsn_model_forward(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                                 float* d_out, void* stream) {
+    if (!d_out) return fail(FSN_EINVAL, "null argument");
+    return forward_plain(m, d_mag, d_real, d_imag, B, T, d_out, nullptr, stream);
+}
+extern "C" int fsn_model_forward_enhance(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                                         float* d_enh, void* stream) {
+    if (!d_enh) return fail(FSN_EINVAL, "null argument");
+    return forward_plain(m, d_mag, d_real, d_imag, B, T, nullptr, d_enh, stream);
+}
+extern "C" int fsn_model_submit(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                                float* d_out, void* stream) {
+    if (!d_out) return fail(FSN_EINVAL, "null argument");
+    return submit_plain(m, d_mag, d_real, d_imag, B, T, d_out, nullptr, stream);
+}
+extern "C" int fsn_model_submit_enhance(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                                        float* d_enh, void* stream) {
+    if (!d_enh) return fail(FSN_EINVAL, "null argument");
+    return submit_plain(m, d_mag, d_real, d_imag, B, T, nullptr, d_enh, stream);
 }
 
 extern "C" int fsn_model_last_lane(const fsn_model* m) { return m ? m->last_lane : 0; }
@@ -990,7 +1055,7 @@ extern "C" int fsn_model_forward_host_async(fsn_model* m, const float* h_mag, co
     if (m->d2h_used[slot]) CK(cudaStreamWaitEvent(m->s_lstm, m->ev_d2h[slot], 0));   // the copy-out that read this output slot is done
     int used = 0;
     rc = submit_impl(m, m->ev_h2d[slot], static_cast<const float*>(m->a_in[slot][0].p), static_cast<const float*>(m->a_in[slot][1].p),
-                     static_cast<const float*>(m->a_in[slot][2].p), B, T, static_cast<float*>(m->a_out[slot].p), &used);
+                     static_cast<const float*>(m->a_in[slot][2].p), B, T, static_cast<float*>(m->a_out[slot].p), nullptr, &used);
     if (rc) return rc;
     CK(cudaStreamWaitEvent(m->s_out, ln.ev_lstm, 0));
     CK(cudaMemcpyAsync(h_out, m->a_out[slot].p, out_bytes, cudaMemcpyDeviceToHost, m->s_out));
@@ -1018,6 +1083,11 @@ extern "C" int fsn_model_get_stage(fsn_model* m, const char* name, float* d_dst,
     const std::string n(name);
     if (n == "fb_in" || n == "fb_out") {
         if (numel != (int64_t)nbr * B * F * Tp) return fail(FSN_EINVAL, "%s needs %lld elements", name, (long long)nbr * B * F * Tp);
+        if (n == "fb_out" && ln.fbo_valid) {                            // fused-unfold path: the outputs exist time-major only
+            launch_tm_to_fm(static_cast<const float*>(ln.fbo.p), d_dst, nbr * B, F, Tp, m->Cp, s);
+            CK(cudaGetLastError());
+            return FSN_OK;
+        }
         const void* src = (n == "fb_in") ? ln.fbin.p : ln.fbout.p;
         CK(cudaMemcpy2DAsync(d_dst, (size_t)Tp * 4, src, (size_t)Pp * 4, (size_t)Tp * 4, (size_t)nbr * B * F, cudaMemcpyDeviceToDevice, s));
         return FSN_OK;

@@ -40,6 +40,13 @@ __device__ __forceinline__ float apply_act(float y, int act) {
     return y;
 }
 
+// decompress_cIRM (audio_zen/acoustics/mask.py:60-63, K = 10, limit = 9.9): limit*(m >= limit) - limit*(m <= -limit) + m*(|m| < limit)
+// is a clamp; then -K log((K - m) / (K + m)).
+__device__ __forceinline__ float decompress_cirm(float v) {
+    v = (v >= 9.9f) ? 9.9f : ((v <= -9.9f) ? -9.9f : v);
+    return -10.f * logf((10.f - v) / (10.f + v));
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);

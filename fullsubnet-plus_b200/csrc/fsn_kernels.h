@@ -51,6 +51,7 @@ struct SbPackLaunch {
     const float* fb[3];      // [B, F, P] full-band outputs (nfb of them)
     int nfb, P;
     int B, F, Tp, Ns, Nf;    // neighbours
+    long long fb_sb, fb_sf, fb_st;   // sb_stats only: element strides of fb[] (0, 0, 0 = the default [B, F, P] layout)
     float* mu;               // [B] utterance mean of the concatenated sub-band input
     float* sigma;            // [B] unbiased std (offline_gaussian_norm only)
     float* rowsum;           // [B, 1 + nfb, F, 2] scratch: row sums and sums of squares
@@ -66,7 +67,10 @@ void launch_pad_copy(const float* x, float* y, int B, int F, int T, int P, cudaS
 // full-band LSTM input: [B, F, P] fp32 -> [Tp, Bpad, Ipad] fp16 (rows >= B and k >= F zero)
 void launch_fb_pack(const float* x, __half* y, int B, int F, int Tp, int P, int rows_pad, int Ipad, cudaStream_t s);
 
+void launch_tm_to_fm(const float* x, float* y, int Z, int F, int Tp, int ld, cudaStream_t s);
 void launch_apply_cirm(const float* crm, const float2* noisy, float2* enh, int B, int F, int T, cudaStream_t s);
+// same with the noisy spectrum as two planes [B, F, T] (the model's own real / imag inputs)
+void launch_apply_cirm_planar(const float* crm, const float* nreal, const float* nimag, float2* enh, int B, int F, int T, cudaStream_t s);
 
 // streaming step kernels (k_front.cu): one frame of the cumulative norms with running sums carried in global memory
 struct StreamNormLaunch { const float* x; float* y; double* cum; int B, F, P, n, type; };       // x [B,F] -> y [B,F,P] (t = 0)
@@ -118,6 +122,19 @@ bool lstm_ws_supported(int L, int H, int Ipad, int rows, int num_sms);
 int launch_lstm_ws(const LstmWsLaunch& a, cudaStream_t s);
 
 // ---- k_lstm_tc5d.cu --------------------------------------------------------------------------
+// Where the sub-band LSTM's x-tile builders find the (never materialised) unfolded input: the window source and the full-band
+// outputs as strided [sample, frequency, frame] views, plus the per-sample normaliser.  reference: base_model.py:15-47 (unfold),
+// fullsubnet_plus.py:167-202 / fullsubnet.py:90-111 (concat + norm).
+struct XSrc {
+    const float* win;                      // null: the kernel streams pre-packed images (LstmTc5Launch::img) instead
+    long long win_sb, win_sf, win_st;      // element strides: sample, frequency bin, frame
+    const float* fb[3];
+    long long fb_sb, fb_sf, fb_st;
+    int nfb, Ns, Nf;
+    const float* mu;                       // [B] utterance mean of the concatenated input (sb_stats_kernel)
+    const float* sigma;                    // [B] unbiased std (offline_gaussian_norm), else unused
+    int gauss;                             // 0: x / (mu + 1e-5); 1: (x - mu) / (sigma + 1e-5)
+};
 struct LstmTc5Launch {
     const __half* wstream;    // packed weight stream (fsn_tc5_pack_weights)
     const float* bias;        // [2][4H] permuted to the stream's gate-column order
@@ -125,12 +142,16 @@ struct LstmTc5Launch {
     const float* fc_b;        // [2]
     int H, I;
     int rows, Tp;
-    const __half* img; int ntiles;   // [ntiles, Tp, 16 KB]
+    const __half* img; int ntiles;   // [ntiles, Tp, 16 KB] pre-packed SW128 images (used when xs.win is null)
+    XSrc xs;                  // fused unfold + norm: the kernel builds the image of every step itself
     float* cstate;            // [ntiles][2 layers][H/16 chunks][4][128][4] fp32
     float* out; int F, la;
     int act;                  // FSN_ACT_* applied to the Linear output (sb_output_activate_function, sequence_model.py:120-121)
     int fast;
     int gru;                  // 1: pseudo-gate GRU cell
+    // fused post-processing (inferencer.py:152-157): when enh != null the epilogue decompresses the cIRM and multiplies it with the
+    // noisy spectrum (planes [B, F, T]) instead of writing the mask: enh [B, F, T] complex64 (interleaved re, im)
+    const float* nreal; const float* nimag; float2* enh;
 };
 size_t lstm_tc5_cstate_bytes(int ntiles, int H);
 bool lstm_tc5_supported(int L, int H, int I, int O);
@@ -149,6 +170,7 @@ struct LstmTc5rLaunch {
     float* out; int F, la;    // last layer: mask [B, 2, F, Tp - la]
     int act;                  // FSN_ACT_* on the Linear output (last layer)
     int fast, gru, last;
+    const float* nreal; const float* nimag; float2* enh;   // fused post-processing, see LstmTc5Launch
 };
 bool lstm_tc5r_supported(int H, int O);
 size_t lstm_tc5r_cstate_bytes(int ntiles, int H);
@@ -170,7 +192,8 @@ struct GemmTc5Launch {
     const double* stats_in; double count_in;
     float* Y; int ldY;                         // PRELU_STATS: output; GLN_RES: new residual stream
     const float* Xold; float* Xrelu;           // GLN_RES: residual input, optional relu'd copy
-    float* out; int F, P, act;                 // OUT: [Z, F, P]
+    float* out; int F, P, act;                 // OUT: [Z, F, P] (frequency-major) ...
+    float* out_tm;                             // ... or, when set, time-major [(branch, b, t), ldY] (read by the LSTM's x-tile builders)
 };
 int make_tmap_f32_2d(void* out_map /*128 B, 64 B aligned*/, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 int launch_gemm_tc5(const void* mapA, const void* mapB, GemmTc5Launch a, int num_sms, cudaStream_t s);

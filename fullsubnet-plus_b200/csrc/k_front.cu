@@ -343,6 +343,21 @@ __global__ void __launch_bounds__(256) sb_rowsum_kernel(SbPackLaunch a) {
     if (lane == 0) { a.rowsum[2 * (size_t)r] = acc; a.rowsum[2 * (size_t)r + 1] = acq; }
 }
 
+// window-source rows only, written into the [b][nsrc][f] slots of the full table (the full-band sources come from sb_colsum_kernel)
+__global__ void __launch_bounds__(256) sb_rowsum_strided_kernel(SbPackLaunch a, int nsrc) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int F = a.F, Tp = a.Tp;
+    const int r0 = blockIdx.x * 8 + warp;                      // (b, f)
+    if (r0 >= a.B * F) return;
+    const int b = r0 / F, f = r0 % F;
+    const float* row = a.win + ((size_t)b * F + f) * a.Pw;
+    float acc = 0.f, acq = 0.f;
+    for (int t = lane; t < Tp; t += 32) { const float v = row[t]; acc += v; acq = fmaf(v, v, acq); }
+    acc = warp_sum(acc); acq = warp_sum(acq);
+    const size_t r = ((size_t)b * nsrc) * F + f;
+    if (lane == 0) { a.rowsum[2 * r] = acc; a.rowsum[2 * r + 1] = acq; }
+}
+
 __global__ void __launch_bounds__(256) sb_stats_kernel(SbPackLaunch a) {
     const int b = blockIdx.x, F = a.F, Tp = a.Tp, nsrc = 1 + a.nfb;
     __shared__ double red[16];
@@ -371,8 +386,28 @@ __global__ void __launch_bounds__(256) sb_stats_kernel(SbPackLaunch a) {
     }
 }
 
+// Same sums for full-band outputs stored TIME-major (fb_st > 1: element (b, f, t) at fb[q] + b fb_sb + f fb_sf + t fb_st with
+// fb_sf == 1): one CTA per (sample, source), threads over bins, every thread walks the frames -> coalesced rows.
+__global__ void __launch_bounds__(256) sb_colsum_kernel(SbPackLaunch a) {
+    const int b = blockIdx.x, q = blockIdx.y, F = a.F, Tp = a.Tp, nsrc = 1 + a.nfb;
+    const float* base = ((q == 0) ? a.fb[0] : (q == 1) ? a.fb[1] : a.fb[2]) + (size_t)b * a.fb_sb;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        float acc = 0.f, acq = 0.f;
+        for (int t = 0; t < Tp; ++t) { const float v = base[(size_t)t * a.fb_st + f]; acc += v; acq = fmaf(v, v, acq); }
+        const size_t r = ((size_t)b * nsrc + 1 + q) * F + f;
+        a.rowsum[2 * r] = acc; a.rowsum[2 * r + 1] = acq;
+    }
+}
+
 void launch_sb_stats(const SbPackLaunch& a, cudaStream_t s) {
-    sb_rowsum_kernel<<<(a.B * (1 + a.nfb) * a.F + 7) / 8, 256, 0, s>>>(a);
+    if (a.fb_st > 1) {                                           // window source frequency-major, full-band outputs time-major
+        SbPackLaunch w = a;
+        w.nfb = 0;                                               // rows of the window source only ...
+        sb_rowsum_strided_kernel<<<(a.B * a.F + 7) / 8, 256, 0, s>>>(w, 1 + a.nfb);
+        sb_colsum_kernel<<<dim3(a.B, a.nfb), 256, 0, s>>>(a);    // ... the full-band outputs by columns
+    } else {
+        sb_rowsum_kernel<<<(a.B * (1 + a.nfb) * a.F + 7) / 8, 256, 0, s>>>(a);
+    }
     sb_stats_kernel<<<a.B, 256, 0, s>>>(a);
 }
 
@@ -571,9 +606,34 @@ __global__ void apply_cirm_kernel(const float* crm, const float2* noisy, float2*
     const float2 x = noisy[i];
     enh[i] = make_float2(m[0] * x.x - m[1] * x.y, m[1] * x.x + m[0] * x.y);
 }
+__global__ void apply_cirm_planar_kernel(const float* crm, const float* nreal, const float* nimag, float2* enh, int FT, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t b = i / FT, e = i % FT;
+    const float m0 = decompress_cirm(crm[(b * 2 + 0) * FT + e]), m1 = decompress_cirm(crm[(b * 2 + 1) * FT + e]);
+    const float xr = nreal[i], xi = nimag[i];
+    enh[i] = make_float2(m0 * xr - m1 * xi, m1 * xr + m0 * xi);
+}
+void launch_apply_cirm_planar(const float* crm, const float* nreal, const float* nimag, float2* enh, int B, int F, int T, cudaStream_t s) {
+    const size_t n = (size_t)B * F * T;
+    apply_cirm_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(crm, nreal, nimag, enh, F * T, n);
+}
 void launch_apply_cirm(const float* crm, const float2* noisy, float2* enh, int B, int F, int T, cudaStream_t s) {
     const size_t n = (size_t)B * F * T;
     apply_cirm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(crm, noisy, enh, F * T, n);
+}
+
+// test hook: time-major [(z, t), ld] -> frequency-major [z, F, Tp]
+__global__ void tm_to_fm_kernel(const float* x, float* y, int Z, int F, int Tp, int ld) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)Z * F * Tp) return;
+    const int t = (int)(i % Tp), f = (int)((i / Tp) % F);
+    const size_t z = i / ((size_t)Tp * F);
+    y[i] = x[(z * Tp + t) * ld + f];
+}
+void launch_tm_to_fm(const float* x, float* y, int Z, int F, int Tp, int ld, cudaStream_t s) {
+    const size_t n = (size_t)Z * F * Tp;
+    tm_to_fm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, Z, F, Tp, ld);
 }
 
 __global__ void pad_copy_kernel(const float* x, float* y, int rows, int T, int P) {

@@ -205,16 +205,23 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             if (dr) dr[i4] = make_float4(fmaxf(o[0], 0.f), fmaxf(o[1], 0.f), fmaxf(o[2], 0.f), fmaxf(o[3], 0.f));
                         }
                     }
+                } else if (a.out_tm) {
+                    // time-major output [(branch, b, t), Npad]: the layout the sub-band LSTM's x-tile builders read (k_lstm_tc5d.cu);
+                    // each thread owns a row -> 64 contiguous bytes per chunk (pad columns: zero weights, zero bias)
+                    if (valid) {
+                        float4* dst = reinterpret_cast<float4*>(a.out_tm + grow * a.ldY + n);
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n) + i4);
+                            dst[i4] = make_float4(apply_act(__uint_as_float(v[4 * i4]) + b4.x, a.act), apply_act(__uint_as_float(v[4 * i4 + 1]) + b4.y, a.act),
+                                                  apply_act(__uint_as_float(v[4 * i4 + 2]) + b4.z, a.act), apply_act(__uint_as_float(v[4 * i4 + 3]) + b4.w, a.act));
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        if (valid && n + i < a.F) {
-                            float t = __uint_as_float(v[i]) + __ldg(bias + n + i);
-                            if (a.act == FSN_ACT_RELU) t = fmaxf(t, 0.f);
-                            else if (a.act == FSN_ACT_TANH) t = tanhf(t);
-                            else if (a.act == FSN_ACT_RELU6) t = fminf(fmaxf(t, 0.f), 6.f);
-                            a.out[((size_t)z * a.F + n + i) * a.P + tt] = t;
-                        }
+                        if (valid && n + i < a.F)
+                            a.out[((size_t)z * a.F + n + i) * a.P + tt] = apply_act(__uint_as_float(v[i]) + __ldg(bias + n + i), a.act);
                     }
                 }
             }

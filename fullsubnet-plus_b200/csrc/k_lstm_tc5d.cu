@@ -28,7 +28,8 @@ constexpr int D5_STAGE = 4 * D5_SUB; // a ring slot holds a GROUP of up to 4 sub
 constexpr int D5_STAGE_FULL = 16384;
 constexpr int D5_XIMG = 16384;
 constexpr int D5_EPI_WARPS = 16;
-constexpr int D5_THREADS = (D5_EPI_WARPS + 2) * 32;
+constexpr int D5_XB_WARPS = 2;                                  // x-tile builders (fused unfold + norm), 64 threads x 2 rows
+constexpr int D5_THREADS = (D5_EPI_WARPS + 2 + D5_XB_WARPS) * 32;
 constexpr int D5_MAX_SMEM = 227 * 1024;
 
 struct D5Plan { int nstage; size_t total; };
@@ -74,7 +75,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
 
     if (tid == 0) {
         for (int i = 0; i < nstage; ++i) { mbar_init(&full[i], leader ? 2 : 1); mbar_init(&empty[i], 1); }
-        mbar_init(xfull, leader ? 2 : 1); mbar_init(xempty, 1);
+        // x image of a step: either ONE bulk copy of a pre-packed image (producer's expect_tx arrive) or built in place by the
+        // D5_XB_WARPS builder warps (one arrive each); the leader additionally gets the peer's relay arrive
+        const uint32_t xarr = a.xs.win ? D5_XB_WARPS : 1;
+        mbar_init(xfull, leader ? xarr + 1 : xarr); mbar_init(xempty, 1);
         for (int h = 0; h < 2; ++h) { mbar_init(&accfull[h], 1); mbar_init(&accempty[h], D5_EPI_WARPS); }   // 8 warps x 2 CTAs
         mbar_init(&hready[0], 2 * D5_EPI_WARPS); mbar_init(&hready[1], 2 * D5_EPI_WARPS);
         mbar_init(layerdone, 1);
@@ -96,8 +100,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
             const uint8_t* xsrc = reinterpret_cast<const uint8_t*>(a.img) + (size_t)tile * Tp * D5_XIMG;
             int slot = 0; uint32_t ph = 0;
             const uint64_t pol_x = l2_policy_evict_first(), pol_w = l2_policy_evict_last();
-            mbar_arrive_expect_tx(xfull, D5_XIMG);
-            bulk_g2s_hint(ximg, xsrc, D5_XIMG, xfull, pol_x);
+            const bool packed = (a.xs.win == nullptr);
+            if (packed) {
+                mbar_arrive_expect_tx(xfull, D5_XIMG);
+                bulk_g2s_hint(ximg, xsrc, D5_XIMG, xfull, pol_x);
+            }
             constexpr int NKB0 = 1 + KBH, NKB1 = 2 * KBH;           // k-blocks per chunk: x | h0, h0 | h1
             for (int t = 0; t < Tp; ++t) {
                 for (int layer = 0; layer < 2; ++layer) {
@@ -105,7 +112,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                     for (int j = 0; j < NCH; ++j) {
                         const int kb_base = layer == 0 ? j * NKB0 : NCH * NKB0 + j * NKB1;   // k-block index in the per-step stream
                         for (int half = 0; half < 2; ++half) {
-                            if (layer == 1 && j == NCH / 2 && half == 0 && t + 1 < Tp) {     // x_{t+1}: layer 0 of step t is long done
+                            if (packed && layer == 1 && j == NCH / 2 && half == 0 && t + 1 < Tp) {     // x_{t+1}: layer 0 of step t is long done
                                 mbar_wait(xempty, t & 1);
                                 mbar_arrive_expect_tx(xfull, D5_XIMG);
                                 bulk_g2s_hint(ximg, xsrc + (size_t)(t + 1) * D5_XIMG, D5_XIMG, xfull, pol_x);
@@ -230,6 +237,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                 }
             }
         }
+    } else if (warp >= D5_EPI_WARPS + 2) {
+        // ======================= x-tile builders: fused BaseModel.unfold + concat + norm ====
+        // reference base_model.py:15-47, fullsubnet_plus.py:167-202 / fullsubnet.py:90-111.  Row (b, f) of step t is
+        //   [ win(b, reflect(f - Ns .. f + Ns), t) | fb_q(b, reflect(f - Nf .. f + Nf), t), q < nfb ] normalised per utterance,
+        // written as fp16 straight into the SWIZZLE_128B image the layer-0 MMAs read -- the 31x unfolded tensor (392 MB in
+        // fp16 at B = 64) is never written to or read from global memory.  Same arithmetic as sb_pack_kernel (k_front.cu).
+        if (a.xs.win) {
+            const XSrc& xs = a.xs;
+            const int j0 = (warp - (D5_EPI_WARPS + 2)) * 32 + lane;    // rows j0 and j0 + 64: lanes <-> consecutive bins (coalesced loads)
+            const int nw = 2 * xs.Ns + 1, nf = 2 * xs.Nf + 1, I = nw + xs.nfb * nf, nchunk = (I + 7) >> 3;
+            const int F = a.F;
+            int rb[2], rf[2];
+            float inv[2], sub[2];
+            bool ok[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int grow = tile * 128 + j0 + 64 * i;
+                ok[i] = grow < a.rows;
+                rb[i] = ok[i] ? grow / F : 0; rf[i] = ok[i] ? grow % F : 0;
+                const float mu = __ldg(xs.mu + rb[i]);
+                inv[i] = xs.gauss ? 1.0f / (__ldg(xs.sigma + rb[i]) + 1e-5f) : 1.0f / (mu + 1e-5f);
+                sub[i] = xs.gauss ? mu : 0.f;
+                for (int c = 0; c < 8; ++c)                            // columns >= I and rows >= B*F stay zero for the whole launch
+                    *reinterpret_cast<uint4*>(ximg + sw128_offset(j0 + 64 * i, c * 8)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            auto src = [&](int i, int k, int t) -> const float* {
+                if (k < nw) return xs.win + rb[i] * xs.win_sb + reflect_idx(rf[i] + k - xs.Ns, F) * xs.win_sf + t * xs.win_st;
+                const int kk = k - nw, q = kk / nf, jn = kk - q * nf;
+                const float* base = (q == 0) ? xs.fb[0] : (q == 1) ? xs.fb[1] : xs.fb[2];
+                return base + rb[i] * xs.fb_sb + reflect_idx(rf[i] + jn - xs.Nf, F) * xs.fb_sf + t * xs.fb_st;
+            };
+            for (int t = 0; t < Tp; ++t) {
+                if (t > 0) mbar_wait(xempty, (t - 1) & 1);             // the layer-0 MMAs of step t-1 have read the image
+                for (int c = 0; c < nchunk; ++c) {
+                    float v[2][8];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[i][e] = (ok[i] && c * 8 + e < I) ? __ldg(src(i, c * 8 + e, t)) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        if (!ok[i]) continue;
+                        float w[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) w[e] = (c * 8 + e < I) ? fminf(fmaxf((v[i][e] - sub[i]) * inv[i], -65504.f), 65504.f) : 0.f;
+                        *reinterpret_cast<uint4*>(ximg + sw128_offset(j0 + 64 * i, c * 8)) =
+                            make_uint4(pack_half2(w[0], w[1]), pack_half2(w[2], w[3]), pack_half2(w[4], w[5]), pack_half2(w[6], w[7]));
+                    }
+                }
+                fence_proxy_async();                                   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(xfull);
+            }
+        }
     } else {
         // ======================= epilogue warps (both CTAs, own 128 sequences) ==============
         const int cg = warp >> 2;
@@ -263,6 +324,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
         for (int t = 0; t < Tp; ++t) {
             for (int layer = 0; layer < 2; ++layer, ++ls) {
                 float fc0 = 0.f, fc1 = 0.f;
+                float2 nx = make_float2(0.f, 0.f);                 // noisy (re, im) of my output bin, in flight during the chunk loop
+                if (layer == 1 && a.enh && cg == 0 && t >= a.la && grow < a.rows) {
+                    const size_t ni = ((size_t)ob * a.F + of) * Tout + (t - a.la);
+                    nx = make_float2(__ldg(a.nreal + ni), __ldg(a.nimag + ni));
+                }
                 for (int j = 0; j < NCH; ++j) {
                     float4* cp = reinterpret_cast<float4*>(cbase + ((size_t)((layer * NCH + j) * 4 + cg) * 2) * 128 * 4) + r;
                     const float4 c4[2] = {cnext[0], cnext[1]};     // prefetched during the previous chunk
@@ -341,8 +407,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                     if (cg == 0 && t >= a.la && grow < a.rows) {
                         const float o0 = fc0 + fcpart[(128 + r) * 2] + fcpart[(256 + r) * 2] + fcpart[(384 + r) * 2] + fcb0;
                         const float o1 = fc1 + fcpart[(128 + r) * 2 + 1] + fcpart[(256 + r) * 2 + 1] + fcpart[(384 + r) * 2 + 1] + fcb1;
-                        __stcs(&a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)], apply_act(o0, a.act));   // streaming stores: written once
-                        __stcs(&a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)], apply_act(o1, a.act));
+                        if (a.enh) {                                   // fused decompress_cIRM x noisy spectrum (inferencer.py:152-157)
+                            const float m0 = decompress_cirm(apply_act(o0, a.act)), m1 = decompress_cirm(apply_act(o1, a.act));
+                            __stcs(a.enh + ((size_t)ob * a.F + of) * Tout + (t - a.la), make_float2(m0 * nx.x - m1 * nx.y, m1 * nx.x + m0 * nx.y));
+                        } else {
+                            __stcs(&a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)], apply_act(o0, a.act));   // streaming stores: written once
+                            __stcs(&a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)], apply_act(o1, a.act));
+                        }
                     }
                     asm volatile("bar.sync 2, 512;" ::: "memory");
                 }

@@ -195,6 +195,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
             const size_t mrow = ((size_t)tile * Tp + t) * 128 + r;  // my row of the (tile, t) block of Gin / hseq
             const uint4* gsrc = reinterpret_cast<const uint4*>(a.gin + mrow * (size_t)(4 * H) + cg * 32);
             float fc0 = 0.f, fc1 = 0.f;
+            float2 nx = make_float2(0.f, 0.f);                     // noisy (re, im) of my output bin, in flight during the chunk loop
+            if (LAST && a.enh && cg == 0 && t >= a.la && grow < a.rows) {
+                const size_t ni = ((size_t)ob * a.F + of) * Tout + (t - a.la);
+                nx = make_float2(__ldg(a.nreal + ni), __ldg(a.nimag + ni));
+            }
             for (int j = 0; j < NCH; ++j) {
                 float4* cp = reinterpret_cast<float4*>(cbase + ((size_t)(j * 4 + cg) * 2) * 128 * 4) + r;
                 const float4 c4[2] = {cnext[0], cnext[1]};         // prefetched during the previous chunk
@@ -280,8 +285,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
                 if (cg == 0 && t >= a.la && grow < a.rows) {
                     const float o0 = fc0 + fcpart[(128 + r) * 2] + fcpart[(256 + r) * 2] + fcpart[(384 + r) * 2] + fcb0;
                     const float o1 = fc1 + fcpart[(128 + r) * 2 + 1] + fcpart[(256 + r) * 2 + 1] + fcpart[(384 + r) * 2 + 1] + fcb1;
-                    a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)] = apply_act(o0, a.act);
-                    a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)] = apply_act(o1, a.act);
+                    if (a.enh) {                                       // fused decompress_cIRM x noisy spectrum (inferencer.py:152-157)
+                        const float m0 = decompress_cirm(apply_act(o0, a.act)), m1 = decompress_cirm(apply_act(o1, a.act));
+                        a.enh[((size_t)ob * a.F + of) * Tout + (t - a.la)] = make_float2(m0 * nx.x - m1 * nx.y, m1 * nx.x + m0 * nx.y);
+                    } else {
+                        a.out[(((size_t)ob * 2 + 0) * a.F + of) * Tout + (t - a.la)] = apply_act(o0, a.act);
+                        a.out[(((size_t)ob * 2 + 1) * a.F + of) * Tout + (t - a.la)] = apply_act(o1, a.act);
+                    }
                 }
                 asm volatile("bar.sync 2, 512;" ::: "memory");
             }

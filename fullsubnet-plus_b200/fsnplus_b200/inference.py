@@ -60,6 +60,9 @@ def enhance_batch(model, noisy, n_fft=512, hop_length=256, win_length=512, compl
     complex_inputs=True mirrors mag_complex_full_band_crm_mask (FullSubNet_Plus), False full_band_crm_mask (Model)."""
     X = stft(noisy, n_fft, hop_length, win_length)
     mag = X.abs().unsqueeze(1)
+    if hasattr(model, "enhance_spectrum") and X.is_cuda:          # model + decompress + complex multiply in one call (fused epilogue)
+        enh = model.enhance_spectrum(mag, X.real.unsqueeze(1).contiguous(), X.imag.unsqueeze(1).contiguous())
+        return istft(enh, n_fft, hop_length, win_length, length=noisy.size(-1))
     if complex_inputs:
         crm = model(mag, X.real.unsqueeze(1).contiguous(), X.imag.unsqueeze(1).contiguous())
     else:
@@ -126,8 +129,9 @@ class EnhancePipeline:
     """
 
     def __init__(self, model, length, n_fft=512, hop_length=256, win_length=512, complex_inputs=True, gather=True, to_host=False,
-                 keep_results=True, group=None):
+                 keep_results=True, group=None, fused_post=True):
         self.model, self.length, self.stft_args = model, length, (n_fft, hop_length, win_length)
+        self.fused = fused_post
         self.complex_inputs, self.to_host, self.keep, self.group = complex_inputs, to_host, keep_results, group
         self.world = dist.get_world_size(group) if (gather and dist.is_available() and dist.is_initialized()) else 1
         self.dev = next(model.parameters()).device
@@ -141,8 +145,9 @@ class EnhancePipeline:
     def _finish(self, item):
         lane, X, mask, slot = item
         with torch.cuda.stream(self.post):
-            self.model.wait_lane(lane, self.post)                       # the sub-band LSTM of that batch has written `mask`
-            enh = istft(apply_cirm(mask, X), *self.stft_args, length=self.length)
+            self.model.wait_lane(lane, self.post)                       # the sub-band LSTM of that batch has written its output
+            spec = mask if mask.is_complex() else apply_cirm(mask, X)    # fused epilogue: the enhanced spectrum itself
+            enh = istft(spec, *self.stft_args, length=self.length)
             res = enh
             if self.world > 1:
                 if self.gathered[slot] is None:
@@ -187,8 +192,14 @@ class EnhancePipeline:
             real, imag = (X.real.unsqueeze(1).contiguous(), X.imag.unsqueeze(1).contiguous()) if self.complex_inputs else (None, None)
         B, F, T = X.shape
         if self.masks[slot] is None or self.masks[slot].shape[0] != B or self.masks[slot].shape[-1] != T:
-            self.masks[slot] = torch.empty((B, 2, F, T), dtype=torch.float32, device=self.dev)
-        self.model.submit(mag, real, imag, out=self.masks[slot])
+            self.masks[slot] = (torch.empty((B, F, T), dtype=torch.complex64, device=self.dev) if self.fused else
+                                torch.empty((B, 2, F, T), dtype=torch.float32, device=self.dev))
+        if self.fused:                                                  # model + decompress_cIRM x spectrum in the LSTM epilogue
+            if real is None:
+                real, imag = X.real.unsqueeze(1).contiguous(), X.imag.unsqueeze(1).contiguous()
+            self.model.enhance_spectrum(mag, real, imag, pipelined=True, out=self.masks[slot])
+        else:
+            self.model.submit(mag, real, imag, out=self.masks[slot])
         item = (self.model.last_lane, X, self.masks[slot], slot)
         if self.pending is not None:
             self._finish(self.pending)

@@ -185,7 +185,14 @@ class _B200Model(nn.Module):
             pass
 
     # -- forward -------------------------------------------------------------------------------
-    def _run(self, mag, real, imag):
+    def enhance_spectrum(self, noisy_mag, noisy_real, noisy_imag, pipelined=False, out=None):
+        """Model forward + decompress_cIRM + complex multiply with the noisy spectrum in ONE call (C ABI: fsn_model_forward_enhance /
+        fsn_model_submit_enhance; reference inferencer.py:149-157): [B, 1, F, T] x3 -> enhanced spectrum complex64 [B, F, T], the
+        argument of the inferencer's iSTFT.  The cIRM never goes to memory (fused into the sub-band LSTM's epilogue).
+        ``pipelined=True``: like ``submit()`` -- valid after ``wait()`` / ``wait_lane()``."""
+        return self._run(noisy_mag, noisy_real, noisy_imag, enhance=True, pipelined=pipelined, out=out)
+
+    def _run(self, mag, real, imag, enhance=False, pipelined=False, out=None):
         assert mag.dim() == 4                                            # fullsubnet_plus.py:136
         B, Cn, F, T = mag.shape
         assert Cn == 1, f"{self.__class__.__name__} takes the mag feature as inputs."      # :141
@@ -198,10 +205,17 @@ class _B200Model(nn.Module):
         ins = [x.detach().to(dtype=torch.float32).contiguous() if x is not None else None for x in (mag, real, imag)]
         with torch.cuda.device(mag.device):
             lib = self._ensure_handle(mag.device)
-            out = torch.empty((B, self._cfg.output_size, F, T), dtype=torch.float32, device=mag.device)
+            if out is None:
+                out = (torch.empty((B, F, T), dtype=torch.complex64, device=mag.device) if enhance else
+                       torch.empty((B, self._cfg.output_size, F, T), dtype=torch.float32, device=mag.device))
             ptr = lambda x: C.c_void_p(x.data_ptr()) if x is not None else C.c_void_p()
             stream = C.c_void_p(torch.cuda.current_stream(mag.device).cuda_stream)
-            _lib.check(lib.fsn_model_forward(self._handle, ptr(ins[0]), ptr(ins[1]), ptr(ins[2]), B, T, ptr(out), stream))
+            fn = {(False, False): lib.fsn_model_forward, (True, False): lib.fsn_model_forward_enhance,
+                  (False, True): lib.fsn_model_submit, (True, True): lib.fsn_model_submit_enhance}[(enhance, pipelined)]
+            _lib.check(fn(self._handle, ptr(ins[0]), ptr(ins[1]), ptr(ins[2]), B, T, ptr(out), stream))
+            if pipelined:
+                self._inflight.append((ins, out))
+                self.last_lane = int(lib.fsn_model_last_lane(self._handle))     # ticket for wait_lane()
         return out
 
     def submit(self, mag, real=None, imag=None, out=None):
@@ -209,26 +223,7 @@ class _B200Model(nn.Module):
         immediately; it is valid on the current stream after ``wait()``.  The full-band front end of this batch runs while the
         sub-band LSTM of the previously submitted batch is still running (two internal streams, two workspace lanes).  The inputs
         must not be modified before ``wait()``; references to them are held until then."""
-        assert mag.dim() == 4
-        B, Cn, F, T = mag.shape
-        assert Cn == 1
-        if self.training:
-            raise NotImplementedError("fsnplus_b200 implements the inference (eval) forward only; call .eval()")
-        if not mag.is_cuda:
-            raise RuntimeError("fsnplus_b200 has no CPU fallback: move the model and its inputs to a B200 (cuda) device")
-        if F != self._cfg.num_freqs:
-            raise ValueError(f"expected {self._cfg.num_freqs} frequency bins, got {F}")
-        ins = [x.detach().to(dtype=torch.float32).contiguous() if x is not None else None for x in (mag, real, imag)]
-        with torch.cuda.device(mag.device):
-            lib = self._ensure_handle(mag.device)
-            if out is None:
-                out = torch.empty((B, self._cfg.output_size, F, T), dtype=torch.float32, device=mag.device)
-            ptr = lambda x: C.c_void_p(x.data_ptr()) if x is not None else C.c_void_p()
-            stream = C.c_void_p(torch.cuda.current_stream(mag.device).cuda_stream)
-            _lib.check(lib.fsn_model_submit(self._handle, ptr(ins[0]), ptr(ins[1]), ptr(ins[2]), B, T, ptr(out), stream))
-        self._inflight.append((ins, out))
-        self.last_lane = int(lib.fsn_model_last_lane(self._handle))     # ticket for wait_lane()
-        return out
+        return self._run(mag, real, imag, enhance=False, pipelined=True, out=out)
 
     def wait_lane(self, lane, stream=None):
         """Make ``stream`` (default: the current stream) wait for the batch most recently submitted into workspace lane ``lane``

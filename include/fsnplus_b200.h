@@ -111,6 +111,13 @@ int fsn_model_finalize(fsn_model* m);
  * called with batch 1; the training-only drop_band of fullsubnet_plus.py:192-196 is never applied). */
 int fsn_model_forward(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
                       float* d_out, void* stream);
+/* The model call PLUS the two lines that follow it in the reference's inferencer methods (fullsubnet_plus/inferencer/inferencer.py:152-157,
+ * audio_zen/acoustics/mask.py:60-63): decompress_cIRM and the complex multiplication with the noisy spectrum, fused into the epilogue
+ * of the sub-band LSTM kernel -- the mask never goes to memory.  d_real / d_imag are the planes the model takes anyway (required
+ * here also for fullsubnet.Model, which does not read them in its forward); d_enh: [B, F, T] complex64 (interleaved re, im) =
+ * the argument of the inferencer's iSTFT. */
+int fsn_model_forward_enhance(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                              float* d_enh, void* stream);
 /* Same call with HOST buffers (pinned or pageable): H2D copies, the forward and the D2H copy of the
  * mask are all enqueued on `stream` and the call returns after the result is in h_out. */
 int fsn_model_forward_host(fsn_model* m, const float* h_mag, const float* h_real, const float* h_imag, int32_t B, int32_t T,
@@ -132,6 +139,8 @@ int fsn_model_forward_host(fsn_model* m, const float* h_mag, const float* h_real
  * untouched (h_out unread) until fsn_model_sync_host() returns. */
 int fsn_model_submit(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
                      float* d_out, void* stream);
+int fsn_model_submit_enhance(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
+                             float* d_enh, void* stream);   /* pipelined fsn_model_forward_enhance */
 int fsn_model_wait(fsn_model* m, void* stream);
 /* Finer-grained completion for consumers that post-process batch i while batch i+1 runs: the workspace lane (0 / 1) the LAST
  * fsn_model_submit used, and a wait on the batch most recently submitted into one lane (valid until the next submit into it). */

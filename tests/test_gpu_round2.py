@@ -309,3 +309,62 @@ def test_causal_tcn_variant(built_lib, golden):
     err = O.rel_l2(out.cpu().numpy(), ref)
     print(f"[causal TCN default geometry] cIRM {err:.3e} (differs from the non-causal golden by {O.rel_l2(ref, gd['out']):.2e})")
     assert err < MASK_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fused post-processing: decompress_cIRM x noisy spectrum in the LSTM epilogue
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", ["fused", "layerwise", "mma"])
+def test_enhance_spectrum_matches_mask_then_postprocess(built_lib, path):
+    """fsn_model_forward_enhance == fsn_model_forward followed by the reference's decompress_cIRM + complex multiply
+    (inferencer.py:152-157, mask.py:60-63), on the three sub-band kernels; masks scaled so the +-9.9 clamp is exercised."""
+    from fsnplus_b200 import inference as inf
+    H, L, impl = {"fused": (64, 2, "tcgen05"), "layerwise": (64, 3, "tcgen05"), "mma": (32, 2, "mma")}[path]
+    cfg = _small(H)
+    params = O.make_params_plus(cfg, seed=61, num_layers=L, lstm_scale=2.0)
+    params["sb_model.fc_output_layer.weight"] = params["sb_model.fc_output_layer.weight"] * 40.0
+    mag, real, imag = _inputs(3, 33, 21, 17)
+    m = _plus(cfg, params, num_layers=L, lstm_impl=impl)
+    X = torch.complex(_t(real)[:, 0], _t(imag)[:, 0])
+    with torch.no_grad():
+        crm = m(_t(mag), _t(real), _t(imag))
+        assert (crm.abs() > 9.9).any() and (crm.abs() < 9.9).any()
+        d = inf.decompress_cIRM(crm)
+        want = torch.complex(d[:, 0] * X.real - d[:, 1] * X.imag, d[:, 1] * X.real + d[:, 0] * X.imag)
+        got = m.enhance_spectrum(_t(mag), _t(real), _t(imag))
+        got_p = m.enhance_spectrum(_t(mag), _t(real), _t(imag), pipelined=True)
+        m.wait()
+    torch.cuda.synchronize()
+    assert got.dtype == torch.complex64 and got.shape == (3, 33, 21)
+    assert torch.allclose(torch.view_as_real(got), torch.view_as_real(want), rtol=2e-5, atol=1e-6)
+    assert torch.equal(torch.view_as_real(got), torch.view_as_real(got_p))
+
+
+def test_enhance_pipeline_matches_enhance_batch(built_lib, golden):
+    """EnhancePipeline (pipelined submit, fused post-processing, side-stream iSTFT) == enhance_batch per batch == the reference
+    pipeline's waveform on the golden clip."""
+    from fsnplus_b200 import inference as inf
+    g = golden("plus_default")
+    cfg = O.default_plus_config()
+    m = _plus(cfg, O.make_params_plus(cfg, seed=0))
+    clips = torch.from_numpy(O.synth_clips(6).astype(np.float32)).to(DEV)
+    batches = [clips[0:2], clips[2:4], clips[4:6], clips[0:2]]
+    want = [inf.enhance_batch(m, b) for b in batches]
+    for fused in (True, False):
+        pipe = inf.EnhancePipeline(m, 48000, fused_post=fused)
+        for b in batches:
+            pipe.push(inf.stft(b))
+        got = [r.clone() for r in pipe.flush()]
+        # results are double-buffered: only the last two are still intact -- compare those, and the earlier ones through a second run
+        for k in (2, 3):
+            assert O.rel_l2(got[k].cpu().numpy(), want[k].cpu().numpy()) < 1e-5, (fused, k)
+    assert O.rel_l2(want[0][0].cpu().numpy(), g["enhanced"][0]) < 2e-3
+    pin = lambda x: x.cpu().pin_memory()
+    pipe = inf.EnhancePipeline(m, 48000, to_host=True, keep_results=False)
+    outs = []
+    for b in batches[:2]:
+        X = inf.stft(b)
+        pipe.push(host=(pin(X.abs().unsqueeze(1)), pin(X.real.unsqueeze(1).contiguous()), pin(X.imag.unsqueeze(1).contiguous())))
+    pipe.flush()
+    for k in (0, 1):
+        assert O.rel_l2(pipe.host_out[k].numpy(), want[k].cpu().numpy()) < 1e-5
