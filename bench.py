@@ -264,19 +264,27 @@ def reference_arm(args, w, state):
             times.append(t)
     pool.close()
     per_step = statistics.median(times)
-    fps = nworkers * n * frames / per_step
+    fps_conc = nworkers * n * frames / per_step
+    fps_single = frames / single
+    # the arm's value is the reference CPU path at its BEST use of the host: several concurrent B=1 workers or one process,
+    # whichever is faster (on the 128-core GPU hosts the workers are memory-bound and one 16-thread process wins)
+    use_conc = fps_conc >= fps_single
+    fps = fps_conc if use_conc else fps_single
+    step_ms = per_step * 1e3 if use_conc else single * n * 1e3
     line = {
         "impl": "reference", "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": K, "warmup": W, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": K, "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "rtf": per_step / (nworkers * n * clip_s),
+        "rtf": (per_step / (nworkers * n * clip_s)) if use_conc else single / clip_s,
         "config": {"workload": w["name"]},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": nworkers * threads, "kind": kind,
-                         "sample": f"{nworkers} concurrent worker processes x {threads} threads, {n} clips per worker per step x {K} steps, one 3 s clip "
-                                   f"per call (the reference inference batch size), model forward only, torch {torch.__version__} CPU fp32"
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": nworkers * threads if use_conc else threads, "kind": kind,
+                         "sample": (f"{nworkers} concurrent worker processes x {threads} threads, {n} clips per worker per step x {K} steps" if use_conc else
+                                    f"one process x {threads} threads (faster than {nworkers} concurrent workers on this host), {max(3, n)} clips")
+                                   + f", one 3 s clip per call (the reference inference batch size), model forward only, torch {torch.__version__} CPU fp32"
                                    + (" (the reference cannot stream: offline forward of 3 s clips)" if w["id"] == 4 else ""),
                          "host_cores": ncpu, "thread_sweep_s_per_clip": sweep,
-                         "single_process": {"value": frames / single, "unit": "frames/s", "cores": threads, "rtf": single / clip_s}},
+                         "single_process": {"value": fps_single, "unit": "frames/s", "cores": threads, "rtf": single / clip_s},
+                         "concurrent": {"value": fps_conc, "unit": "frames/s", "workers": nworkers, "threads_per_worker": threads, "ms_per_step": per_step * 1e3}},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))

@@ -125,8 +125,11 @@ class EnhancePipeline:
 
     The collective therefore runs on the side stream underneath the NEXT batch's forward, never on the
     critical path.  Results: device tensors [world * B, L] (gathered) or [B, L]; with ``to_host=True`` this rank's shard in
-    pinned host memory.  Result buffers are double-buffered: a result is valid until two pushes later (copy it if kept longer).
+    pinned host memory.  Result / staging buffers form a ring of NSLOT: a result is valid until NSLOT pushes later (copy it if kept
+    longer).  The ring is deeper than the two batches in flight on purpose: reusing a slot waits for the post-processing that last read
+    it, and with only two slots that wait would hold back the FRONT END of batch i+1 until the iSTFT of batch i-1 is done.
     """
+    NSLOT = 4
 
     def __init__(self, model, length, n_fft=512, hop_length=256, win_length=512, complex_inputs=True, gather=True, to_host=False,
                  keep_results=True, group=None, fused_post=True):
@@ -138,8 +141,8 @@ class EnhancePipeline:
         self.post, self.copy = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
         self.pending = None                       # (lane, X, mask, slot) of the batch whose LSTM may still be running
         self.n = 0
-        two = lambda: [None, None]
-        self.masks, self.post_done, self.stage, self.host_out, self.gathered = two(), two(), two(), two(), two()
+        ring = lambda: [None] * self.NSLOT
+        self.masks, self.post_done, self.stage, self.host_out, self.gathered = ring(), ring(), ring(), ring(), ring()
         self.results = []
 
     def _finish(self, item):
@@ -169,7 +172,7 @@ class EnhancePipeline:
     def push(self, X=None, host=None):
         """One batch: ``X`` complex64 [B, F, T] on the device, or ``host`` = (mag, real, imag) pinned CPU float32 [B, 1, F, T]
         (the C ABI's host-buffer layout; X is rebuilt on the device from real / imag)."""
-        slot = self.n & 1
+        slot = self.n % self.NSLOT
         main = torch.cuda.current_stream(self.dev)
         if self.post_done[slot] is not None:
             main.wait_event(self.post_done[slot])                       # mask / staging buffers of this slot are free again

@@ -30,7 +30,10 @@ def available():
 def _stubs():
     if "librosa" not in sys.modules:
         lib = types.ModuleType("librosa")
-        lib.stft = lib.istft = lib.load = None
+
+        def _absent(*a, **k):
+            raise RuntimeError("librosa is not installed in this image (stub): the model path never calls it")
+        lib.stft = lib.istft = lib.load = _absent      # base_inferencer.py:54-55 wraps them in functools.partial (must be callable)
         lib.util = types.ModuleType("librosa.util")
         sys.modules["librosa"], sys.modules["librosa.util"] = lib, lib.util
     if "soundfile" not in sys.modules:
