@@ -332,6 +332,7 @@ def product_batched(args, w, model, state, rank, local_rank, world):
             e0.record()
             for i in range(steps):
                 body(warm + i)
+            timed.host_ms = (time.time() - t0) * 1e3 / steps          # host time to ENQUEUE one step (before the drain)
             if drain:
                 drain()
             e1.record()
@@ -355,6 +356,7 @@ def product_batched(args, w, model, state, rank, local_rank, world):
         sampler.start()
         time.sleep(0.3)
     ms_step, t0, t1 = timed(lambda i: pipe.push(Xs[i % NSETS]), K, W, drain=pipe.flush)
+    host_ms = timed.host_ms
     clocks = sampler.stop(t0, t1) if sampler else None
     lstm_ms = [x for x in model.lstm_ms_history(min(K, 32)) if x > 0]
     tl = model.timeline(min(K, 6))
@@ -410,6 +412,7 @@ def product_batched(args, w, model, state, rank, local_rank, world):
                            + "; pipelined (fsn_model_submit): front end of batch i+1 and post-processing of batch i-1 overlap the sub-band LSTM of batch i",
                    "l2": f"inputs rotated over {NSETS} batches ({NSETS * in_bytes / 1e6:.0f} MB > L2); per-step intermediates exceed L2"},
         "model_tflops": world * B * tot_flops / (ms_step * 1e-3) / 1e12,
+        "host_enqueue_ms_per_step": host_ms,
         "roofline": roofline,
         "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": ms_e2e, "rtf": ms_e2e * 1e-3 / (B * w["clip_s"]),
                 "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": wav_bytes,

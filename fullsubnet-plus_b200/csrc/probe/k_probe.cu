@@ -514,3 +514,35 @@ extern "C" int fsn_probe_tcgen05(float* h_report, int32_t n) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -1;
     return fsn::run_probe_tcgen05(h_report, n);
 }
+
+// Minimal reproducer for the one racecheck report of round 1 ("race" between tcgen05.alloc's own shared-memory write of the TMEM
+// base address and the read of that slot): a 2-CTA cluster that ONLY allocates tensor memory, synchronises exactly like the LSTM
+// kernels (tcgen05.fence::before_thread_sync, __syncthreads, cluster barrier, fence::after), reads the slot and frees it.  If
+// compute-sanitizer --tool racecheck flags this kernel too, the report is about the instruction's asynchronous write (which the tool
+// does not order with bar.sync), not about the kernels' protocol.  Returns the TMEM base address read by thread 0 (0 = column 0).
+namespace fsn {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) tmem_alloc_repro_kernel(uint32_t* out) {
+    __shared__ uint32_t slot;
+    if (threadIdx.x < 32) tmem_alloc_pair<512>(&slot);
+    tc5_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc5_fence_after();
+    const uint32_t t = slot;
+    if (threadIdx.x == 0) out[blockIdx.x] = t;
+    tc5_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (threadIdx.x < 32) tmem_dealloc_pair<512>(t);
+}
+}  // namespace fsn
+
+extern "C" int fsn_probe_tmem_alloc(void) {
+    uint32_t* d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return -1;
+    fsn::tmem_alloc_repro_kernel<<<2, 128>>>(d);
+    uint32_t h[2] = {1, 1};
+    const cudaError_t e = cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? (int)(h[0] | h[1]) : -(int)e - 1000;
+}

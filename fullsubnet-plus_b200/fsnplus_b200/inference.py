@@ -117,17 +117,19 @@ class EnhancePipeline:
     """Enhancement of a STREAM of equal-shape batches with everything overlapped (what the reference's inferencer loop,
     base_inferencer.py:133-160, does one clip at a time):
 
-        push(i):   [optional H2D of pinned host spectra on a copy stream] -> model.submit(batch i)      (front end of batch i runs
-                   while the sub-band LSTM of batch i-1 is still running, see fsn_model_submit)
-                   then, on a side stream, for batch i-1: decompress_cIRM x noisy spectrum (fused kernel) -> torch.istft ->
+        push(i):   [optional H2D of pinned host spectra on a copy stream] -> pipelined model call for batch i  (the front end of batch i
+                   runs while the sub-band LSTM of batch i-1 is still running, see fsn_model_submit; with fused_post the LSTM epilogue
+                   also does decompress_cIRM x noisy spectrum, fsn_model_submit_enhance)
+                   then, on a side stream, for batch i-1: [cIRM post-processing if not fused] -> torch.istft ->
                    ONE all-gather of the enhanced waveforms over the process group (world > 1) [-> D2H into pinned host memory]
         flush():   post-process the last batch and synchronise; returns the list of results in push order.
 
     The collective therefore runs on the side stream underneath the NEXT batch's forward, never on the
     critical path.  Results: device tensors [world * B, L] (gathered) or [B, L]; with ``to_host=True`` this rank's shard in
-    pinned host memory.  Result / staging buffers form a ring of NSLOT: a result is valid until NSLOT pushes later (copy it if kept
-    longer).  The ring is deeper than the two batches in flight on purpose: reusing a slot waits for the post-processing that last read
-    it, and with only two slots that wait would hold back the FRONT END of batch i+1 until the iSTFT of batch i-1 is done.
+    pinned host memory.  Input / result buffers form a ring of NSLOT preallocated slots (no allocation on the steady-state path: a
+    cudaMalloc would synchronise the device): a result is valid until NSLOT pushes later (copy it if kept longer).  The ring is
+    deeper than the two batches in flight on purpose: reusing a slot waits for the post-processing that last read it, and with only
+    two slots that wait would hold back the FRONT END of batch i+1 until the iSTFT of batch i-1 is done.
     """
     NSLOT = 4
 
@@ -139,17 +141,30 @@ class EnhancePipeline:
         self.world = dist.get_world_size(group) if (gather and dist.is_available() and dist.is_initialized()) else 1
         self.dev = next(model.parameters()).device
         self.post, self.copy = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
-        self.pending = None                       # (lane, X, mask, slot) of the batch whose LSTM may still be running
+        self.pending = None                       # (lane, slot) of the batch whose LSTM may still be running
         self.n = 0
         ring = lambda: [None] * self.NSLOT
-        self.masks, self.post_done, self.stage, self.host_out, self.gathered = ring(), ring(), ring(), ring(), ring()
+        self.inbuf, self.outbuf, self.post_done, self.host_out, self.gathered = ring(), ring(), ring(), ring(), ring()
         self.results = []
 
+    def _slot(self, slot, B, F, T):
+        if self.inbuf[slot] is None or tuple(self.inbuf[slot][0].shape) != (B, 1, F, T):
+            self.inbuf[slot] = [torch.empty((B, 1, F, T), dtype=torch.float32, device=self.dev) for _ in range(3)]
+            self.outbuf[slot] = (torch.empty((B, F, T), dtype=torch.complex64, device=self.dev) if self.fused else
+                                 torch.empty((B, 2, F, T), dtype=torch.float32, device=self.dev))
+            self.gathered[slot] = self.host_out[slot] = None
+        return self.inbuf[slot], self.outbuf[slot]
+
     def _finish(self, item):
-        lane, X, mask, slot = item
+        lane, slot = item
         with torch.cuda.stream(self.post):
             self.model.wait_lane(lane, self.post)                       # the sub-band LSTM of that batch has written its output
-            spec = mask if mask.is_complex() else apply_cirm(mask, X)    # fused epilogue: the enhanced spectrum itself
+            out = self.outbuf[slot]
+            if out.is_complex():                                        # fused epilogue: the enhanced spectrum itself
+                spec = out
+            else:
+                _, real, imag = self.inbuf[slot]
+                spec = apply_cirm(out, torch.complex(real[:, 0], imag[:, 0]))
             enh = istft(spec, *self.stft_args, length=self.length)
             res = enh
             if self.world > 1:
@@ -162,48 +177,46 @@ class EnhancePipeline:
                     self.host_out[slot] = torch.empty(tuple(enh.shape), dtype=enh.dtype).pin_memory()
                 self.host_out[slot].copy_(enh, non_blocking=True)       # this rank's shard -> pinned host memory
                 res = self.host_out[slot]
-            ev = torch.cuda.Event()
-            ev.record(self.post)
-            self.post_done[slot] = ev
-            X.record_stream(self.post)
+            if self.post_done[slot] is None:
+                self.post_done[slot] = torch.cuda.Event()
+            self.post_done[slot].record(self.post)
         if self.keep:
             self.results.append(res)
 
     def push(self, X=None, host=None):
         """One batch: ``X`` complex64 [B, F, T] on the device, or ``host`` = (mag, real, imag) pinned CPU float32 [B, 1, F, T]
-        (the C ABI's host-buffer layout; X is rebuilt on the device from real / imag)."""
+        (the C ABI's host-buffer layout)."""
         slot = self.n % self.NSLOT
         main = torch.cuda.current_stream(self.dev)
+        if host is not None:
+            B, _, F, T = host[0].shape
+        else:
+            B, F, T = X.shape
+        (mag, real, imag), out = self._slot(slot, B, F, T)
         if self.post_done[slot] is not None:
-            main.wait_event(self.post_done[slot])                       # mask / staging buffers of this slot are free again
+            main.wait_event(self.post_done[slot])                       # input / output buffers of this slot are free again
         if host is not None:
             with torch.cuda.stream(self.copy):
                 if self.post_done[slot] is not None:
                     self.copy.wait_event(self.post_done[slot])
-                if self.stage[slot] is None:
-                    self.stage[slot] = [torch.empty(tuple(h.shape), dtype=torch.float32, device=self.dev) for h in host]
-                for d, h in zip(self.stage[slot], host):
-                    d.copy_(h, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self.copy)
-            main.wait_event(ev)
-            mag = self.stage[slot][0]
-            real, imag = (self.stage[slot][1], self.stage[slot][2]) if self.complex_inputs else (None, None)
-            X = torch.complex(self.stage[slot][1][:, 0], self.stage[slot][2][:, 0])
+                for d, h in zip((mag, real, imag), host):
+                    if h is not None:
+                        d.copy_(h, non_blocking=True)
+                if getattr(self, "_h2d_ev", None) is None:
+                    self._h2d_ev = [torch.cuda.Event() for _ in range(self.NSLOT)]
+                self._h2d_ev[slot].record(self.copy)
+            main.wait_event(self._h2d_ev[slot])
         else:
-            mag = X.abs().unsqueeze(1)
-            real, imag = (X.real.unsqueeze(1).contiguous(), X.imag.unsqueeze(1).contiguous()) if self.complex_inputs else (None, None)
-        B, F, T = X.shape
-        if self.masks[slot] is None or self.masks[slot].shape[0] != B or self.masks[slot].shape[-1] != T:
-            self.masks[slot] = (torch.empty((B, F, T), dtype=torch.complex64, device=self.dev) if self.fused else
-                                torch.empty((B, 2, F, T), dtype=torch.float32, device=self.dev))
+            torch.abs(X, out=mag[:, 0])
+            real[:, 0].copy_(X.real)
+            imag[:, 0].copy_(X.imag)
         if self.fused:                                                  # model + decompress_cIRM x spectrum in the LSTM epilogue
-            if real is None:
-                real, imag = X.real.unsqueeze(1).contiguous(), X.imag.unsqueeze(1).contiguous()
-            self.model.enhance_spectrum(mag, real, imag, pipelined=True, out=self.masks[slot])
+            self.model.enhance_spectrum(mag, real, imag, pipelined=True, out=out, hold=False)
+        elif self.complex_inputs:
+            self.model.submit(mag, real, imag, out=out, hold=False)
         else:
-            self.model.submit(mag, real, imag, out=self.masks[slot])
-        item = (self.model.last_lane, X, self.masks[slot], slot)
+            self.model.submit(mag, out=out, hold=False)
+        item = (self.model.last_lane, slot)
         if self.pending is not None:
             self._finish(self.pending)
         self.pending = item

@@ -185,14 +185,14 @@ class _B200Model(nn.Module):
             pass
 
     # -- forward -------------------------------------------------------------------------------
-    def enhance_spectrum(self, noisy_mag, noisy_real, noisy_imag, pipelined=False, out=None):
+    def enhance_spectrum(self, noisy_mag, noisy_real, noisy_imag, pipelined=False, out=None, hold=True):
         """Model forward + decompress_cIRM + complex multiply with the noisy spectrum in ONE call (C ABI: fsn_model_forward_enhance /
         fsn_model_submit_enhance; reference inferencer.py:149-157): [B, 1, F, T] x3 -> enhanced spectrum complex64 [B, F, T], the
         argument of the inferencer's iSTFT.  The cIRM never goes to memory (fused into the sub-band LSTM's epilogue).
         ``pipelined=True``: like ``submit()`` -- valid after ``wait()`` / ``wait_lane()``."""
-        return self._run(noisy_mag, noisy_real, noisy_imag, enhance=True, pipelined=pipelined, out=out)
+        return self._run(noisy_mag, noisy_real, noisy_imag, enhance=True, pipelined=pipelined, out=out, hold=hold)
 
-    def _run(self, mag, real, imag, enhance=False, pipelined=False, out=None):
+    def _run(self, mag, real, imag, enhance=False, pipelined=False, out=None, hold=True):
         assert mag.dim() == 4                                            # fullsubnet_plus.py:136
         B, Cn, F, T = mag.shape
         assert Cn == 1, f"{self.__class__.__name__} takes the mag feature as inputs."      # :141
@@ -214,16 +214,17 @@ class _B200Model(nn.Module):
                   (False, True): lib.fsn_model_submit, (True, True): lib.fsn_model_submit_enhance}[(enhance, pipelined)]
             _lib.check(fn(self._handle, ptr(ins[0]), ptr(ins[1]), ptr(ins[2]), B, T, ptr(out), stream))
             if pipelined:
-                self._inflight.append((ins, out))
+                if hold:                                                        # hold=False: the caller keeps the buffers alive itself (EnhancePipeline's ring)
+                    self._inflight.append((ins, out))
                 self.last_lane = int(lib.fsn_model_last_lane(self._handle))     # ticket for wait_lane()
         return out
 
-    def submit(self, mag, real=None, imag=None, out=None):
+    def submit(self, mag, real=None, imag=None, out=None, hold=True):
         """Pipelined forward for STREAMS of batches (C ABI: fsn_model_submit): same inputs as forward(), returns the output tensor
         immediately; it is valid on the current stream after ``wait()``.  The full-band front end of this batch runs while the
         sub-band LSTM of the previously submitted batch is still running (two internal streams, two workspace lanes).  The inputs
         must not be modified before ``wait()``; references to them are held until then."""
-        return self._run(mag, real, imag, enhance=False, pipelined=True, out=out)
+        return self._run(mag, real, imag, enhance=False, pipelined=True, out=out, hold=hold)
 
     def wait_lane(self, lane, stream=None):
         """Make ``stream`` (default: the current stream) wait for the batch most recently submitted into workspace lane ``lane``

@@ -323,7 +323,7 @@ def test_enhance_spectrum_matches_mask_then_postprocess(built_lib, path):
     H, L, impl = {"fused": (64, 2, "tcgen05"), "layerwise": (64, 3, "tcgen05"), "mma": (32, 2, "mma")}[path]
     cfg = _small(H)
     params = O.make_params_plus(cfg, seed=61, num_layers=L, lstm_scale=2.0)
-    params["sb_model.fc_output_layer.weight"] = params["sb_model.fc_output_layer.weight"] * 40.0
+    params["sb_model.fc_output_layer.weight"] = params["sb_model.fc_output_layer.weight"] * 150.0
     mag, real, imag = _inputs(3, 33, 21, 17)
     m = _plus(cfg, params, num_layers=L, lstm_impl=impl)
     X = torch.complex(_t(real)[:, 0], _t(imag)[:, 0])
