@@ -98,6 +98,7 @@ struct fsn_model {
     // tuning knobs, read ONCE at fsn_model_create (never on the forward path): FSN_LSTM_IMPL overrides cfg.lstm_impl,
     // FSN_NO_WS=1 keeps the full-band LSTM of fullsubnet.Model off the weight-stationary kernel
     int env_impl = 0;
+    int env_split = 0;                                 // FSN_TC5_SPLIT: force the small-batch column split (1 / 2 / 4; 0 = auto)
     bool env_no_ws = false, env_no_xfuse = false;      // FSN_NO_XFUSE=1: packed sub-band images instead of the fused unfold (A/B only)
     // pipelined execution: front-end stream, LSTM stream (higher priority), copy-in / copy-out streams, per-slot events
     cudaStream_t s_front = nullptr, s_lstm = nullptr, s_in = nullptr, s_out = nullptr;
@@ -373,6 +374,7 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     { const char* e = getenv("FSN_LSTM_IMPL"); if (e && *e) m->env_impl = atoi(e); }
     { const char* e = getenv("FSN_NO_WS"); m->env_no_ws = e && atoi(e) != 0; }
     { const char* e = getenv("FSN_NO_XFUSE"); m->env_no_xfuse = e && atoi(e) != 0; }
+    { const char* e = getenv("FSN_TC5_SPLIT"); if (e && *e) m->env_split = atoi(e); }
     build_specs(m);
     for (int i = 0; i < fsn_model::NEV; ++i) { cudaEventCreate(&m->ev0[i]); cudaEventCreate(&m->ev1[i]); cudaEventCreate(&m->evf0[i]); cudaEventCreate(&m->evf1[i]); }
     { cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev); if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) m->num_sms = prop.multiProcessorCount; }
@@ -647,6 +649,7 @@ static int run_sb_lstm(fsn_model* m, fsn_model::Lane& ln, int B, int T, float* d
         a.H = c.sb_hidden; a.I = m->Isb; a.rows = rows; a.Tp = Tp;
         a.img = static_cast<const __half*>(ln.ximg.p); a.ntiles = ntiles;
         a.xs = xs;
+        a.split = m->env_split;
         a.nreal = d_real; a.nimag = d_imag; a.enh = reinterpret_cast<float2*>(d_enh);
         a.cstate = static_cast<float*>(m->cstate.p);
         a.out = d_out; a.F = F; a.la = c.look_ahead; a.act = c.sb_act; a.fast = c.fast_math; a.gru = c.rnn_type == FSN_RNN_GRU;

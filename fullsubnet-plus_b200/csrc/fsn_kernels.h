@@ -149,12 +149,14 @@ struct LstmTc5Launch {
     int act;                  // FSN_ACT_* applied to the Linear output (sb_output_activate_function, sequence_model.py:120-121)
     int fast;
     int gru;                  // 1: pseudo-gate GRU cell
+    int split;                // column split S for small batches: 0 = auto (4 / 2 / 1 by the number of row tiles), or forced 1 / 2 / 4
     // fused post-processing (inferencer.py:152-157): when enh != null the epilogue decompresses the cIRM and multiplies it with the
     // noisy spectrum (planes [B, F, T]) instead of writing the mask: enh [B, F, T] complex64 (interleaved re, im)
     const float* nreal; const float* nimag; float2* enh;
 };
 size_t lstm_tc5_cstate_bytes(int ntiles, int H);
 bool lstm_tc5_supported(int L, int H, int I, int O);
+int lstm_tc5_split_for(int H, int ntiles, int forced);              // the column split launch_lstm_tc5_dbuf will use
 int launch_lstm_tc5_dbuf(const LstmTc5Launch& a, cudaStream_t s);   // k_lstm_tc5d.cu: CTA-pair kernel with two 64-column accumulators
 
 // ---- k_lstm_tc5r.cu: single-layer recurrent kernel (time-batched input projection) for stacks outside the fused kernel's envelope

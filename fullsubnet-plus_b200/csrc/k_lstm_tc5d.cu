@@ -36,9 +36,9 @@ struct D5Plan { int nstage; size_t total; };
 bool lstm_tc5_supported(int L, int H, int I, int O) { return L == 2 && H % 64 == 0 && H >= 64 && H <= 384 && I <= 64 && O == 2; }
 size_t lstm_tc5_cstate_bytes(int ntiles, int H) { return (size_t)ntiles * 2 * H * 128 * sizeof(float); }
 
-static inline D5Plan d5_plan(int H) {
+static inline D5Plan d5_plan(int H, int S) {
     D5Plan p;
-    const size_t fixed = D5_XIMG + (size_t)128 * H * 2 /*park*/ + (size_t)2 * 4 * H * 4 /*pre-scaled biases*/ + 4 * 128 * 2 * 4 + 64 * 8;
+    const size_t fixed = D5_XIMG + (size_t)128 * H * 2 /*park*/ + (size_t)2 * 4 * H * 4 /*pre-scaled biases*/ + (size_t)S * 4 * 128 * 2 * 4 /*fc partials*/ + 64 * 8;
     long avail = D5_MAX_SMEM - 1024 - (long)fixed;
     p.nstage = (int)(avail / D5_STAGE);
     if (p.nstage > 8) p.nstage = 8;
@@ -46,13 +46,23 @@ static inline D5Plan d5_plan(int H) {
     return p;
 }
 
-template <int H, bool FAST, bool GRU>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_tc5d_kernel(LstmTc5Launch a, int nstage) {
+// S > 1: COLUMN-SPLIT mode for small batches (B*F rows fill fewer than half of the SMs).  A cluster holds S CTA pairs that all work on
+// the SAME 256 sequences; pair s computes the gate chunks [s NCH/S, (s+1) NCH/S) of every layer-step (1/S of the MMA stream, of the
+// weight traffic and of the cell updates), the new hidden values are exchanged through distributed shared memory (each epilogue
+// thread stores its 16 bytes into the `park` buffer of the S-1 other CTAs that own the same rows), and every CTA then refills its own
+// tensor-memory copy of h.  The latency of one layer-step drops from ~18 us to ~(18 / S + exchange) us: B = 1 (the only batch size
+// the reference's inferencer issues, base_inferencer.py:65-69) uses 16 SMs instead of 4.
+template <int H, bool FAST, bool GRU, int S>
+__global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_tc5d_kernel(LstmTc5Launch a, int nstage) {
     extern __shared__ uint8_t smem_raw[];
-    constexpr int NCH = H / 32, KBH = H / 64, hcols = H / 2;
+    constexpr int NCH = H / 32, KBH = H / 64, hcols = H / 2, NCHS = NCH / S;
+    static_assert(NCH % S == 0, "the gate chunks must split evenly over the pairs of a cluster");
     const int Tp = a.Tp;
-    const int tile = blockIdx.x;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t rank = crank & 1u, sidx = crank >> 1, lead = crank & ~1u;   // row half, column split, cluster rank of my pair's leader
+    const int tile = (blockIdx.x / (2 * S)) * 2 + (int)rank;
+    const int j0 = (int)sidx * NCHS;                                          // my pair's chunks: [j0, j0 + NCHS)
+    const uint16_t pairmask = (uint16_t)(3u << (2 * sidx));                    // multicast commits go to the two CTAs of my pair
     const bool leader = (rank == 0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -61,8 +71,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
     uint8_t* ximg = stages + (size_t)nstage * D5_STAGE;
     uint8_t* park = ximg + D5_XIMG;
     float* bsm = reinterpret_cast<float*>(park + (size_t)128 * H * 2);       // [2][NCH][128] pre-scaled biases
-    float* fcpart = bsm + 2 * 4 * H;                                         // [4][128][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(fcpart + 4 * 128 * 2);
+    float* fcpart = bsm + 2 * 4 * H;                                         // [S][4][128][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fcpart + S * 4 * 128 * 2);
     uint64_t* full = bars;
     uint64_t* empty = full + nstage;
     uint64_t* xfull = empty + nstage;
@@ -71,7 +81,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
     uint64_t* accempty = accfull + 2;                                        // [2]
     uint64_t* hready = accempty + 2;                                         // [2]: h of layer 0 / layer 1 is in TMEM
     uint64_t* layerdone = hready + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layerdone + 1);
+    uint64_t* hall = layerdone + 1;                                          // S > 1: the other pairs' h chunks of this layer-step are parked here
+    uint64_t* pfree = hall + 1;                                              // S > 1: the other CTAs have consumed what I parked there last layer-step
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfree + 1);
 
     if (tid == 0) {
         for (int i = 0; i < nstage; ++i) { mbar_init(&full[i], leader ? 2 : 1); mbar_init(&empty[i], 1); }
@@ -82,6 +94,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
         for (int h = 0; h < 2; ++h) { mbar_init(&accfull[h], 1); mbar_init(&accempty[h], D5_EPI_WARPS); }   // 8 warps x 2 CTAs
         mbar_init(&hready[0], 2 * D5_EPI_WARPS); mbar_init(&hready[1], 2 * D5_EPI_WARPS);
         mbar_init(layerdone, 1);
+        if (S > 1) { mbar_init(hall, (S - 1) * D5_EPI_WARPS); mbar_init(pfree, (S - 1) * D5_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == D5_EPI_WARPS + 1) tmem_alloc_pair<512>(tmem_slot);
@@ -109,10 +122,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
             for (int t = 0; t < Tp; ++t) {
                 for (int layer = 0; layer < 2; ++layer) {
                     const int nkb = layer == 0 ? NKB0 : NKB1;
-                    for (int j = 0; j < NCH; ++j) {
+                    for (int j = j0; j < j0 + NCHS; ++j) {
                         const int kb_base = layer == 0 ? j * NKB0 : NCH * NKB0 + j * NKB1;   // k-block index in the per-step stream
                         for (int half = 0; half < 2; ++half) {
-                            if (packed && layer == 1 && j == NCH / 2 && half == 0 && t + 1 < Tp) {     // x_{t+1}: layer 0 of step t is long done
+                            if (packed && layer == 1 && j == j0 + NCHS / 2 && half == 0 && t + 1 < Tp) {     // x_{t+1}: layer 0 of step t is long done
                                 mbar_wait(xempty, t & 1);
                                 mbar_arrive_expect_tx(xfull, D5_XIMG);
                                 bulk_g2s_hint(ximg, xsrc + (size_t)(t + 1) * D5_XIMG, D5_XIMG, xfull, pol_x);
@@ -180,7 +193,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                     tc5_fence_after();
                     constexpr int NKB0 = 1 + KBH, NKB1 = 2 * KBH;
                     const int nkb = layer == 0 ? NKB0 : NKB1;
-                    for (int j = 0; j < NCH; ++j) {
+                    for (int j = j0; j < j0 + NCHS; ++j) {
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
                             mbar_wait(&accempty[half], (accuse & 1) ^ 1);
@@ -196,18 +209,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
 #pragma unroll
                                         for (int i = 0; i < 4; ++i)
                                             if (kb0 + i < nkb) {
-                                                if (layer == 1 && kb0 + i == KBH && j == 0 && half == 0) {   // h0(t) is needed from here on
+                                                if (layer == 1 && kb0 + i == KBH && j == j0 && half == 0) {   // h0(t) is needed from here on
                                                     mbar_wait(&hready[0], (t + 1) & 1);
                                                     tc5_fence_after();
                                                 }
                                                 kblock(layer, kb0 + i, b_lo + i * (D5_SUB >> 4));
                                             }
-                                        umma2_commit_mc(&empty[slot], 3);
+                                        umma2_commit_mc(&empty[slot], pairmask);
                                         if (kb0 + 4 >= nkb) {
-                                            umma2_commit_mc(&accfull[half], 3);
-                                            if (j == NCH - 1 && half == 1) {
-                                                if (layer == 0) umma2_commit_mc(xempty, 3);
-                                                umma2_commit_mc(layerdone, 3);
+                                            umma2_commit_mc(&accfull[half], pairmask);
+                                            if (j == j0 + NCHS - 1 && half == 1) {
+                                                if (layer == 0) umma2_commit_mc(xempty, pairmask);
+                                                umma2_commit_mc(layerdone, pairmask);
                                             }
                                         }
                                     }
@@ -223,15 +236,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
         } else {
             // ======================= peer relay: my half-tiles have landed -> leader ========
             if (lane == 0) {
-                const uint32_t r_xfull = mapa_u32(smem_u32(xfull), 0);
+                const uint32_t r_xfull = mapa_u32(smem_u32(xfull), lead);
                 int slot = 0; uint32_t ph = 0;
-                constexpr int NG = 2 * NCH * ((1 + KBH + 3) / 4 + (2 * KBH + 3) / 4);   // groups per time step (producer loop)
+                constexpr int NG = 2 * NCHS * ((1 + KBH + 3) / 4 + (2 * KBH + 3) / 4);   // groups per time step (producer loop)
                 for (int t = 0; t < Tp; ++t) {
                     mbar_wait(xfull, t & 1);
                     mbar_arrive_remote(r_xfull);
                     for (int g = 0; g < NG; ++g) {
                         mbar_wait(&full[slot], ph);
-                        mbar_arrive_remote(mapa_u32(smem_u32(&full[slot]), 0));
+                        mbar_arrive_remote(mapa_u32(smem_u32(&full[slot]), lead));
                         if (++slot == nstage) { slot = 0; ph ^= 1; }
                     }
                 }
@@ -245,7 +258,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
         // fp16 at B = 64) is never written to or read from global memory.  Same arithmetic as sb_pack_kernel (k_front.cu).
         if (a.xs.win) {
             const XSrc& xs = a.xs;
-            const int j0 = (warp - (D5_EPI_WARPS + 2)) * 32 + lane;    // rows j0 and j0 + 64: lanes <-> consecutive bins (coalesced loads)
+            const int rj = (warp - (D5_EPI_WARPS + 2)) * 32 + lane;    // rows rj and rj + 64: lanes <-> consecutive bins (coalesced loads)
             const int nw = 2 * xs.Ns + 1, nf = 2 * xs.Nf + 1, I = nw + xs.nfb * nf, nchunk = (I + 7) >> 3;
             const int F = a.F;
             int rb[2], rf[2];
@@ -253,14 +266,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
             bool ok[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                const int grow = tile * 128 + j0 + 64 * i;
+                const int grow = tile * 128 + rj + 64 * i;
                 ok[i] = grow < a.rows;
                 rb[i] = ok[i] ? grow / F : 0; rf[i] = ok[i] ? grow % F : 0;
                 const float mu = __ldg(xs.mu + rb[i]);
                 inv[i] = xs.gauss ? 1.0f / (__ldg(xs.sigma + rb[i]) + 1e-5f) : 1.0f / (mu + 1e-5f);
                 sub[i] = xs.gauss ? mu : 0.f;
                 for (int c = 0; c < 8; ++c)                            // columns >= I and rows >= B*F stay zero for the whole launch
-                    *reinterpret_cast<uint4*>(ximg + sw128_offset(j0 + 64 * i, c * 8)) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(ximg + sw128_offset(rj + 64 * i, c * 8)) = make_uint4(0u, 0u, 0u, 0u);
             }
             auto src = [&](int i, int k, int t) -> const float* {
                 if (k < nw) return xs.win + rb[i] * xs.win_sb + reflect_idx(rf[i] + k - xs.Ns, F) * xs.win_sf + t * xs.win_st;
@@ -282,7 +295,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                         float w[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) w[e] = (c * 8 + e < I) ? fminf(fmaxf((v[i][e] - sub[i]) * inv[i], -65504.f), 65504.f) : 0.f;
-                        *reinterpret_cast<uint4*>(ximg + sw128_offset(j0 + 64 * i, c * 8)) =
+                        *reinterpret_cast<uint4*>(ximg + sw128_offset(rj + 64 * i, c * 8)) =
                             make_uint4(pack_half2(w[0], w[1]), pack_half2(w[2], w[3]), pack_half2(w[4], w[5]), pack_half2(w[6], w[7]));
                     }
                 }
@@ -301,8 +314,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
         const uint32_t acc_my = acc_col + 64 * set + 32 * (cg >> 1);
         uint64_t* my_accfull = &accfull[set];
         uint64_t* my_accempty = &accempty[set];
-        const uint32_t r_accempty = mapa_u32(smem_u32(my_accempty), 0);
-        const uint32_t r_hready[2] = {mapa_u32(smem_u32(&hready[0]), 0), mapa_u32(smem_u32(&hready[1]), 0)};
+        const uint32_t r_accempty = mapa_u32(smem_u32(my_accempty), lead);
+        const uint32_t r_hready[2] = {mapa_u32(smem_u32(&hready[0]), lead), mapa_u32(smem_u32(&hready[1]), lead)};
         {
             const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int c = cg; c < 2 * NCH * 2; c += 4) tmem_st8(tl + c * 8, z);
@@ -316,6 +329,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
         float4 cnext[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};   // t = 0: zero cell state
         float* cbase = a.cstate + (size_t)tile * 2 * H * 128;
         uint8_t* mypark = park + ((size_t)cg * NCH * 128 + r) * 16;
+        // S > 1: the same-row CTAs of the other pairs (cluster ranks 2 s' + rank): their park / fc-partial / barrier addresses
+        uint32_t r_park[S > 1 ? S - 1 : 1], r_hall[S > 1 ? S - 1 : 1], r_pfree[S > 1 ? S - 1 : 1];
+        uint32_t r_fcp = 0;
+        if (S > 1) {
+            int n = 0;
+            for (int sp = 0; sp < S; ++sp) {
+                if (sp == (int)sidx) continue;
+                const uint32_t cr = 2 * sp + rank;
+                r_park[n] = mapa_u32(smem_u32(mypark), cr);
+                r_hall[n] = mapa_u32(smem_u32(hall), cr);
+                r_pfree[n] = mapa_u32(smem_u32(pfree), cr);
+                ++n;
+            }
+            r_fcp = mapa_u32(smem_u32(fcpart + ((size_t)(sidx * 4 + cg) * 128 + r) * 2), rank);   // pair 0 (same rows) sums the fc partials
+        }
         const int grow = tile * 128 + r;
         const int ob = grow / a.F, of = grow % a.F;
         const int Tout = Tp - a.la;
@@ -329,7 +357,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                     const size_t ni = ((size_t)ob * a.F + of) * Tout + (t - a.la);
                     nx = make_float2(__ldg(a.nreal + ni), __ldg(a.nimag + ni));
                 }
-                for (int j = 0; j < NCH; ++j) {
+                if (S > 1 && ls > 0) mbar_wait_cluster(pfree, (ls - 1) & 1);   // what I parked remotely last layer-step has been consumed
+                for (int j = j0; j < j0 + NCHS; ++j) {
                     float4* cp = reinterpret_cast<float4*>(cbase + ((size_t)((layer * NCH + j) * 4 + cg) * 2) * 128 * 4) + r;
                     const float4 c4[2] = {cnext[0], cnext[1]};     // prefetched during the previous chunk
                     const float4* bj = reinterpret_cast<const float4*>(bsm + (size_t)(layer * NCH + j) * 128 + cg * 32);
@@ -344,9 +373,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                     __syncwarp();
                     if (lane == 0) { if (leader) mbar_arrive(my_accempty); else mbar_arrive_remote(r_accempty); }
                     {   // cell state of the NEXT chunk in program order: (layer, j+1), else chunk 0 of the other layer (next step after layer 1)
-                        const int nj = (j + 1 < NCH) ? j + 1 : 0;
-                        const int nl = (j + 1 < NCH) ? layer : (layer ^ 1);
-                        const int nt = (j + 1 < NCH || layer == 0) ? t : t + 1;
+                        const int nj = (j + 1 < j0 + NCHS) ? j + 1 : j0;
+                        const int nl = (j + 1 < j0 + NCHS) ? layer : (layer ^ 1);
+                        const int nt = (j + 1 < j0 + NCHS || layer == 0) ? t : t + 1;
                         const float4* np = reinterpret_cast<const float4*>(cbase + ((size_t)((nl * NCH + nj) * 4 + cg) * 2) * 128 * 4) + r;
                         if (nt == 0 || nt >= Tp) { cnext[0] = make_float4(0.f, 0.f, 0.f, 0.f); cnext[1] = cnext[0]; }
                         else { cnext[0] = np[0]; cnext[1] = np[128]; }
@@ -388,8 +417,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                     cp[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
                     cp[128] = make_float4(cn[4], cn[5], cn[6], cn[7]);
                     *reinterpret_cast<uint4*>(mypark + (size_t)j * 128 * 16) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                    if (S > 1) {
+#pragma unroll
+                        for (int n = 0; n < S - 1; ++n) st_cluster_v4(r_park[n] + (uint32_t)j * 128 * 16, make_uint4(hp[0], hp[1], hp[2], hp[3]));
+                    }
+                }
+                if (S > 1) {
+                    if (layer == 1) {                              // my pair's share of Linear(H -> 2): summed by pair 0 after the exchange
+                        if (sidx == 0) { fcpart[((size_t)cg * 128 + r) * 2] = fc0; fcpart[((size_t)cg * 128 + r) * 2 + 1] = fc1; }
+                        else st_cluster_v2f(r_fcp, fc0, fc1);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        fence_acq_rel_cluster();                   // the warp's remote stores happen-before the arrives below
+#pragma unroll
+                        for (int n = 0; n < S - 1; ++n) mbar_arrive_remote(r_hall[n]);
+                    }
                 }
                 mbar_wait(layerdone, ls & 1);
+                if (S > 1) mbar_wait_cluster(hall, ls & 1);        // every other pair's chunks of this layer-step are in my park buffer
                 tc5_fence_after();
                 for (int j = 0; j < NCH; ++j) {
                     const uint4 p0 = *reinterpret_cast<const uint4*>(mypark + (size_t)j * 128 * 16);
@@ -402,11 +448,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                 if (lane == 0) { if (leader) mbar_arrive(&hready[layer]); else mbar_arrive_remote(r_hready[layer]); }
 
                 if (layer == 1) {
-                    if (cg != 0) { fcpart[(cg * 128 + r) * 2] = fc0; fcpart[(cg * 128 + r) * 2 + 1] = fc1; }
+                    if (S == 1 && cg != 0) { fcpart[(cg * 128 + r) * 2] = fc0; fcpart[(cg * 128 + r) * 2 + 1] = fc1; }
                     asm volatile("bar.sync 1, 512;" ::: "memory");
-                    if (cg == 0 && t >= a.la && grow < a.rows) {
-                        const float o0 = fc0 + fcpart[(128 + r) * 2] + fcpart[(256 + r) * 2] + fcpart[(384 + r) * 2] + fcb0;
-                        const float o1 = fc1 + fcpart[(128 + r) * 2 + 1] + fcpart[(256 + r) * 2 + 1] + fcpart[(384 + r) * 2 + 1] + fcb1;
+                    if (cg == 0 && t >= a.la && grow < a.rows && sidx == 0) {
+                        float o0 = fcb0, o1 = fcb1;
+                        if (S == 1) {
+                            o0 += fc0 + fcpart[(128 + r) * 2] + fcpart[(256 + r) * 2] + fcpart[(384 + r) * 2];
+                            o1 += fc1 + fcpart[(128 + r) * 2 + 1] + fcpart[(256 + r) * 2 + 1] + fcpart[(384 + r) * 2 + 1];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4 * S; ++i) { o0 += fcpart[((size_t)i * 128 + r) * 2]; o1 += fcpart[((size_t)i * 128 + r) * 2 + 1]; }
+                        }
                         if (a.enh) {                                   // fused decompress_cIRM x noisy spectrum (inferencer.py:152-157)
                             const float m0 = decompress_cirm(apply_act(o0, a.act)), m1 = decompress_cirm(apply_act(o1, a.act));
                             __stcs(a.enh + ((size_t)ob * a.F + of) * Tout + (t - a.la), make_float2(m0 * nx.x - m1 * nx.y, m1 * nx.x + m0 * nx.y));
@@ -416,6 +468,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
                         }
                     }
                     asm volatile("bar.sync 2, 512;" ::: "memory");
+                }
+                if (S > 1) {                                       // park (and, after layer 1, the fc partials) of this layer-step are consumed
+                    __syncwarp();
+                    if (lane == 0) {
+#pragma unroll
+                        for (int n = 0; n < S - 1; ++n) mbar_arrive_remote(r_pfree[n]);
+                    }
                 }
             }
         }
@@ -427,29 +486,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D5_THREADS, 1) lstm_
     if (warp == D5_EPI_WARPS + 1) tmem_dealloc_pair<512>(tmem);
 }
 
-int launch_lstm_tc5_dbuf(const LstmTc5Launch& a, cudaStream_t s) {
-    if (!lstm_tc5_supported(2, a.H, a.I, 2)) return (int)cudaErrorInvalidValue;
-    D5Plan p = d5_plan(a.H);
+// column split for small batches: the largest S in {4, 2, 1} that divides the chunk count and whose clusters (2 S CTAs, one per SM)
+// all fit on the GPU at once (8-CTA clusters: two per GPC); a.split forces a value (0 = auto)
+static int d5_pick_split(int H, int npairs, int forced) {
+    const int nch = H / 32;
+    if (forced == 1 || forced == 2 || forced == 4) return (nch % forced == 0) ? forced : 1;
+    if (nch % 4 == 0 && npairs <= 16) return 4;
+    if (nch % 2 == 0 && npairs <= 32) return 2;
+    return 1;
+}
+
+template <int HH, bool FF, bool GG, int SS>
+static int d5_go(const LstmTc5Launch& a, int npairs, cudaStream_t s) {
+    const D5Plan p = d5_plan(HH, SS);
     if (p.nstage < 2) return (int)cudaErrorInvalidValue;
-    const int grid = (a.ntiles + 1) / 2 * 2;                        // whole pairs; the buffers cover the padded tile
-    cudaError_t e = cudaErrorInvalidValue;
-#define D5_GO(HH, FF, GG)                                                                                               \
-    {                                                                                                                   \
-        e = cudaFuncSetAttribute(lstm_tc5d_kernel<HH, FF, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);  \
-        if (e != cudaSuccess) return (int)e;                                                                            \
-        lstm_tc5d_kernel<HH, FF, GG><<<grid, D5_THREADS, p.total, s>>>(a, p.nstage);                                   \
-    }
-#define D5_LAUNCH(HH)                                                                                                   \
-    if (a.H == HH) {                                                                                                    \
-        if (a.gru) { if (a.fast) D5_GO(HH, true, true) else D5_GO(HH, false, true) }                                    \
-        else { if (a.fast) D5_GO(HH, true, false) else D5_GO(HH, false, false) }                                        \
-    }
-    D5_LAUNCH(64) D5_LAUNCH(128) D5_LAUNCH(192) D5_LAUNCH(256) D5_LAUNCH(320) D5_LAUNCH(384)
-#undef D5_GO
-#undef D5_LAUNCH
+    cudaError_t e = cudaFuncSetAttribute(lstm_tc5d_kernel<HH, FF, GG, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);
     if (e != cudaSuccess) return (int)e;
+    lstm_tc5d_kernel<HH, FF, GG, SS><<<npairs * 2 * SS, D5_THREADS, p.total, s>>>(a, p.nstage);
     return (int)cudaGetLastError();
 }
+template <int HH, int SS>
+static int d5_dispatch(const LstmTc5Launch& a, int npairs, cudaStream_t s) {
+    if (a.gru) return a.fast ? d5_go<HH, true, true, SS>(a, npairs, s) : d5_go<HH, false, true, SS>(a, npairs, s);
+    return a.fast ? d5_go<HH, true, false, SS>(a, npairs, s) : d5_go<HH, false, false, SS>(a, npairs, s);
+}
+template <int HH>
+static int d5_split(const LstmTc5Launch& a, int npairs, int S, cudaStream_t s) {
+    constexpr int nch = HH / 32;
+    if constexpr (nch % 4 == 0) { if (S == 4) return d5_dispatch<HH, 4>(a, npairs, s); }
+    if constexpr (nch % 2 == 0) { if (S == 2) return d5_dispatch<HH, 2>(a, npairs, s); }
+    return d5_dispatch<HH, 1>(a, npairs, s);
+}
+
+int launch_lstm_tc5_dbuf(const LstmTc5Launch& a, cudaStream_t s) {
+    if (!lstm_tc5_supported(2, a.H, a.I, 2)) return (int)cudaErrorInvalidValue;
+    const int npairs = (a.ntiles + 1) / 2;                          // whole pairs; the buffers cover the padded tile
+    const int S = d5_pick_split(a.H, npairs, a.split);
+    switch (a.H) {
+        case 64: return d5_split<64>(a, npairs, S, s);
+        case 128: return d5_split<128>(a, npairs, S, s);
+        case 192: return d5_split<192>(a, npairs, S, s);
+        case 256: return d5_split<256>(a, npairs, S, s);
+        case 320: return d5_split<320>(a, npairs, S, s);
+        case 384: return d5_split<384>(a, npairs, S, s);
+    }
+    return (int)cudaErrorInvalidValue;
+}
+
+int lstm_tc5_split_for(int H, int ntiles, int forced) { return d5_pick_split(H, (ntiles + 1) / 2, forced); }
 
 }  // namespace fsn
 

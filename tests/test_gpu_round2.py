@@ -368,3 +368,53 @@ def test_enhance_pipeline_matches_enhance_batch(built_lib, golden):
     pipe.flush()
     for k in (0, 1):
         assert O.rel_l2(pipe.host_out[k].numpy(), want[k].cpu().numpy()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# small-batch column-split mode of the fused tcgen05 kernel (k_lstm_tc5d.cu, S CTA pairs per 256 sequences)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,S,rnn", [(64, 2, "LSTM"), (128, 2, "LSTM"), (128, 4, "LSTM"), (128, 4, "GRU"), (256, 4, "LSTM")])
+def test_column_split_small_configs(built_lib, monkeypatch, H, S, rnn):
+    """Forced split (FSN_TC5_SPLIT is read once at model creation) against the oracle and against the unsplit kernel: several row
+    tiles (B*F = 9*33 = 297 rows -> 3 tiles -> 2 pairs, the second half empty), sb activation on, fused enhance output."""
+    cfg = dict(_small(H), sequence_model=rnn, sb_output_activate_function="Tanh")
+    params = O.make_params_plus(cfg, seed=70 + S, lstm_scale=2.0)
+    mag, real, imag = _inputs(9, 33, 23, 31)
+    ref = O.fullsubnet_plus_forward(params, cfg, mag, real, imag)
+    monkeypatch.setenv("FSN_TC5_SPLIT", "1")
+    m1 = _plus(cfg, params, lstm_impl="tcgen05")
+    monkeypatch.setenv("FSN_TC5_SPLIT", str(S))
+    ms = _plus(cfg, params, lstm_impl="tcgen05")
+    with torch.no_grad():
+        o1 = m1(_t(mag), _t(real), _t(imag))
+        os_ = ms(_t(mag), _t(real), _t(imag))
+        os2 = ms(_t(mag), _t(real), _t(imag))
+        e1 = m1.enhance_spectrum(_t(mag), _t(real), _t(imag))
+        es = ms.enhance_spectrum(_t(mag), _t(real), _t(imag))
+    err, dsplit = O.rel_l2(os_.cpu().numpy(), ref), O.rel_l2(os_.cpu().numpy(), o1.cpu().numpy())
+    print(f"\n[column split H={H} S={S} {rnn}] cIRM vs oracle {err:.3e}; vs unsplit kernel {dsplit:.2e}")
+    assert torch.equal(os_, os2)                                         # deterministic
+    assert err < MASK_TOL and dsplit < 1e-5                              # same arithmetic; only the fp32 summation order of Linear(H -> 2) differs
+    assert O.rel_l2(torch.view_as_real(es).cpu().numpy(), torch.view_as_real(e1).cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("B", [1, 2, 8, 20])
+def test_column_split_default_geometry_auto(built_lib, golden, monkeypatch, B):
+    """Default geometry, automatic split (B = 1, 2, 8 -> S = 4; B = 20 -> 21 pairs -> S = 2): sample 0 is the golden clip, the others
+    are shifted / scaled copies; every sample against the unsplit kernel (FSN_TC5_SPLIT=1), sample 0 against the reference golden."""
+    g = golden("plus_default")
+    cfg = O.default_plus_config()
+    params = O.make_params_plus(cfg, seed=0)
+    m = _plus(cfg, params)
+    monkeypatch.setenv("FSN_TC5_SPLIT", "1")
+    m1 = _plus(cfg, params)
+    rng = np.random.default_rng(B)
+    sc = np.concatenate([[1.0], rng.uniform(0.5, 2.0, B - 1)]).astype(np.float32).reshape(B, 1, 1, 1)
+    sh = np.concatenate([[0], rng.integers(0, 188, B - 1)])
+    rep = lambda x: np.stack([np.roll(x[0], int(k), axis=-1) for k in sh]) * sc
+    ins = [_t(rep(g[k])) for k in ("mag", "real", "imag")]
+    with torch.no_grad():
+        out, out1 = m(*ins), m1(*ins)
+    e0, d = O.rel_l2(out[0:1].cpu().numpy(), g["out"]), O.rel_l2(out.cpu().numpy(), out1.cpu().numpy())
+    print(f"\n[column split default geometry B={B}] sample 0 vs reference golden {e0:.3e}; batch vs unsplit kernel {d:.2e}")
+    assert e0 < MASK_TOL and d < 1e-5
