@@ -50,6 +50,9 @@ def plus_cfg(**over):
     return c
 
 
+default_cfg = plus_cfg          # name used by scripts/ and tests/dist_check.py
+
+
 def fsn_cfg(**over):
     """fullsubnet.Model with the same hyper-parameters (reference fullsubnet.py:13-26)."""
     c = dict(sb_num_neighbors=15, fb_num_neighbors=0, num_freqs=257, look_ahead=2, sequence_model="LSTM",

@@ -146,6 +146,21 @@ __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_s
                  : "memory");
 }
 
+// plain global accesses with an L2 eviction-priority hint (same policies as the bulk copies above)
+__device__ __forceinline__ float ldg_hint(const float* p, uint64_t policy) {
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ float4 ld_f4_hint(const float4* p, uint64_t policy) {
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_f4_hint(float4* p, float4 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
+}
+
 // One lane of a fully converged warp (elect.sync).  The tcgen05 issue loops must stay warp-uniform and predicate only
 // the instruction on this: an `if (lane == 0)` region forces every UTCHMMA operand through R2UR moves and serialises the
 // mbarrier polls with the issue -- measured 109 vs 64 cycles per M=128,N=128 MMA (fsn_probe_tcgen05, "probe4").

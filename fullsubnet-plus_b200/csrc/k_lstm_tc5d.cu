@@ -275,6 +275,7 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
                 for (int c = 0; c < 8; ++c)                            // columns >= I and rows >= B*F stay zero for the whole launch
                     *reinterpret_cast<uint4*>(ximg + sw128_offset(rj + 64 * i, c * 8)) = make_uint4(0u, 0u, 0u, 0u);
             }
+            const uint64_t pol_x = l2_policy_evict_first();          // read (almost) once: must not push the cell-state scratch out of L2
             auto src = [&](int i, int k, int t) -> const float* {
                 if (k < nw) return xs.win + rb[i] * xs.win_sb + reflect_idx(rf[i] + k - xs.Ns, F) * xs.win_sf + t * xs.win_st;
                 const int kk = k - nw, q = kk / nf, jn = kk - q * nf;
@@ -288,7 +289,7 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
 #pragma unroll
                     for (int i = 0; i < 2; ++i)
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[i][e] = (ok[i] && c * 8 + e < I) ? __ldg(src(i, c * 8 + e, t)) : 0.f;
+                        for (int e = 0; e < 8; ++e) v[i][e] = (ok[i] && c * 8 + e < I) ? ldg_hint(src(i, c * 8 + e, t), pol_x) : 0.f;
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         if (!ok[i]) continue;
@@ -326,6 +327,7 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
                 for (int l = 0; l < 2; ++l) { if (leader) mbar_arrive(&hready[l]); else mbar_arrive_remote(r_hready[l]); }
         }
         uint32_t accn = 0, ls = 0;
+        const uint64_t pol_c = l2_policy_evict_last();               // the fp32 cell state lives in L2 for the whole launch
         float4 cnext[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};   // t = 0: zero cell state
         float* cbase = a.cstate + (size_t)tile * 2 * H * 128;
         uint8_t* mypark = park + ((size_t)cg * NCH * 128 + r) * 16;
@@ -378,7 +380,7 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
                         const int nt = (j + 1 < j0 + NCHS || layer == 0) ? t : t + 1;
                         const float4* np = reinterpret_cast<const float4*>(cbase + ((size_t)((nl * NCH + nj) * 4 + cg) * 2) * 128 * 4) + r;
                         if (nt == 0 || nt >= Tp) { cnext[0] = make_float4(0.f, 0.f, 0.f, 0.f); cnext[1] = cnext[0]; }
-                        else { cnext[0] = np[0]; cnext[1] = np[128]; }
+                        else { cnext[0] = ld_f4_hint(np, pol_c); cnext[1] = ld_f4_hint(np + 128, pol_c); }
                     }
 
                     const float L2E = 1.4426950408889634f;
@@ -414,8 +416,8 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
                         hp[2 * u4] = pack_half2(hv[0], hv[1]);
                         hp[2 * u4 + 1] = pack_half2(hv[2], hv[3]);
                     }
-                    cp[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                    cp[128] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                    st_f4_hint(cp, make_float4(cn[0], cn[1], cn[2], cn[3]), pol_c);
+                    st_f4_hint(cp + 128, make_float4(cn[4], cn[5], cn[6], cn[7]), pol_c);
                     *reinterpret_cast<uint4*>(mypark + (size_t)j * 128 * 16) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                     if (S > 1) {
 #pragma unroll

@@ -25,10 +25,41 @@ def stft(y, n_fft=512, hop_length=256, win_length=512):
                       return_complex=True)
 
 
+_ISTFT_ENV = {}
+
+
 def istft(spec, n_fft=512, hop_length=256, win_length=512, length=None):
-    """reference audio_zen/acoustics/feature.py:34-65 (complex input)."""
-    return torch.istft(spec, n_fft, hop_length, win_length, window=torch.hann_window(n_fft, device=spec.device),
-                       length=length)
+    """reference audio_zen/acoustics/feature.py:34-65 (complex input) = torch.istft(spec, n_fft, hop, win, hann window, center=True).
+
+    Restated with the same ATen operators torch.istft issues (irfft -> window -> overlap-add by ``fold`` -> division by the
+    overlap-added squared window) but WITHOUT its "window overlap add min" check: that check reads a GPU scalar back to the host and
+    therefore synchronises the calling thread with the stream on every call, which would serialise the pipelined harness
+    (EnhancePipeline: the host must be able to enqueue batch i+1 while batch i is still on the GPU).  The envelope depends only on
+    (n_fft, hop, window, frames), so it is built -- and checked -- once per geometry and cached.  CPU tensors use torch.istft."""
+    if not spec.is_cuda or win_length != n_fft:
+        return torch.istft(spec, n_fft, hop_length, win_length, window=torch.hann_window(n_fft, device=spec.device), length=length)
+    B, F, T = spec.shape
+    full = n_fft + hop_length * (T - 1)
+    key = (n_fft, hop_length, T, spec.device)
+    if key not in _ISTFT_ENV:
+        window = torch.hann_window(n_fft, device=spec.device)
+        env = torch.nn.functional.fold((window * window).view(1, n_fft, 1).expand(1, n_fft, T), output_size=(1, full),
+                                       kernel_size=(1, n_fft), stride=(1, hop_length)).reshape(full)
+        start = n_fft // 2
+        if not bool(env[start: full - start].abs().min() > 1e-11):          # the check torch.istft makes on every call, made once here
+            raise RuntimeError("istft: window overlap add min is zero for this n_fft / hop_length")
+        _ISTFT_ENV[key] = (window, env)
+    window, env = _ISTFT_ENV[key]
+    frames = torch.fft.irfft(spec.transpose(1, 2), n=n_fft, dim=-1) * window              # [B, T, n_fft]
+    y = torch.nn.functional.fold(frames.transpose(1, 2), output_size=(1, full), kernel_size=(1, n_fft),
+                                 stride=(1, hop_length)).reshape(B, full)
+    start = n_fft // 2
+    end = start + length if length is not None else full - start
+    if end > full:                                                                        # torch.istft pads with zeros up to `length`
+        y = torch.nn.functional.pad(y, (0, end - full))
+        envp = torch.nn.functional.pad(env, (0, end - full), value=1.0)
+        return y[:, start:end] / envp[start:end]
+    return y[:, start:end] / env[start:end]
 
 
 def decompress_cIRM(mask, K=10, limit=9.9):

@@ -26,6 +26,18 @@ def main():
     ref = inf.enhance_batch(model, clips)
     err = (out - ref).norm() / ref.norm()
     ok = out.shape == ref.shape and err.item() < 1e-5
+    # the pipelined path of bench.py: every rank pushes its own batches, the all-gather of batch i runs on the side stream under the
+    # forward of batch i+1; result k must be the concatenation of all ranks' enhanced batch k
+    mine = [synth_clips(3, 48000, 16000, seed=100 * k + rank).to(dev) for k in range(3)]
+    pipe = inf.EnhancePipeline(model, 48000)
+    for b in mine:
+        pipe.push(inf.stft(b))
+    got = [r.clone() for r in pipe.flush()]
+    for k in range(3):
+        want = torch.cat([inf.enhance_batch(model, synth_clips(3, 48000, 16000, seed=100 * k + r).to(dev)) for r in range(world)], 0)
+        e2 = ((got[k] - want).norm() / want.norm()).item()
+        ok = ok and got[k].shape == want.shape and e2 < 1e-5
+        err = torch.maximum(err, torch.tensor(e2, device=dev))
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
