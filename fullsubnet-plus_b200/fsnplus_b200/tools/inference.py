@@ -87,6 +87,19 @@ def read_wav(path, sr):
     return np.ascontiguousarray(y, dtype=np.float32)
 
 
+def wav_length(path, sr):
+    """Number of samples read_wav(path, sr) will return, from the header only (the data stay on disk: memory-mapped)."""
+    from scipy.io import wavfile
+    rate, x = wavfile.read(str(path), mmap=True)
+    n = int(x.shape[0])
+    if rate != sr:
+        from math import gcd
+        g = gcd(int(rate), int(sr))
+        up, down = sr // g, rate // g
+        n = -(-n * up // down)                                            # scipy.signal.resample_poly: ceil(n * up / down)
+    return n
+
+
 def to_int16(enhanced):
     """base_inferencer.py:151-152."""
     amp = np.iinfo(np.int16).max
@@ -113,14 +126,15 @@ def bucket_by_length(lengths, batch_size):
     return batches
 
 
-def build_model(model_config, checkpoint_path, device):
-    """base_inferencer.py:97-110 (_load_model)."""
+def build_model(model_config, checkpoint_path, device, trust_checkpoint=False):
+    """base_inferencer.py:97-110 (_load_model).  The checkpoint is read with ``weights_only=True`` (tensors and plain containers
+    only: the reference's ``{"model": state_dict, "epoch": int}`` loads); ``trust_checkpoint=True`` opts into full unpickling."""
     from .. import model as M
     path = model_config["path"]
     if path not in MODEL_PATHS:
         raise NotImplementedError(f"[model].path = {path!r} is not one of {sorted(MODEL_PATHS)}")
     net = getattr(M, MODEL_PATHS[path])(**model_config["args"])
-    ckpt = torch.load(str(checkpoint_path), map_location="cpu", weights_only=False)
+    ckpt = torch.load(str(checkpoint_path), map_location="cpu", weights_only=not trust_checkpoint)
     net.load_state_dict(ckpt["model"])
     return net.to(device).eval(), ckpt["epoch"]
 
@@ -130,7 +144,7 @@ def _rank_world():
 
 
 @torch.no_grad()
-def run(config, checkpoint_path, output_dir, batch_size=64, device=None, log=print, model_and_epoch=None):
+def run(config, checkpoint_path, output_dir, batch_size=64, device=None, log=print, model_and_epoch=None, trust_checkpoint=False):
     """Enhance every file of config["dataset"]["args"]["dataset_dir_list"].  Under torchrun each rank takes every
     world-size-th batch (files are independent: no collective).  Returns {name: path} of the files this rank wrote.
     ``model_and_epoch`` (tests of the host logic) replaces the checkpoint load with a ready ``(callable, epoch)``."""
@@ -144,18 +158,19 @@ def run(config, checkpoint_path, output_dir, batch_size=64, device=None, log=pri
         raise NotImplementedError(f"Not implemented Inferencer type: {itype}")       # base_inferencer.py:135
     files = find_files(config["dataset"]["args"]["dataset_dir_list"])
     ds_sr = config["dataset"]["args"].get("sr", sr)
-    model, epoch = model_and_epoch or build_model(config["model"], Path(checkpoint_path).expanduser().absolute(), device)
+    model, epoch = model_and_epoch or build_model(config["model"], Path(checkpoint_path).expanduser().absolute(), device, trust_checkpoint)
     on_gpu = torch.device(device).type == "cuda"
     enhanced_dir = Path(output_dir).expanduser().absolute() / f"enhanced_{str(epoch).zfill(4)}"
     enhanced_dir.mkdir(parents=True, exist_ok=True)
 
-    clips = [read_wav(p, ds_sr) for p in files]
-    batches = bucket_by_length([len(c) for c in clips], batch_size)
+    # bucket on the lengths from the WAV headers; a rank decodes only the files of ITS batches, one batch at a time (host memory
+    # and start-up time scale with the batch, not with the dataset -- the reference streams one clip at a time)
+    batches = bucket_by_length([wav_length(p, ds_sr) for p in files], batch_size)
     written, audio_s, gpu_s = {}, 0.0, 0.0
     for bi, idx in enumerate(batches):
         if bi % world != rank:
             continue
-        noisy = torch.from_numpy(np.stack([clips[i] for i in idx]))
+        noisy = torch.from_numpy(np.stack([read_wav(files[i], ds_sr) for i in idx]))
         if on_gpu:
             noisy = noisy.pin_memory().to(device, non_blocking=True)
             torch.cuda.synchronize(device)
@@ -186,12 +201,13 @@ def main(argv=None):
                         type=lambda s: [item.strip() for item in s.split(",")])
     parser.add_argument("-O", "--output_dir", type=str, required=True, help="The path for saving enhanced speeches.")
     parser.add_argument("--batch_size", type=int, default=64, help="clips of equal length per launch (additive)")
+    parser.add_argument("--trust_checkpoint", action="store_true", help="unpickle arbitrary objects from the checkpoint (default: tensors only)")
     args = parser.parse_args(argv)
     configuration = load_toml(args.configuration)
     if len(args.dataset_dir_list) > 0:
         print(f"use specified dataset_dir_list: {args.dataset_dir_list}, instead of in config")
         configuration["dataset"]["args"]["dataset_dir_list"] = args.dataset_dir_list
-    run(configuration, args.model_checkpoint_path, args.output_dir, batch_size=args.batch_size)
+    run(configuration, args.model_checkpoint_path, args.output_dir, batch_size=args.batch_size, trust_checkpoint=args.trust_checkpoint)
 
 
 if __name__ == "__main__":

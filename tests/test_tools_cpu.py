@@ -116,3 +116,14 @@ def test_run_host_logic_with_rank_sharding(tmp_path, monkeypatch):
         assert rate == 16000 and pcm.dtype == np.int16 and pcm.shape == (n,)
         want = T.to_int16(x)                                   # a positive gain cancels in the peak normalisation
         assert np.abs(pcm.astype(int) - want.astype(int)).max() <= 2, i     # STFT -> iSTFT round trip in fp32
+
+
+def test_wav_length_matches_read_wav_without_decoding(tmp_path):
+    """Bucketing uses the header-only length (mmap); it must equal what read_wav returns, also after resampling."""
+    from scipy.io import wavfile
+    from fsnplus_b200.tools import inference as T
+    rng = np.random.default_rng(0)
+    for rate, n in ((16000, 12345), (44100, 30001), (8000, 7999), (48000, 48000)):
+        p = tmp_path / f"x_{rate}.wav"
+        wavfile.write(p, rate, (rng.standard_normal(n) * 3000).astype(np.int16))
+        assert T.wav_length(p, 16000) == len(T.read_wav(p, 16000)), (rate, n)
