@@ -99,12 +99,16 @@ struct fsn_model {
     // FSN_NO_WS=1 keeps the full-band LSTM of fullsubnet.Model off the weight-stationary kernel
     int env_impl = 0;
     int env_split = 0;                                 // FSN_TC5_SPLIT: force the small-batch column split (1 / 2 / 4; 0 = auto)
+    // FSN_FRONT_OVERLAP=1: the pipelined entry points run the front end of batch i+1 concurrently with the sub-band LSTM of batch i
+    // (two lanes, two streams).  Off by default: measured zero-sum on B200 -- the LSTM kernel runs at the board's power cap, and
+    // what the front end gains on the 18 idle SMs the LSTM loses in clock (profiles/r02_front_overlap.txt).
+    bool env_front_overlap = false;
     bool env_no_ws = false, env_no_xfuse = false;      // FSN_NO_XFUSE=1: packed sub-band images instead of the fused unfold (A/B only)
     // pipelined execution: front-end stream, LSTM stream (higher priority), copy-in / copy-out streams, per-slot events
     cudaStream_t s_front = nullptr, s_lstm = nullptr, s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in = nullptr, ev_plain = nullptr;   // caller's inputs ready / last plain forward finished
     bool plain_pending = false;
-    cudaEvent_t ev_h2d[2] = {}, ev_d2h[2] = {};
+    cudaEvent_t ev_h2d[2] = {}, ev_d2h[2] = {}, ev_done[2] = {};   // per staging slot: inputs copied / mask copied out / forward finished
     bool d2h_used[2] = {false, false};
     DevBuf a_in[2][3], a_out[2];
     int64_t nsub = 0;
@@ -375,6 +379,7 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     { const char* e = getenv("FSN_NO_WS"); m->env_no_ws = e && atoi(e) != 0; }
     { const char* e = getenv("FSN_NO_XFUSE"); m->env_no_xfuse = e && atoi(e) != 0; }
     { const char* e = getenv("FSN_TC5_SPLIT"); if (e && *e) m->env_split = atoi(e); }
+    { const char* e = getenv("FSN_FRONT_OVERLAP"); m->env_front_overlap = e && atoi(e) != 0; }
     build_specs(m);
     for (int i = 0; i < fsn_model::NEV; ++i) { cudaEventCreate(&m->ev0[i]); cudaEventCreate(&m->ev1[i]); cudaEventCreate(&m->evf0[i]); cudaEventCreate(&m->evf1[i]); }
     { cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev); if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) m->num_sms = prop.multiProcessorCount; }
@@ -399,7 +404,7 @@ extern "C" void fsn_model_destroy(fsn_model* m) {
     if (m->cublas) cublasDestroy(m->cublas);
     if (m->s_front) { cudaStreamDestroy(m->s_front); cudaStreamDestroy(m->s_lstm); cudaEventDestroy(m->ev_in); }
     if (m->ev_plain) cudaEventDestroy(m->ev_plain);
-    if (m->s_in) { cudaStreamDestroy(m->s_in); cudaStreamDestroy(m->s_out); for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_h2d[i]); cudaEventDestroy(m->ev_d2h[i]); } }
+    if (m->s_in) { cudaStreamDestroy(m->s_in); cudaStreamDestroy(m->s_out); for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_h2d[i]); cudaEventDestroy(m->ev_d2h[i]); cudaEventDestroy(m->ev_done[i]); } }
     for (int i = 0; i < 2; ++i) { m->a_out[i].release(); for (int j = 0; j < 3; ++j) m->a_in[i][j].release(); }
     for (int i = 0; i < fsn_model::NEV; ++i) {
         if (m->ev0[i]) cudaEventDestroy(m->ev0[i]);
@@ -921,8 +926,10 @@ static int submit_impl(fsn_model* m, cudaEvent_t ready, const float* d_mag, cons
                        float* d_out, float* d_enh, int* lane_out) {
     int rc = ensure_pipeline(m);
     if (rc) return rc;
-    const bool overlap = (m->cfg.model_kind == FSN_KIND_PLUS);           // fullsubnet.Model: its full-band LSTM is a cooperative launch and
-    const int slot = overlap ? (int)(m->nsub & 1) : 0;                   // shares the LSTM scratch -> one lane, one stream, no overlap
+    // overlap needs the opt-in (see env_front_overlap) and FullSubNet+ (fullsubnet.Model's full-band LSTM is a cooperative launch and
+    // shares the LSTM scratch): otherwise one lane, one stream -- the pipeline still overlaps copies and the caller's post-processing
+    const bool overlap = m->env_front_overlap && (m->cfg.model_kind == FSN_KIND_PLUS);
+    const int slot = overlap ? (int)(m->nsub & 1) : 0;
     fsn_model::Lane& ln = m->lane[slot];
     cudaStream_t sf = overlap ? m->s_front : m->s_lstm;
     if (ready) CK(cudaStreamWaitEvent(sf, ready, 0));
@@ -1032,16 +1039,15 @@ extern "C" int fsn_model_forward_host_async(fsn_model* m, const float* h_mag, co
         for (int i = 0; i < 2; ++i) {
             CK(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&m->ev_d2h[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
         }
     }
-    const bool overlap = (c.model_kind == FSN_KIND_PLUS);
-    const int slot = overlap ? (int)(m->nsub & 1) : 0;                   // staging slot == lane
-    fsn_model::Lane& ln = m->lane[slot];
+    const int slot = (int)(m->nsub & 1);                                 // staging slot (the workspace lane is chosen by submit_impl)
     const size_t in_bytes = (size_t)B * c.num_freqs * T * 4, out_bytes = (size_t)B * c.output_size * c.num_freqs * T * 4;
     const float* hin[3] = {h_mag, h_real, h_imag};
     const int nin = (c.model_kind == FSN_KIND_PLUS) ? 3 : 1;
-    // the front end that read this input slot: it finished before the lane's LSTM did
-    if (ln.used) CK(cudaStreamWaitEvent(m->s_in, ln.ev_lstm, 0));
+    // the forward that read this input slot (front end: mag / real / imag; fused epilogue: real / imag) has finished
+    if (m->d2h_used[slot]) CK(cudaStreamWaitEvent(m->s_in, m->ev_done[slot], 0));
     for (int i = 0; i < nin; ++i) {
         if (!hin[i]) return fail(FSN_EINVAL, "missing input %d", i);
         if (m->a_in[slot][i].bytes < in_bytes) {
@@ -1060,7 +1066,8 @@ extern "C" int fsn_model_forward_host_async(fsn_model* m, const float* h_mag, co
     rc = submit_impl(m, m->ev_h2d[slot], static_cast<const float*>(m->a_in[slot][0].p), static_cast<const float*>(m->a_in[slot][1].p),
                      static_cast<const float*>(m->a_in[slot][2].p), B, T, static_cast<float*>(m->a_out[slot].p), nullptr, &used);
     if (rc) return rc;
-    CK(cudaStreamWaitEvent(m->s_out, ln.ev_lstm, 0));
+    CK(cudaEventRecord(m->ev_done[slot], m->s_lstm));
+    CK(cudaStreamWaitEvent(m->s_out, m->ev_done[slot], 0));
     CK(cudaMemcpyAsync(h_out, m->a_out[slot].p, out_bytes, cudaMemcpyDeviceToHost, m->s_out));
     CK(cudaEventRecord(m->ev_d2h[slot], m->s_out));
     m->d2h_used[slot] = true;

@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#ifdef FSN_MBAR_DEBUG
+#include <cstdio>
+#endif
 
 #if defined(__CUDA_ARCH__) && !defined(__CUDA_ARCH_FEAT_SM100_ALL)
 #error "fsnplus_b200 kernels must be compiled with -gencode arch=compute_100a,code=sm_100a"
@@ -110,6 +113,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef FSN_MBAR_TIMEOUT_CYCLES
 #define FSN_MBAR_TIMEOUT_CYCLES 3000000000ll   // ~2 s at B200 clocks; no legitimate wait is longer than ms
 #endif
+#ifdef FSN_MBAR_DEBUG
+// debug builds (-DFSN_MBAR_DEBUG): a watchdog expiry reports WHICH wait of which role hung before trapping
+#define mbar_wait(bar, parity) mbar_wait_dbg(bar, parity, __LINE__)
+__device__ __noinline__ void mbar_report(int line, uint32_t parity) {
+    printf("mbar timeout: line %d block %d thread %d (warp %d) parity %u\n", line, (int)blockIdx.x, (int)threadIdx.x, (int)(threadIdx.x >> 5), parity);
+}
+__device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, int line) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > FSN_MBAR_TIMEOUT_CYCLES) { mbar_report(line, parity); __nanosleep(2000000); __trap(); }
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
@@ -117,6 +134,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > FSN_MBAR_TIMEOUT_CYCLES) { __trap(); }
     }
 }
+#endif
 
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -273,6 +291,16 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
         : "memory");
     return ok != 0;
 }
+#ifdef FSN_MBAR_DEBUG
+#define mbar_wait_cluster(bar, parity) mbar_wait_cluster_dbg(bar, parity, __LINE__)
+__device__ __forceinline__ void mbar_wait_cluster_dbg(uint64_t* bar, uint32_t parity, int line) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > FSN_MBAR_TIMEOUT_CYCLES) { mbar_report(line, parity); __nanosleep(2000000); __trap(); }
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait_cluster(bar, parity)) return;
     const long long t0 = clock64();
@@ -280,6 +308,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         if (clock64() - t0 > FSN_MBAR_TIMEOUT_CYCLES) { __trap(); }
     }
 }
+#endif
 __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint4 v) {
     asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

@@ -190,6 +190,16 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
                 for (int layer = 0; layer < 2; ++layer, ++ls) {
                     if (layer == 0) mbar_wait(xfull, t & 1);
                     else mbar_wait(&hready[1], t & 1);
+                    if (NCHS == 1) {
+                        // One chunk per layer-step: each accumulator is used ONCE per layer-step, so nothing would stop this warp from
+                        // running a whole layer-step ahead of a slow epilogue warp -- `layerdone` would then complete two phases before
+                        // that warp tests the first one and its parity wait could never succeed (found on B200: H = 64 / 128 with S = 2 /
+                        // 4 hung in layer 1).  With >= 2 chunks per layer-step the second use of an accumulator already orders the issuer
+                        // behind every epilogue warp.  Here: do not start layer-step ls before the h of layer-step ls - 1 is in tensor
+                        // memory (all epilogue warps are past their layerdone wait then); the same phases are awaited again below.
+                        if (layer == 0) { if (t > 0) mbar_wait(&hready[1], t & 1); }
+                        else mbar_wait(&hready[0], (t + 1) & 1);
+                    }
                     tc5_fence_after();
                     constexpr int NKB0 = 1 + KBH, NKB1 = 2 * KBH;
                     const int nkb = layer == 0 ? NKB0 : NKB1;
@@ -488,14 +498,13 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
     if (warp == D5_EPI_WARPS + 1) tmem_dealloc_pair<512>(tmem);
 }
 
-// column split for small batches: the largest S in {4, 2, 1} that divides the chunk count and whose clusters (2 S CTAs, one per SM)
-// all fit on the GPU at once (8-CTA clusters: two per GPC); a.split forces a value (0 = auto)
+// column split for small batches: S = 4 when it divides the chunk count and the 8-CTA clusters all fit on the GPU at once (two per
+// GPC -> 16 clusters = 16 row-tile pairs = B <= 15 at F = 257); a.split forces a value (0 = auto)
 static int d5_pick_split(int H, int npairs, int forced) {
     const int nch = H / 32;
     if (forced == 1 || forced == 2 || forced == 4) return (nch % forced == 0) ? forced : 1;
-    if (nch % 4 == 0 && npairs <= 16) return 4;
-    if (nch % 2 == 0 && npairs <= 32) return 2;
-    return 1;
+    if (nch % 4 == 0 && npairs <= 16) return 4;          // measured (B200, H = 384): 18.3 -> 10.3 us per layer-step; S = 2 does not pay
+    return 1;                                            // (19.9 us: the exchange costs as much as half the MMA stream saves)
 }
 
 template <int HH, bool FF, bool GG, int SS>

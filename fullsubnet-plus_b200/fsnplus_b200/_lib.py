@@ -33,7 +33,8 @@ class FsnConfig(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libfsnplus_b200.so")
+    """The in-tree library; FSN_B200_LIB points at another build of the same sources (e.g. a -DFSN_MBAR_DEBUG build)."""
+    return os.environ.get("FSN_B200_LIB") or os.path.join(_HERE, "libfsnplus_b200.so")
 
 
 def load_library():
