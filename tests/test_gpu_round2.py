@@ -217,10 +217,12 @@ def test_batch_of_64_distinct_clips_vs_cpu_port(built_lib):
 # ---------------------------------------------------------------------------------------------------------------------
 # pipelined entry points
 # ---------------------------------------------------------------------------------------------------------------------
-def test_submit_wait_matches_forward(built_lib, golden):
-    """fsn_model_submit / fsn_model_wait: five batches in flight through the two lanes (front end of batch i+1 overlapping the
-    sub-band LSTM of batch i), default geometry, different batch contents; every result must be bit-identical to forward()
-    up to the order of the fp64 atomics of the gLN statistics."""
+@pytest.mark.parametrize("overlap", ["0", "1"])
+def test_submit_wait_matches_forward(built_lib, golden, monkeypatch, overlap):
+    """fsn_model_submit / fsn_model_wait: five batches in flight, default geometry, different batch contents; every result must be
+    bit-identical to forward() up to the order of the fp64 atomics of the gLN statistics.  overlap = 1 (FSN_FRONT_OVERLAP, read at
+    model creation): two workspace lanes, the front end of batch i+1 concurrent with the sub-band LSTM of batch i."""
+    monkeypatch.setenv("FSN_FRONT_OVERLAP", overlap)
     g = golden("plus_default")
     cfg = O.default_plus_config()
     m = _plus(cfg, O.make_params_plus(cfg, seed=0))
@@ -400,7 +402,7 @@ def test_column_split_small_configs(built_lib, monkeypatch, H, S, rnn):
 
 @pytest.mark.parametrize("B", [1, 2, 8, 20])
 def test_column_split_default_geometry_auto(built_lib, golden, monkeypatch, B):
-    """Default geometry, automatic split (B = 1, 2, 8 -> S = 4; B = 20 -> 21 pairs -> S = 2): sample 0 is the golden clip, the others
+    """Default geometry, automatic split (B = 1, 2, 8 -> S = 4; B = 20 -> 21 row-tile pairs -> unsplit): sample 0 is the golden clip, the others
     are shifted / scaled copies; every sample against the unsplit kernel (FSN_TC5_SPLIT=1), sample 0 against the reference golden."""
     g = golden("plus_default")
     cfg = O.default_plus_config()
