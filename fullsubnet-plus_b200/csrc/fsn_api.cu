@@ -4,8 +4,6 @@
 #include "fsn_common.cuh"
 #include "fsn_kernels.h"
 
-#include <cublas_v2.h>
-
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -65,7 +63,6 @@ struct fsn_model {
     // layer-wise tcgen05 path (k_lstm_tc5r.cu): per-layer recurrent streams, permuted input-projection matrices, biases
     bool tc5r_ok = false;
     DevBuf r_stream[4], r_wih[4], r_bias[4], r_gin, r_hseq;
-    cublasHandle_t cublas = nullptr;
     // Front-end workspaces (everything the full-band stage writes and the sub-band LSTM reads), grow-only, keyed by the last
     // (B, T).  TWO lanes: the pipelined entry points (fsn_model_submit / fsn_model_forward_host_async) run the front end of
     // batch i+1 in lane (i+1)&1 on the front stream while the sub-band LSTM of batch i still reads lane i&1 on the LSTM stream.
@@ -401,7 +398,6 @@ extern "C" void fsn_model_destroy(fsn_model* m) {
     }
     for (int i = 0; i < 4; ++i) { m->r_stream[i].release(); m->r_wih[i].release(); m->r_bias[i].release(); }
     m->r_gin.release(); m->r_hseq.release();
-    if (m->cublas) cublasDestroy(m->cublas);
     if (m->s_front) { cudaStreamDestroy(m->s_front); cudaStreamDestroy(m->s_lstm); cudaEventDestroy(m->ev_in); }
     if (m->ev_plain) cudaEventDestroy(m->ev_plain);
     if (m->s_in) { cudaStreamDestroy(m->s_in); cudaStreamDestroy(m->s_out); for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_h2d[i]); cudaEventDestroy(m->ev_d2h[i]); cudaEventDestroy(m->ev_done[i]); } }
@@ -612,21 +608,16 @@ static int run_sb_lstm(fsn_model* m, fsn_model::Lane& ln, int B, int T, float* d
     const int impl = pick_impl(m);
     m->last_impl = impl;
     if (use_layerwise(m)) {
-        // one GEMM (input projection of every row and time step) + one recurrent launch per layer
-        if (!m->cublas) {
-            if (cublasCreate(&m->cublas) != CUBLAS_STATUS_SUCCESS) return fail(FSN_ECUDA, "cublasCreate failed");
-        }
-        if (cublasSetStream(m->cublas, s) != CUBLAS_STATUS_SUCCESS) return fail(FSN_ECUDA, "cublasSetStream failed");
+        // one GEMM (input projection of every row and time step, k_gemm_f16.cu) + one recurrent launch per layer
         const int H = c.sb_hidden, ntp = (ntiles + 1) / 2 * 2;
         const long long M = (long long)ntp * Tp * 128;
-        const float one = 1.f, zero = 0.f;
         for (int l = 0; l < c.num_layers; ++l) {
             const int K = (l == 0) ? 64 : H;
             const void* X = (l == 0) ? ln.ximg.p : m->r_hseq.p;
-            // row-major Gin[M, 4H] = X[M, K] * Wp[4H, K]^T  ==  column-major Gin^T[4H, M] = Wp^T(op T) * X^T
-            cublasStatus_t st = cublasGemmEx(m->cublas, CUBLAS_OP_T, CUBLAS_OP_N, 4 * H, (int)M, K, &one, m->r_wih[l].p, CUDA_R_16F, K, X, CUDA_R_16F, K,
-                                             &zero, m->r_gin.p, CUDA_R_16F, 4 * H, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT_TENSOR_OP);
-            if (st != CUBLAS_STATUS_SUCCESS) return fail(FSN_ECUDA, "cublasGemmEx (input projection, layer %d) failed: %d", l, (int)st);
+            // row-major Gin[M, 4H] = X[M, K] * Wp[4H, K]^T, both operands K-major
+            GemmF16Launch g{M, 4 * H, K, static_cast<__half*>(m->r_gin.p), 4LL * H};
+            int ge = launch_gemm_f16(X, m->r_wih[l].p, g, m->num_sms, s);
+            if (ge) return fail(FSN_ECUDA, "input-projection GEMM launch failed (layer %d): %s", l, cudaGetErrorString((cudaError_t)ge));
             m->launches++;
             LstmTc5rLaunch a{};
             a.wstream = static_cast<const __half*>(m->r_stream[l].p);

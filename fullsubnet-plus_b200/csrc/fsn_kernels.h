@@ -181,6 +181,11 @@ int launch_lstm_tc5r(const LstmTc5rLaunch& a, cudaStream_t s);
 void lstm_tc5r_pack_layer(int H, int Kin, int Kpad, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, bool gru,
                           std::vector<uint16_t>& stream, std::vector<uint16_t>& wih_perm, std::vector<float>& bias);
 
+// ---- k_gemm_f16.cu: C[M, N] = A[M, K] B[N, K]^T, fp16 in / fp32 accumulate / fp16 out (input projection of the layer-wise path)
+struct GemmF16Launch { long long M; int N, K; __half* C; long long ldc; };
+bool gemm_f16_supported(long long M, int N, int K);
+int launch_gemm_f16(const void* A, const void* B, const GemmF16Launch& a, int num_sms, cudaStream_t s);
+
 // ---- k_gemm_tc5.cu (TCN on tcgen05, time-major activations) ----------------------------------
 enum { EPI5_PRELU_STATS = 1, EPI5_GLN_RES = 2, EPI5_OUT = 3 };
 struct GemmTc5Launch {
