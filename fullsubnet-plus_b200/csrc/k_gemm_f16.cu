@@ -5,9 +5,11 @@
 // K = 64 (layer 0: the packed sub-band input) or H.
 //
 // Persistent kernel, one CTA per SM, tiles of 128 x 256: both operands K-major and fetched by TMA (cp.async.bulk.tensor.2d,
-// SWIZZLE_128B, 64-half k-blocks) into a 4-stage ring, tcgen05.mma.kind::f16 (M = 128, N = 256, K = 16) into two 256-column
+// SWIZZLE_128B, 64-half k-blocks) into a 3-stage ring, tcgen05.mma.kind::f16 (M = 128, N = 256, K = 16) into two 256-column
 // accumulators so the drain of tile i overlaps the MMAs of tile i + 1; eight epilogue warps (two per TMEM lane quarter) convert to
-// fp16 and store 32 bytes per thread and 16-column chunk.  Tiles are walked N-fastest: the eight CTAs that share an A tile run at
+// fp16, stage the tile in shared memory in the swizzled layout of the result's tensor map and hand it to the TMA engine
+// (cp.async.bulk.tensor store: full 128-byte lines, asynchronous -- per-thread 32-byte stores at a 4 KB row pitch reached only 2.3 TB/s
+// on the write-bound K = 64 layer).  Tiles are walked N-fastest: the eight CTAs that share an A tile run at
 // the same time (A is read from HBM once, the 2 MB of weights stay in L2).  Bound: the fp16 result (M x 4H x 2 bytes, 6.5 GB per
 // layer at BASELINE config #5) has to be written to HBM -- the kernel is write-bound at ~2 ms per layer there.
 #include <cuda.h>
@@ -21,7 +23,9 @@ constexpr int GF_EPI_WARPS = 8;
 constexpr int GF_THREADS = (2 + GF_EPI_WARPS) * 32;     // warp 0 TMA producer, warp 1 MMA issuer + TMEM alloc, warps 2-9 epilogue
 constexpr int GF_BM = 128, GF_BN = 256, GF_BK = 64;
 constexpr int GF_A_BYTES = GF_BM * GF_BK * 2, GF_B_BYTES = GF_BN * GF_BK * 2, GF_STAGE = GF_A_BYTES + GF_B_BYTES;
-constexpr int GF_NSTAGE = 4;
+constexpr int GF_NSTAGE = 3;
+constexpr int GF_CSUB = GF_BM * 64 * 2;                  // one 128-row x 64-column fp16 sub-tile of the result staged for the TMA store (SW128)
+constexpr int GF_CSTAGE = (GF_BN / 64) * GF_CSUB;        // 64 KB: the whole 128 x 256 result tile
 
 __device__ __forceinline__ void gf_tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -30,11 +34,31 @@ __device__ __forceinline__ void gf_tma_load_2d(void* smem_dst, const CUtensorMap
                  : "memory");
 }
 
+// result tile: shared memory -> global through the TMA engine (full 128-byte lines, asynchronous: the epilogue warps go on to the next tile)
+__device__ __forceinline__ void gf_tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)) : "memory");
+}
+__device__ __forceinline__ void gf_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void gf_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void gf_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void gf_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+        "%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+          "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+          "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
 __global__ void __launch_bounds__(GF_THREADS, 1)
-gemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmF16Launch a) {
+gemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapC,
+                GemmF16Launch a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)GF_NSTAGE * GF_STAGE);
+    uint8_t* cstage = smem + (size_t)GF_NSTAGE * GF_STAGE;                 // [4 sub-tiles][128 rows][64 halves], SWIZZLE_128B
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cstage + GF_CSTAGE);
     uint64_t* full = bars;
     uint64_t* empty = full + GF_NSTAGE;
     uint64_t* accfull = empty + GF_NSTAGE;
@@ -95,33 +119,54 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else {
-        const int q = warp & 3, r = q * 32 + lane, half = (warp - 2) >> 2;       // TMEM lane quarter, row in the tile, column half
+        // epilogue: TMEM -> fp16 -> shared memory (the swizzled layout of the C tensor map) -> TMA store.  Warp (q, half): rows
+        // q*32.., columns half*128.. = two 64-column sub-tiles; the accumulator is released as soon as it is in registers.
+        const int q = warp & 3, r = q * 32 + lane, half = (warp - 2) >> 2;
+        const bool chief = (warp == 2 && lane == 0);
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t use[2] = {0, 0}, it = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
             const int mt = tile / tiles_n, nt = tile % tiles_n, buf = it & 1;
-            __half* crow = a.C + ((size_t)mt * GF_BM + r) * a.ldc + (size_t)nt * GF_BN + half * (GF_BN / 2);
             mbar_wait(&accfull[buf], use[buf] & 1);
             ++use[buf];
             tc5_fence_after();
-#pragma unroll 2
-            for (int c = 0; c < GF_BN / 2 / 16; ++c) {
-                uint32_t v[16];
-                tmem_ld16(tl + buf * GF_BN + half * (GF_BN / 2) + c * 16, v);
-                tmem_wait_ld();
-                uint4 o0, o1;
-                o0.x = pack_half2(__uint_as_float(v[0]), __uint_as_float(v[1]));   o0.y = pack_half2(__uint_as_float(v[2]), __uint_as_float(v[3]));
-                o0.z = pack_half2(__uint_as_float(v[4]), __uint_as_float(v[5]));   o0.w = pack_half2(__uint_as_float(v[6]), __uint_as_float(v[7]));
-                o1.x = pack_half2(__uint_as_float(v[8]), __uint_as_float(v[9]));   o1.y = pack_half2(__uint_as_float(v[10]), __uint_as_float(v[11]));
-                o1.z = pack_half2(__uint_as_float(v[12]), __uint_as_float(v[13])); o1.w = pack_half2(__uint_as_float(v[14]), __uint_as_float(v[15]));
-                uint4* dst = reinterpret_cast<uint4*>(crow + c * 16);
-                __stcs(dst, o0);                                          // written once, read once by the recurrent kernel: streaming
-                __stcs(dst + 1, o1);
+            if (it > 0) {                                             // the previous tile's TMA stores have read the staging buffer
+                if (chief) gf_bulk_wait_read0();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-            tc5_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&accempty[buf]);
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+                uint8_t* cs = cstage + (size_t)(half * 2 + sub) * GF_CSUB;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    gf_tmem_ld32(tl + buf * GF_BN + half * 128 + sub * 64 + c * 32, v);
+                    tmem_wait_ld();
+                    if (sub == 1 && c == 1) {                         // last read of this accumulator: hand it back to the MMA issuer
+                        tc5_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&accempty[buf]);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 o;
+                        o.x = pack_half2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
+                        o.y = pack_half2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
+                        o.z = pack_half2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
+                        o.w = pack_half2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
+                        *reinterpret_cast<uint4*>(cs + sw128_offset(r, c * 32 + g * 8)) = o;
+                    }
+                }
+            }
+            fence_proxy_async();                                      // generic-proxy stores -> visible to the TMA engine
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (chief) {
+#pragma unroll
+                for (int sub = 0; sub < GF_BN / 64; ++sub) gf_tma_store_2d(&mapC, cstage + (size_t)sub * GF_CSUB, nt * GF_BN + sub * 64, mt * GF_BM);
+                gf_bulk_commit();
+            }
         }
+        if (chief) gf_bulk_wait0();                                   // all result tiles are in global memory before the CTA exits
     }
     tc5_fence_before();
     __syncthreads();
@@ -159,15 +204,17 @@ bool gemm_f16_supported(long long M, int N, int K) { return M > 0 && M % GF_BM =
 
 int launch_gemm_f16(const void* A, const void* B, const GemmF16Launch& a, int num_sms, cudaStream_t s) {
     if (!gemm_f16_supported(a.M, a.N, a.K)) return (int)cudaErrorInvalidValue;
-    alignas(64) CUtensorMap mA, mB;
-    if (make_tmap_f16_2d(&mA, A, (uint64_t)a.M, (uint64_t)a.K, GF_BM) || make_tmap_f16_2d(&mB, B, (uint64_t)a.N, (uint64_t)a.K, GF_BN))
+    if (a.ldc != a.N) return (int)cudaErrorInvalidValue;          // the C tensor map describes a dense [M, N] matrix
+    alignas(64) CUtensorMap mA, mB, mC;
+    if (make_tmap_f16_2d(&mA, A, (uint64_t)a.M, (uint64_t)a.K, GF_BM) || make_tmap_f16_2d(&mB, B, (uint64_t)a.N, (uint64_t)a.K, GF_BN) ||
+        make_tmap_f16_2d(&mC, a.C, (uint64_t)a.M, (uint64_t)a.N, GF_BM))
         return (int)cudaErrorInvalidValue;
-    const size_t smem = (size_t)GF_NSTAGE * GF_STAGE + 1024 + 256;
+    const size_t smem = (size_t)GF_NSTAGE * GF_STAGE + GF_CSTAGE + 1024 + 256;
     cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const long long total = (a.M / GF_BM) * (long long)(a.N / GF_BN);
     const int grid = total < num_sms ? (int)total : num_sms;
-    gemm_f16_kernel<<<grid, GF_THREADS, smem, s>>>(mA, mB, a);
+    gemm_f16_kernel<<<grid, GF_THREADS, smem, s>>>(mA, mB, mC, a);
     return (int)cudaGetLastError();
 }
 
