@@ -158,6 +158,7 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
             const uint32_t stage_lo0 = ((smem_u32(stages) >> 4) & 0x3FFFu) | (1u << 16);
             const uint32_t x_lo = ((smem_u32(ximg) >> 4) & 0x3FFFu) | (1u << 16);
             int slot = 0; uint32_t ph = 0, accuse = 0, ls = 0;
+            const int nkx = (a.I + 15) >> 4;
             auto mma_ss = [&](uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
                 asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
                              "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(IDESC), "r"(acc), "r"(DESC_HI) : "memory");
@@ -170,8 +171,10 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
             // FIRST, then h0(t): the recurrent half does not depend on the layer-0 epilogue that is still finishing at the boundary)
             auto kblock = [&](int layer, int kbi, uint32_t b_lo) {
                 if (layer == 0 && kbi == 0) {
+                    // x block: only ceil(I / 16) of the four K = 16 slices hold input columns (I = 34 -> 3); the rest is zero padding
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) mma_ss(x_lo + 2 * kk, b_lo + 2 * kk, kk != 0);
+                    for (int kk = 0; kk < 4; ++kk)
+                        if (kk < nkx) mma_ss(x_lo + 2 * kk, b_lo + 2 * kk, kk != 0);
                 } else {
                     const uint32_t acol = (layer == 0) ? (kbi - 1) * 32 : (kbi < KBH ? hcols + kbi * 32 : (kbi - KBH) * 32);
 #pragma unroll
