@@ -144,7 +144,7 @@ def _rank_world():
 
 
 @torch.no_grad()
-def run(config, checkpoint_path, output_dir, batch_size=64, device=None, log=print, model_and_epoch=None, trust_checkpoint=False):
+def run(config, checkpoint_path, output_dir, batch_size=64, device=None, log=print, model_and_epoch=None, trust_checkpoint=False, streams=4):
     """Enhance every file of config["dataset"]["args"]["dataset_dir_list"].  Under torchrun each rank takes every
     world-size-th batch (files are independent: no collective).  Returns {name: path} of the files this rank wrote.
     ``model_and_epoch`` (tests of the host logic) replaces the checkpoint load with a ready ``(callable, epoch)``."""
@@ -166,21 +166,22 @@ def run(config, checkpoint_path, output_dir, batch_size=64, device=None, log=pri
     # bucket on the lengths from the WAV headers; a rank decodes only the files of ITS batches, one batch at a time (host memory
     # and start-up time scale with the batch, not with the dataset -- the reference streams one clip at a time)
     batches = bucket_by_length([wav_length(p, ds_sr) for p in files], batch_size)
-    written, audio_s, gpu_s = {}, 0.0, 0.0
-    for bi, idx in enumerate(batches):
-        if bi % world != rank:
-            continue
-        noisy = torch.from_numpy(np.stack([read_wav(files[i], ds_sr) for i in idx]))
-        if on_gpu:
-            noisy = noisy.pin_memory().to(device, non_blocking=True)
-            torch.cuda.synchronize(device)
-        t1 = time.time()
-        enhanced = H.enhance_batch(model, noisy, n_fft, hop, win, complex_inputs=INFERENCE_TYPES[itype]).cpu().numpy()
-        t2 = time.time()
-        dur = len(idx) * noisy.size(1) / sr
-        audio_s += dur
-        gpu_s += t2 - t1
-        log(f"[rank {rank}] batch {bi}: {len(idx)} x {noisy.size(1)} samples, rtf: {(t2 - t1) / dur:.3e}")
+    mine = [(bi, idx) for bi, idx in enumerate(batches) if bi % world == rank]
+    # Ragged real recordings make many small batches (a lone clip occupies 16 of 148 SMs in the column-split kernel): up to `streams`
+    # batches are in flight at once, each on its own CUDA stream and its own model replica (own C handle and workspaces).
+    nstream = max(1, min(streams, len(mine))) if (on_gpu and model_and_epoch is None) else 1
+    models = [model] + [build_model(config["model"], Path(checkpoint_path).expanduser().absolute(), device, trust_checkpoint)[0]
+                        for _ in range(nstream - 1)]
+    cuda_streams = [torch.cuda.Stream(device) for _ in range(nstream)] if on_gpu else [None]
+    written, audio_s, inflight = {}, 0.0, []
+    t_start = time.time()
+
+    def finish(item):
+        bi, idx, host, ev, n_samples = item
+        if ev is not None:
+            ev.synchronize()
+        enhanced = host.numpy()
+        log(f"[rank {rank}] batch {bi}: {len(idx)} x {n_samples} samples done")
         for j, i in enumerate(idx):
             y = enhanced[j]
             if (np.abs(y) > 1).any():
@@ -188,8 +189,28 @@ def run(config, checkpoint_path, output_dir, batch_size=64, device=None, log=pri
             out = enhanced_dir / f"{files[i].stem}.wav"
             write_wav_int16(out, to_int16(y), sr)
             written[files[i].stem] = out
+
+    for n, (bi, idx) in enumerate(mine):
+        noisy = torch.from_numpy(np.stack([read_wav(files[i], ds_sr) for i in idx]))
+        audio_s += len(idx) * noisy.size(1) / sr
+        k = n % nstream
+        if len(inflight) >= nstream:
+            finish(inflight.pop(0))                                        # the batch that used this stream / replica last
+        if on_gpu:
+            with torch.cuda.stream(cuda_streams[k]):
+                dev_noisy = noisy.pin_memory().to(device, non_blocking=True)
+                enh = H.enhance_batch(models[k], dev_noisy, n_fft, hop, win, complex_inputs=INFERENCE_TYPES[itype])
+                host = torch.empty(tuple(enh.shape), dtype=enh.dtype).pin_memory()
+                host.copy_(enh, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cuda_streams[k])
+            inflight.append((bi, idx, host, ev, noisy.size(1)))
+        else:
+            inflight.append((bi, idx, H.enhance_batch(models[k], noisy, n_fft, hop, win, complex_inputs=INFERENCE_TYPES[itype]).cpu(), None, noisy.size(1)))
+    while inflight:
+        finish(inflight.pop(0))
     if audio_s > 0:
-        log(f"[rank {rank}] {len(written)} files, {audio_s:.1f} s of audio, overall rtf: {gpu_s / audio_s:.3e}")
+        log(f"[rank {rank}] {len(written)} files, {audio_s:.1f} s of audio, {nstream} stream(s), overall rtf: {(time.time() - t_start) / audio_s:.3e}")
     return written
 
 
@@ -202,12 +223,13 @@ def main(argv=None):
     parser.add_argument("-O", "--output_dir", type=str, required=True, help="The path for saving enhanced speeches.")
     parser.add_argument("--batch_size", type=int, default=64, help="clips of equal length per launch (additive)")
     parser.add_argument("--trust_checkpoint", action="store_true", help="unpickle arbitrary objects from the checkpoint (default: tensors only)")
+    parser.add_argument("--streams", type=int, default=4, help="batches in flight at once, each on its own CUDA stream and model replica (additive)")
     args = parser.parse_args(argv)
     configuration = load_toml(args.configuration)
     if len(args.dataset_dir_list) > 0:
         print(f"use specified dataset_dir_list: {args.dataset_dir_list}, instead of in config")
         configuration["dataset"]["args"]["dataset_dir_list"] = args.dataset_dir_list
-    run(configuration, args.model_checkpoint_path, args.output_dir, batch_size=args.batch_size, trust_checkpoint=args.trust_checkpoint)
+    run(configuration, args.model_checkpoint_path, args.output_dir, batch_size=args.batch_size, trust_checkpoint=args.trust_checkpoint, streams=args.streams)
 
 
 if __name__ == "__main__":
