@@ -501,11 +501,12 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
     if (warp == D5_EPI_WARPS + 1) tmem_dealloc_pair<512>(tmem);
 }
 
-// column split for small batches: S = 4 when it divides the chunk count and the 8-CTA clusters all fit on the GPU at once (two per
-// GPC -> 16 clusters = 16 row-tile pairs = B <= 15 at F = 257); a.split forces a value (0 = auto)
+// column split for small batches: S = 6 (12-CTA clusters, one per GPC) for up to 8 row-tile pairs, S = 4 (8-CTA clusters, two per GPC)
+// for up to 16, when S divides the chunk count; a.split forces a value (0 = auto)
 static int d5_pick_split(int H, int npairs, int forced) {
     const int nch = H / 32;
-    if (forced == 1 || forced == 2 || forced == 4) return (nch % forced == 0) ? forced : 1;
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 6) return (nch % forced == 0) ? forced : 1;
+    if (nch % 6 == 0 && npairs <= 8) return 6;           // 12-CTA clusters (non-portable size, one per GPC): B <= 7 at F = 257
     if (nch % 4 == 0 && npairs <= 16) return 4;          // measured (B200, H = 384): 18.3 -> 10.3 us per layer-step; S = 2 does not pay
     return 1;                                            // (19.9 us: the exchange costs as much as half the MMA stream saves)
 }
@@ -516,6 +517,23 @@ static int d5_go(const LstmTc5Launch& a, int npairs, cudaStream_t s) {
     if (p.nstage < 2) return (int)cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(lstm_tc5d_kernel<HH, FF, GG, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);
     if (e != cudaSuccess) return (int)e;
+    if (2 * SS > 8) {                                               // clusters of more than 8 CTAs are an opt-in on sm_100 (up to 16)
+        e = cudaFuncSetAttribute(lstm_tc5d_kernel<HH, FF, GG, SS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+        static int max_clusters = -1;                               // how many such clusters the device can hold at once (one CTA per SM)
+        if (max_clusters < 0) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * SS, 1, 1); cfg.blockDim = dim3(D5_THREADS, 1, 1); cfg.dynamicSmemBytes = p.total;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 2 * SS; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, lstm_tc5d_kernel<HH, FF, GG, SS>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+            max_clusters = n;
+        }
+        if (max_clusters < npairs) return -1;                       // caller falls back to the next smaller split
+    }
     lstm_tc5d_kernel<HH, FF, GG, SS><<<npairs * 2 * SS, D5_THREADS, p.total, s>>>(a, p.nstage);
     return (int)cudaGetLastError();
 }
@@ -527,6 +545,13 @@ static int d5_dispatch(const LstmTc5Launch& a, int npairs, cudaStream_t s) {
 template <int HH>
 static int d5_split(const LstmTc5Launch& a, int npairs, int S, cudaStream_t s) {
     constexpr int nch = HH / 32;
+    if constexpr (nch % 6 == 0) {
+        if (S == 6) {
+            const int rc = d5_dispatch<HH, 6>(a, npairs, s);
+            if (rc != -1) return rc;                                // -1: the 12-CTA clusters do not fit this device / batch -> S = 4 or 1
+            S = (nch % 4 == 0 && npairs <= 16) ? 4 : 1;
+        }
+    }
     if constexpr (nch % 4 == 0) { if (S == 4) return d5_dispatch<HH, 4>(a, npairs, s); }
     if constexpr (nch % 2 == 0) { if (S == 2) return d5_dispatch<HH, 2>(a, npairs, s); }
     return d5_dispatch<HH, 1>(a, npairs, s);

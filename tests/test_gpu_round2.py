@@ -375,7 +375,7 @@ def test_enhance_pipeline_matches_enhance_batch(built_lib, golden):
 # ---------------------------------------------------------------------------------------------------------------------
 # small-batch column-split mode of the fused tcgen05 kernel (k_lstm_tc5d.cu, S CTA pairs per 256 sequences)
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("H,S,rnn", [(64, 2, "LSTM"), (128, 2, "LSTM"), (128, 4, "LSTM"), (128, 4, "GRU"), (256, 4, "LSTM")])
+@pytest.mark.parametrize("H,S,rnn", [(64, 2, "LSTM"), (128, 2, "LSTM"), (128, 4, "LSTM"), (128, 4, "GRU"), (256, 4, "LSTM"), (192, 6, "LSTM"), (384, 6, "GRU")])
 def test_column_split_small_configs(built_lib, monkeypatch, H, S, rnn):
     """Forced split (FSN_TC5_SPLIT is read once at model creation) against the oracle and against the unsplit kernel: several row
     tiles (B*F = 9*33 = 297 rows -> 3 tiles -> 2 pairs, the second half empty), sb activation on, fused enhance output."""
@@ -402,7 +402,7 @@ def test_column_split_small_configs(built_lib, monkeypatch, H, S, rnn):
 
 @pytest.mark.parametrize("B", [1, 2, 8, 20])
 def test_column_split_default_geometry_auto(built_lib, golden, monkeypatch, B):
-    """Default geometry, automatic split (B = 1, 2, 8 -> S = 4; B = 20 -> 21 row-tile pairs -> unsplit): sample 0 is the golden clip, the others
+    """Default geometry, automatic split (B = 1, 2 -> S = 6; B = 8 -> S = 4; B = 20 -> 21 row-tile pairs -> unsplit): sample 0 is the golden clip, the others
     are shifted / scaled copies; every sample against the unsplit kernel (FSN_TC5_SPLIT=1), sample 0 against the reference golden."""
     g = golden("plus_default")
     cfg = O.default_plus_config()
