@@ -191,6 +191,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
         const int Tout = Tp - a.la;
         const float fcb0 = LAST ? __ldg(a.fc_b) : 0.f, fcb1 = LAST ? __ldg(a.fc_b + 1) : 0.f;
 
+        // Gin of the NEXT chunk is loaded one chunk ahead (64 bytes per thread at a 4 KB row pitch: the loads take longer than one
+        // half-chunk of MMAs, so issuing them only before the accumulator wait left the epilogue waiting for memory)
+        uint4 gn[4];
+        {
+            const uint4* g0p = reinterpret_cast<const uint4*>(a.gin + (((size_t)tile * Tp) * 128 + r) * (size_t)(4 * H) + cg * 32);
+            gn[0] = __ldg(g0p); gn[1] = __ldg(g0p + 1); gn[2] = __ldg(g0p + 2); gn[3] = __ldg(g0p + 3);
+        }
         for (int t = 0; t < Tp; ++t) {
             const size_t mrow = ((size_t)tile * Tp + t) * 128 + r;  // my row of the (tile, t) block of Gin / hseq
             const uint4* gsrc = reinterpret_cast<const uint4*>(a.gin + mrow * (size_t)(4 * H) + cg * 32);
@@ -205,7 +212,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
                 const float4 c4[2] = {cnext[0], cnext[1]};         // prefetched during the previous chunk
                 const float4* bj = reinterpret_cast<const float4*>(bsm + (size_t)j * 128 + cg * 32);
                 // input projection of this chunk: 32 halves = i(8) f(8) g(8) o(8) of my 8 hidden units; in flight during the wait below
-                const uint4 g0 = __ldg(gsrc + j * 16), g1 = __ldg(gsrc + j * 16 + 1), g2 = __ldg(gsrc + j * 16 + 2), g3 = __ldg(gsrc + j * 16 + 3);
+                const uint4 g0 = gn[0], g1 = gn[1], g2 = gn[2], g3 = gn[3];
+                {   // prefetch: chunk j + 1 of this step, or chunk 0 of the next step (one 128-row block further)
+                    const uint4* np = (j + 1 < NCH) ? gsrc + (j + 1) * 16 : gsrc + (size_t)128 * (4 * H) / 8;
+                    if (j + 1 < NCH || t + 1 < Tp) { gn[0] = __ldg(np); gn[1] = __ldg(np + 1); gn[2] = __ldg(np + 2); gn[3] = __ldg(np + 3); }
+                }
                 mbar_wait(my_accfull, accn & 1);
                 ++accn;
                 tc5_fence_after();
