@@ -170,6 +170,11 @@ __device__ __forceinline__ float ldg_hint(const float* p, uint64_t policy) {
     asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
     return v;
 }
+__device__ __forceinline__ uint4 ldg_u4_hint(const uint4* p, uint64_t policy) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
 __device__ __forceinline__ float4 ld_f4_hint(const float4* p, uint64_t policy) {
     float4 v;
     asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy) : "memory");

@@ -91,6 +91,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
         if (lane == 0) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wstream) + (size_t)rank * R5_KB;
             int slot = 0; uint32_t ph = 0;
+            const uint64_t pol_w = l2_policy_evict_last();          // 2 MB of W_hh, re-read every step by every pair: must survive the Gin stream
             for (int t = 0; t < Tp; ++t)
                 for (int j = 0; j < NCH; ++j)
                     for (int half = 0; half < 2; ++half)
@@ -99,8 +100,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
                             mbar_wait(&empty[slot], ph ^ 1);
                             mbar_arrive_expect_tx(&full[slot], nk * R5_SUB);
                             for (int i = 0; i < nk; ++i)
-                                bulk_g2s(stages + (size_t)slot * R5_STAGE + i * R5_SUB,
-                                         wsrc + (size_t)(j * KBH + kb0 + i) * R5_STAGE_FULL + half * R5_SUB, R5_SUB, &full[slot]);
+                                bulk_g2s_hint(stages + (size_t)slot * R5_STAGE + i * R5_SUB,
+                                              wsrc + (size_t)(j * KBH + kb0 + i) * R5_STAGE_FULL + half * R5_SUB, R5_SUB, &full[slot], pol_w);
                             if (++slot == nstage) { slot = 0; ph ^= 1; }
                         }
         }
@@ -193,10 +194,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
 
         // Gin of the NEXT chunk is loaded one chunk ahead (64 bytes per thread at a 4 KB row pitch: the loads take longer than one
         // half-chunk of MMAs, so issuing them only before the accumulator wait left the epilogue waiting for memory)
+        // L2 policies: Gin (6.5 GB per layer at config #5) is read exactly once -> evict_first, so that it does not push the weight
+        // stream and the cell state (evict_last) out of L2
+        const uint64_t pol_g = l2_policy_evict_first(), pol_c = l2_policy_evict_last();
         uint4 gn[4];
         {
             const uint4* g0p = reinterpret_cast<const uint4*>(a.gin + (((size_t)tile * Tp) * 128 + r) * (size_t)(4 * H) + cg * 32);
-            gn[0] = __ldg(g0p); gn[1] = __ldg(g0p + 1); gn[2] = __ldg(g0p + 2); gn[3] = __ldg(g0p + 3);
+            gn[0] = ldg_u4_hint(g0p, pol_g); gn[1] = ldg_u4_hint(g0p + 1, pol_g); gn[2] = ldg_u4_hint(g0p + 2, pol_g); gn[3] = ldg_u4_hint(g0p + 3, pol_g);
         }
         for (int t = 0; t < Tp; ++t) {
             const size_t mrow = ((size_t)tile * Tp + t) * 128 + r;  // my row of the (tile, t) block of Gin / hseq
@@ -215,7 +219,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
                 const uint4 g0 = gn[0], g1 = gn[1], g2 = gn[2], g3 = gn[3];
                 {   // prefetch: chunk j + 1 of this step, or chunk 0 of the next step (one 128-row block further)
                     const uint4* np = (j + 1 < NCH) ? gsrc + (j + 1) * 16 : gsrc + (size_t)128 * (4 * H) / 8;
-                    if (j + 1 < NCH || t + 1 < Tp) { gn[0] = __ldg(np); gn[1] = __ldg(np + 1); gn[2] = __ldg(np + 2); gn[3] = __ldg(np + 3); }
+                    if (j + 1 < NCH || t + 1 < Tp) {
+                        gn[0] = ldg_u4_hint(np, pol_g); gn[1] = ldg_u4_hint(np + 1, pol_g); gn[2] = ldg_u4_hint(np + 2, pol_g); gn[3] = ldg_u4_hint(np + 3, pol_g);
+                    }
                 }
                 mbar_wait(my_accfull, accn & 1);
                 ++accn;
@@ -232,7 +238,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
                     const int nt = (j + 1 < NCH) ? t : t + 1;
                     const float4* np = reinterpret_cast<const float4*>(cbase + ((size_t)(nj * 4 + cg) * 2) * 128 * 4) + r;
                     if (nt == 0 || nt >= Tp) { cnext[0] = make_float4(0.f, 0.f, 0.f, 0.f); cnext[1] = cnext[0]; }
-                    else { cnext[0] = np[0]; cnext[1] = np[128]; }
+                    else { cnext[0] = ld_f4_hint(np, pol_c); cnext[1] = ld_f4_hint(np + 128, pol_c); }
                 }
                 const uint32_t gw[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
                 const float L2E = 1.4426950408889634f;
@@ -273,8 +279,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
                     hp[2 * u4] = pack_half2(hv[0], hv[1]);
                     hp[2 * u4 + 1] = pack_half2(hv[2], hv[3]);
                 }
-                cp[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                cp[128] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                st_f4_hint(cp, make_float4(cn[0], cn[1], cn[2], cn[3]), pol_c);
+                st_f4_hint(cp + 128, make_float4(cn[4], cn[5], cn[6], cn[7]), pol_c);
                 *reinterpret_cast<uint4*>(mypark + (size_t)j * 128 * 16) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
             }
             mbar_wait(stepdone, t & 1);                            // every MMA that reads h(t-1) has retired: h(t) may replace it
@@ -283,7 +289,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
                 const uint4 p0 = *reinterpret_cast<const uint4*>(mypark + (size_t)j * 128 * 16);
                 const uint32_t hv[4] = {p0.x, p0.y, p0.z, p0.w};
                 tmem_st4(tl + j * 16 + cg * 4, hv);
-                if (!LAST) *reinterpret_cast<uint4*>(a.hseq + mrow * (size_t)H + j * 32 + cg * 8) = p0;   // next layer's GEMM input
+                if (!LAST) __stcs(reinterpret_cast<uint4*>(a.hseq + mrow * (size_t)H + j * 32 + cg * 8), p0);   // next layer's GEMM input (streaming)
             }
             tmem_wait_st();
             tc5_fence_before();
