@@ -100,6 +100,7 @@ struct fsn_model {
     // (two lanes, two streams).  Off by default: measured zero-sum on B200 -- the LSTM kernel runs at the board's power cap, and
     // what the front end gains on the 18 idle SMs the LSTM loses in clock (profiles/r02_front_overlap.txt).
     bool env_front_overlap = false;
+    double ws_cap_bytes = 48e9;                        // FSN_WS_CAP_GB: larger batches are run as sub-batches (plain forward entry points)
     bool env_no_ws = false, env_no_xfuse = false;      // FSN_NO_XFUSE=1: packed sub-band images instead of the fused unfold (A/B only)
     // pipelined execution: front-end stream, LSTM stream (higher priority), copy-in / copy-out streams, per-slot events
     cudaStream_t s_front = nullptr, s_lstm = nullptr, s_in = nullptr, s_out = nullptr;
@@ -377,6 +378,7 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     { const char* e = getenv("FSN_NO_XFUSE"); m->env_no_xfuse = e && atoi(e) != 0; }
     { const char* e = getenv("FSN_TC5_SPLIT"); if (e && *e) m->env_split = atoi(e); }
     { const char* e = getenv("FSN_FRONT_OVERLAP"); m->env_front_overlap = e && atoi(e) != 0; }
+    { const char* e = getenv("FSN_WS_CAP_GB"); if (e && atof(e) > 0) m->ws_cap_bytes = atof(e) * 1e9; }
     build_specs(m);
     for (int i = 0; i < fsn_model::NEV; ++i) { cudaEventCreate(&m->ev0[i]); cudaEventCreate(&m->ev1[i]); cudaEventCreate(&m->evf0[i]); cudaEventCreate(&m->evf1[i]); }
     { cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev); if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) m->num_sms = prop.multiProcessorCount; }
@@ -935,13 +937,48 @@ static int submit_impl(fsn_model* m, cudaEvent_t ready, const float* d_mag, cons
     return FSN_OK;
 }
 
+// Workspace per sample (bytes) of a forward with T frames: the per-sample slices of every grow-only buffer of ensure_ws.  The
+// layer-wise path dominates: its time-batched input projection Gin takes 257 x T' x 4H x 2 bytes per sample (0.2 GB at config #5).
+static double ws_bytes_per_sample(const fsn_model* m, int T) {
+    const fsn_config& c = m->cfg;
+    const double F = c.num_freqs, Tp = T + c.look_ahead, rows = F;              // sequences per sample
+    double b = 0;
+    if (c.model_kind == FSN_KIND_PLUS) b += 3 * F * Tp * 4 * 2 + 3 * Tp * (5.0 * m->Cp + 2 * 512) * 4;   // fb_in/out, X0/Xa/Xb/Xr/fbo, Y1/Y2
+    else b += F * Tp * 4 * 4 + Tp * (F + c.fb_hidden) * 4;
+    b += rows * Tp * 128;                                                       // packed sub-band images (when used)
+    b += rows * c.num_layers * c.sb_hidden * 4;                                  // cell state
+    if (use_layerwise(m)) b += rows * Tp * (4.0 * c.sb_hidden + c.sb_hidden) * 2;   // Gin + layer output sequence
+    return b;
+}
+
 static int forward_plain(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
                          float* d_out, float* d_enh, void* stream) {
     if (!m) return fail(FSN_EINVAL, "null argument");
+    if (!m->finalized) return fail(FSN_ESTATE, "fsn_model_finalize has not been called");
+    if (B < 1 || T < 1) return fail(FSN_EINVAL, "bad batch/frames");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     for (auto& ln : m->lane)                                             // batches still in flight in the pipeline share the scratch buffers
         if (ln.used) CK(cudaStreamWaitEvent(s, ln.ev_lstm, 0));
-    int rc = forward_impl(m, m->lane[0], d_mag, d_real, d_imag, B, T, d_out, d_enh, s, s);
+    // Samples are independent, so a batch whose workspace would exceed the cap (FSN_WS_CAP_GB, default 48 of the 180 GB) is run as
+    // equal sub-batches one after the other on the same stream -- same results, bounded memory (e.g. 256 clips on the layer-wise path).
+    const double per = ws_bytes_per_sample(m, T);
+    int Bmax = (int)(m->ws_cap_bytes / (per > 1 ? per : 1));
+    if (Bmax < 1) Bmax = 1;
+    int rc = FSN_OK;
+    if (B <= Bmax) {
+        rc = forward_impl(m, m->lane[0], d_mag, d_real, d_imag, B, T, d_out, d_enh, s, s);
+    } else {
+        const int nsplit = (B + Bmax - 1) / Bmax, Bs = (B + nsplit - 1) / nsplit;
+        const size_t in_stride = (size_t)m->cfg.num_freqs * T, out_stride = (size_t)m->cfg.output_size * m->cfg.num_freqs * T;
+        int64_t launches = 0;
+        for (int b0 = 0; b0 < B && rc == FSN_OK; b0 += Bs) {
+            const int nb = (B - b0 < Bs) ? B - b0 : Bs;
+            rc = forward_impl(m, m->lane[0], d_mag + b0 * in_stride, d_real ? d_real + b0 * in_stride : nullptr, d_imag ? d_imag + b0 * in_stride : nullptr,
+                              nb, T, d_out ? d_out + b0 * out_stride : nullptr, d_enh ? d_enh + b0 * in_stride * 2 : nullptr, s, s);
+            launches += m->launches;
+        }
+        m->launches = launches;
+    }
     if (rc) return rc;
     if (!m->ev_plain) CK(cudaEventCreateWithFlags(&m->ev_plain, cudaEventDisableTiming));
     CK(cudaEventRecord(m->ev_plain, s));

@@ -7,11 +7,11 @@
 //   * the input projection has no recurrence: Gin_l = X_l W_ih_l^T is ONE plain GEMM over all rows and all time steps
 //     (cuBLAS, fp16 in / fp32 accumulate / fp16 out; fsn_api.cu), its gate columns pre-permuted to this kernel's chunk order;
 //   * this kernel runs the recurrence of one layer for all time steps: h_l in tensor memory (H/2 columns, packed fp16, the
-//     A operand of tcgen05.mma), W_hh_l streamed from L2 through a bulk-copy ring, two 64-column accumulators, the epilogue
+//     A operand of tcgen05.mma), W_hh_l streamed from L2 through a bulk-copy ring, four 64-column accumulators, the epilogue
 //     adds Gin_l(t) to the accumulator, does the cell update and either writes h_l(t) as the next layer's GEMM input
 //     (fp16, row-major) or, on the last layer, applies the output Linear(H -> 2) and writes the mask.
-// TMEM: H/2 + 128 <= 512 columns, i.e. any H <= 768; shared memory (h is parked there until the step's MMAs are done) limits
-// H to 512.  Roles, CTA pairs (cta_group::2), multicast commits, half-chunk double buffering and the relay protocol are those
+// TMEM: H/2 + 256 <= 512 columns (four 64-column accumulators), i.e. H <= 512; h(t) is parked in shared memory until the step's MMAs are
+// done (parking it in its global output row instead, to deepen the weight ring from 5 to 12 slots, was tried: 4.34 -> 4.80 ms).  Roles, CTA pairs (cta_group::2), multicast commits, half-chunk double buffering and the relay protocol are those
 // of k_lstm_tc5d.cu; the per-step dependency (every MMA of step t reads h(t-1)) is inherent to a single layer.
 #include "fsn_common.cuh"
 #include "fsn_kernels.h"
@@ -64,15 +64,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
     uint64_t* bars = reinterpret_cast<uint64_t*>(fcpart + 4 * 128 * 2);
     uint64_t* full = bars;
     uint64_t* empty = full + nstage;
-    uint64_t* accfull = empty + nstage;                                      // [2]
-    uint64_t* accempty = accfull + 2;                                        // [2]
-    uint64_t* hready = accempty + 2;                                         // h(t) is in TMEM (phase 0: the initial zeroing)
+    // FOUR 64-column accumulators (two per half-chunk, alternating with the chunk parity): TMEM has H/2 + 256 <= 512 columns to give, and
+    // with only two the issuer stalled whenever one epilogue set was late -- tensor pipe 43 % at H = 512 (profiles/r02_layerwise_c5_ncu.txt)
+    uint64_t* accfull = empty + nstage;                                      // [4]: index 2 * (chunk & 1) + half
+    uint64_t* accempty = accfull + 4;                                        // [4]
+    uint64_t* hready = accempty + 4;                                         // h(t) is in TMEM (phase 0: the initial zeroing)
     uint64_t* stepdone = hready + 1;                                         // every MMA of the step has retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stepdone + 1);
 
     if (tid == 0) {
         for (int i = 0; i < nstage; ++i) { mbar_init(&full[i], leader ? 2 : 1); mbar_init(&empty[i], 1); }
-        for (int h = 0; h < 2; ++h) { mbar_init(&accfull[h], 1); mbar_init(&accempty[h], R5_EPI_WARPS); }   // 8 warps x 2 CTAs
+        for (int h = 0; h < 4; ++h) { mbar_init(&accfull[h], 1); mbar_init(&accempty[h], R5_EPI_WARPS); }   // 8 warps x 2 CTAs
         mbar_init(hready, 2 * R5_EPI_WARPS);
         mbar_init(stepdone, 1);
         fence_barrier_init();
@@ -112,7 +114,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
             constexpr uint32_t DESC_HI = 0x40004040u;              // SBO = 1024 B, version 1, SWIZZLE_128B (umma_desc_sw128)
             uint32_t d = tmem + acc_col;
             const uint32_t stage_lo0 = ((smem_u32(stages) >> 4) & 0x3FFFu) | (1u << 16);
-            int slot = 0; uint32_t ph = 0, accuse = 0;
+            int slot = 0; uint32_t ph = 0, accuse = 0;               // accuse: chunks issued so far (each accumulator is used every second chunk)
             auto mma_ts = [&](uint32_t a_col, uint32_t b_lo, uint32_t acc) {
                 asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 db, {%2, %5};\n\t"
                              "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(d), "r"(tmem + a_col), "r"(b_lo), "r"(IDESC), "r"(acc), "r"(DESC_HI) : "memory");
@@ -123,9 +125,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
                 for (int j = 0; j < NCH; ++j) {
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        mbar_wait(&accempty[half], (accuse & 1) ^ 1);
+                        const int ai = 2 * (j & 1) + half;
+                        mbar_wait(&accempty[ai], ((accuse >> 1) & 1) ^ 1);
                         tc5_fence_after();
-                        d = tmem + acc_col + 64 * half;
+                        d = tmem + acc_col + 64 * ai;
 #pragma unroll
                         for (int kb0 = 0; kb0 < KBH; kb0 += 4) {
                             mbar_wait(&full[slot], ph);
@@ -141,7 +144,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
                                     }
                                 umma2_commit_mc(&empty[slot], 3);
                                 if (kb0 + 4 >= KBH) {
-                                    umma2_commit_mc(&accfull[half], 3);
+                                    umma2_commit_mc(&accfull[ai], 3);
                                     if (j == NCH - 1 && half == 1) umma2_commit_mc(stepdone, 3);
                                 }
                             }
@@ -171,10 +174,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
         const int r = q * 32 + lane;
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
         const int set = cg & 1;                                     // which accumulator / half-chunk this warp serves
-        const uint32_t acc_my = acc_col + 64 * set + 32 * (cg >> 1);
-        uint64_t* my_accfull = &accfull[set];
-        uint64_t* my_accempty = &accempty[set];
-        const uint32_t r_accempty = mapa_u32(smem_u32(my_accempty), 0), r_hready = mapa_u32(smem_u32(hready), 0);
+        const uint32_t acc_my0 = acc_col + 64 * set + 32 * (cg >> 1);          // + 128 for odd chunks
+        const uint32_t r_accempty0 = mapa_u32(smem_u32(&accempty[set]), 0), r_accempty1 = mapa_u32(smem_u32(&accempty[2 + set]), 0);
+        const uint32_t r_hready = mapa_u32(smem_u32(hready), 0);
         {
             const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int c = cg; c < hcols / 8; c += 4) tmem_st8(tl + c * 8, z);
@@ -223,7 +225,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
                         gn[0] = ldg_u4_hint(np, pol_g); gn[1] = ldg_u4_hint(np + 1, pol_g); gn[2] = ldg_u4_hint(np + 2, pol_g); gn[3] = ldg_u4_hint(np + 3, pol_g);
                     }
                 }
-                mbar_wait(my_accfull, accn & 1);
+                const int ai = 2 * (j & 1) + set;
+                const uint32_t acc_my = acc_my0 + 128 * (j & 1);
+                mbar_wait(&accfull[ai], (accn >> 1) & 1);
                 ++accn;
                 tc5_fence_after();
                 uint32_t v[2][16];
@@ -232,7 +236,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R5_THREADS, 1) lstm_
                 tmem_wait_ld();
                 tc5_fence_before();
                 __syncwarp();
-                if (lane == 0) { if (leader) mbar_arrive(my_accempty); else mbar_arrive_remote(r_accempty); }
+                if (lane == 0) { if (leader) mbar_arrive(&accempty[ai]); else mbar_arrive_remote((j & 1) ? r_accempty1 : r_accempty0); }
                 {   // cell state of the next chunk in program order
                     const int nj = (j + 1 < NCH) ? j + 1 : 0;
                     const int nt = (j + 1 < NCH) ? t : t + 1;

@@ -420,3 +420,23 @@ def test_column_split_default_geometry_auto(built_lib, golden, monkeypatch, B):
     e0, d = O.rel_l2(out[0:1].cpu().numpy(), g["out"]), O.rel_l2(out.cpu().numpy(), out1.cpu().numpy())
     print(f"\n[column split default geometry B={B}] sample 0 vs reference golden {e0:.3e}; batch vs unsplit kernel {d:.2e}")
     assert e0 < MASK_TOL and d < 1e-5
+
+
+def test_internal_batch_split_under_a_workspace_cap(built_lib, monkeypatch):
+    """FSN_WS_CAP_GB (read at model creation): a batch whose workspace would exceed the cap runs as equal sub-batches on the same stream;
+    samples are independent, so the result equals the unsplit forward.  Layer-wise path (its time-batched input projection is the big
+    buffer) and the fused path; mask and fused-enhance outputs."""
+    for L, H in ((3, 64), (2, 64)):
+        cfg = _small(H)
+        params = O.make_params_plus(cfg, seed=81, num_layers=L)
+        mag, real, imag = _inputs(11, 33, 20, 41)
+        m = _plus(cfg, params, num_layers=L)
+        monkeypatch.setenv("FSN_WS_CAP_GB", "0.002")                   # ~2 MB: forces 3-4 sub-batches at this geometry
+        ms = _plus(cfg, params, num_layers=L)
+        monkeypatch.delenv("FSN_WS_CAP_GB")
+        with torch.no_grad():
+            a, b = m(_t(mag), _t(real), _t(imag)), ms(_t(mag), _t(real), _t(imag))
+            ea, eb = m.enhance_spectrum(_t(mag), _t(real), _t(imag)), ms.enhance_spectrum(_t(mag), _t(real), _t(imag))
+        assert ms.last_launch_count() > m.last_launch_count()          # it really ran several sub-batches
+        assert O.rel_l2(b.cpu().numpy(), a.cpu().numpy()) < 1e-5
+        assert O.rel_l2(torch.view_as_real(eb).cpu().numpy(), torch.view_as_real(ea).cpu().numpy()) < 1e-5
