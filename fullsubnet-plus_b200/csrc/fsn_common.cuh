@@ -320,6 +320,17 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint4 v) {
 __device__ __forceinline__ void st_cluster_v2f(uint32_t cluster_addr, float a, float b) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
 }
+// remote store that carries its own completion: the 16 (8) bytes land in the destination CTA and its mbarrier's transaction count is
+// decremented by the same amount -- no fence, no separate arrive; a waiter that observes the phase sees the data
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint4 v, uint32_t cluster_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w), "r"(cluster_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_v2f(uint32_t cluster_addr, float a, float b, uint32_t cluster_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(cluster_addr), "f"(a), "f"(b), "r"(cluster_mbar)
+                 : "memory");
+}
 template <uint32_t NCOLS> __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(NCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");

@@ -94,7 +94,8 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
         for (int h = 0; h < 2; ++h) { mbar_init(&accfull[h], 1); mbar_init(&accempty[h], D5_EPI_WARPS); }   // 8 warps x 2 CTAs
         mbar_init(&hready[0], 2 * D5_EPI_WARPS); mbar_init(&hready[1], 2 * D5_EPI_WARPS);
         mbar_init(layerdone, 1);
-        if (S > 1) { mbar_init(hall, (S - 1) * D5_EPI_WARPS); mbar_init(pfree, (S - 1) * D5_EPI_WARPS); }
+        // hall: a transaction-count barrier -- one local arming arrive per layer-step, completed by the bytes of the other pairs' st.async
+        if (S > 1) { mbar_init(hall, 1); mbar_init(pfree, (S - 1) * D5_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == D5_EPI_WARPS + 1) tmem_alloc_pair<512>(tmem_slot);
@@ -359,6 +360,10 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
             }
             r_fcp = mapa_u32(smem_u32(fcpart + ((size_t)(sidx * 4 + cg) * 128 + r) * 2), rank);   // pair 0 (same rows) sums the fc partials
         }
+        const uint32_t r_hall0 = (S > 1) ? mapa_u32(smem_u32(hall), rank) : 0;                   // pair 0's barrier (fc partials)
+        // bytes the other S - 1 same-row CTAs send me per layer-step: their h chunks (16 B x 128 rows x 4 column groups x NCHS chunks
+        // each), plus -- pair 0, layer 1 -- their Linear(H -> 2) partials (8 B x 128 rows x 4 column groups each)
+        constexpr uint32_t HALL_H = (S - 1) * NCHS * 128 * 4 * 16, HALL_FC = (S - 1) * 128 * 4 * 8;
         const int grow = tile * 128 + r;
         const int ob = grow / a.F, of = grow % a.F;
         const int Tout = Tp - a.la;
@@ -373,6 +378,8 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
                     nx = make_float2(__ldg(a.nreal + ni), __ldg(a.nimag + ni));
                 }
                 if (S > 1 && ls > 0) mbar_wait_cluster(pfree, (ls - 1) & 1);   // what I parked remotely last layer-step has been consumed
+                if (S > 1 && warp == 0 && lane == 0)                            // arm this layer-step's phase (the previous one is complete: I waited for it)
+                    mbar_arrive_expect_tx(hall, HALL_H + ((layer == 1 && sidx == 0) ? HALL_FC : 0u));
                 for (int j = j0; j < j0 + NCHS; ++j) {
                     float4* cp = reinterpret_cast<float4*>(cbase + ((size_t)((layer * NCH + j) * 4 + cg) * 2) * 128 * 4) + r;
                     const float4 c4[2] = {cnext[0], cnext[1]};     // prefetched during the previous chunk
@@ -434,19 +441,13 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
                     *reinterpret_cast<uint4*>(mypark + (size_t)j * 128 * 16) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                     if (S > 1) {
 #pragma unroll
-                        for (int n = 0; n < S - 1; ++n) st_cluster_v4(r_park[n] + (uint32_t)j * 128 * 16, make_uint4(hp[0], hp[1], hp[2], hp[3]));
+                        for (int n = 0; n < S - 1; ++n) st_async_v4(r_park[n] + (uint32_t)j * 128 * 16, make_uint4(hp[0], hp[1], hp[2], hp[3]), r_hall[n]);
                     }
                 }
                 if (S > 1) {
                     if (layer == 1) {                              // my pair's share of Linear(H -> 2): summed by pair 0 after the exchange
                         if (sidx == 0) { fcpart[((size_t)cg * 128 + r) * 2] = fc0; fcpart[((size_t)cg * 128 + r) * 2 + 1] = fc1; }
-                        else st_cluster_v2f(r_fcp, fc0, fc1);
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        fence_acq_rel_cluster();                   // the warp's remote stores happen-before the arrives below
-#pragma unroll
-                        for (int n = 0; n < S - 1; ++n) mbar_arrive_remote(r_hall[n]);
+                        else st_async_v2f(r_fcp, fc0, fc1, r_hall0);
                     }
                 }
                 mbar_wait(layerdone, ls & 1);

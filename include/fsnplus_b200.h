@@ -108,7 +108,8 @@ int fsn_model_finalize(fsn_model* m);
  * Model.forward(noisy_mag) (fullsubnet.py:68-118; pass d_real = d_imag = NULL).
  * Inputs: [B, 1, F, T] float32, contiguous, device.  Output: [B, output_size, F, T] float32, contiguous,
  * device, caller-owned.  Every sample is processed independently (the eval semantics of the reference
- * called with batch 1; the training-only drop_band of fullsubnet_plus.py:192-196 is never applied). */
+ * called with batch 1; the training-only drop_band of fullsubnet_plus.py:192-196 is never applied).  Because of that a
+ * batch whose workspace would exceed FSN_WS_CAP_GB (default 48) is run as equal sub-batches on `stream`, with identical results. */
 int fsn_model_forward(fsn_model* m, const float* d_mag, const float* d_real, const float* d_imag, int32_t B, int32_t T,
                       float* d_out, void* stream);
 /* The model call PLUS the two lines that follow it in the reference's inferencer methods (fullsubnet_plus/inferencer/inferencer.py:152-157,
