@@ -34,14 +34,20 @@ def _plus(cfg, params, **kw):
     from fsnplus_b200.model import FullSubNet_Plus
     m = FullSubNet_Plus(**cfg, **kw)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
-    return m.to(DEV).eval()
+    m = m.to(DEV).eval()
+    with torch.cuda.device(DEV):
+        m._ensure_handle(torch.device(DEV))         # the C handle (which reads the FSN_* knobs ONCE) is created here, not at the first forward
+    return m
 
 
 def _fsn(cfg, params, **kw):
     from fsnplus_b200.model import Model
     m = Model(**cfg, **kw)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
-    return m.to(DEV).eval()
+    m = m.to(DEV).eval()
+    with torch.cuda.device(DEV):
+        m._ensure_handle(torch.device(DEV))
+    return m
 
 
 def _inputs(B, F, T, seed):
