@@ -377,7 +377,6 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
                     const size_t ni = ((size_t)ob * a.F + of) * Tout + (t - a.la);
                     nx = make_float2(__ldg(a.nreal + ni), __ldg(a.nimag + ni));
                 }
-                if (S > 1 && ls > 0) mbar_wait_cluster(pfree, (ls - 1) & 1);   // what I parked remotely last layer-step has been consumed
                 if (S > 1 && warp == 0 && lane == 0)                            // arm this layer-step's phase (the previous one is complete: I waited for it)
                     mbar_arrive_expect_tx(hall, HALL_H + ((layer == 1 && sidx == 0) ? HALL_FC : 0u));
                 for (int j = j0; j < j0 + NCHS; ++j) {
@@ -438,6 +437,9 @@ __global__ void __cluster_dims__(2 * S, 1, 1) __launch_bounds__(D5_THREADS, 1) l
                     }
                     st_f4_hint(cp, make_float4(cn[0], cn[1], cn[2], cn[3]), pol_c);
                     st_f4_hint(cp + 128, make_float4(cn[4], cn[5], cn[6], cn[7]), pol_c);
+                    // S > 1: what I parked remotely last layer-step must have been consumed before I overwrite it -- waited for as late as
+                    // possible (after the drain and the cell math of the first chunk), so the other pairs' tails overlap my epilogue
+                    if (S > 1 && ls > 0 && j == j0) mbar_wait_cluster(pfree, (ls - 1) & 1);
                     *reinterpret_cast<uint4*>(mypark + (size_t)j * 128 * 16) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                     if (S > 1) {
 #pragma unroll
