@@ -295,7 +295,8 @@ static int pack_tcn5(fsn_model* m) {
     cudaGetDevice(&dev);
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) m->num_sms = prop.multiProcessorCount;
     const char* sfx[3] = {"", "_real", "_imag"};
-    std::vector<float> W1((size_t)8 * 3 * Hd * Cp, 0.f), W2((size_t)8 * 3 * Cp * Hd, 0.f), Wfc((size_t)3 * Cp * Cp, 0.f);
+    std::vector<float> W1((size_t)8 * 3 * Hd * Cp, 0.f), Wfc((size_t)3 * Cp * Cp, 0.f);
+    std::vector<__half> W2((size_t)8 * 3 * Cp * Hd, __float2half_rn(0.f));      // second 1x1 conv: fp16 operands (hidden activations are fp16)
     std::vector<float> S1((size_t)8 * 3 * Cp, 0.f), S2b((size_t)8 * 3 * Cp, 0.f), Bfc((size_t)3 * Cp, 0.f);
     for (int blk = 0; blk < 8; ++blk)
         for (int b = 0; b < 3; ++b) {
@@ -308,12 +309,13 @@ static int pack_tcn5(fsn_model* m) {
             float* d1 = &W1[((size_t)blk * 3 + b) * Hd * Cp];
             for (int o = 0; o < Hd; ++o)
                 for (int k = 0; k < F; ++k) d1[(size_t)o * Cp + k] = to_tf32(w1[(size_t)o * F + k]);
-            float* d2 = &W2[((size_t)blk * 3 + b) * Cp * Hd];
+            __half* d2 = &W2[((size_t)blk * 3 + b) * Cp * Hd];
             for (int n = 0; n < F; ++n) {
                 double s1 = 0, s2 = 0;
                 for (int k = 0; k < Hd; ++k) {
-                    const float wf = to_tf32(w2[(size_t)n * Hd + k] * g2[k]);
-                    d2[(size_t)n * Hd + k] = wf;
+                    const __half wh = __float2half_rn(w2[(size_t)n * Hd + k] * g2[k]);
+                    const float wf = __half2float(wh);
+                    d2[(size_t)n * Hd + k] = wh;
                     s1 += (double)wf;
                     s2 += (double)w2[(size_t)n * Hd + k] * (double)be2[k];
                 }
@@ -329,12 +331,12 @@ static int pack_tcn5(fsn_model* m) {
             Bfc[(size_t)b * Cp + n] = bb[n];
         }
     }
-    if (upload(m->tW1, W1.data(), W1.size() * 4) || upload(m->tW2, W2.data(), W2.size() * 4) || upload(m->tWfc, Wfc.data(), Wfc.size() * 4) ||
+    if (upload(m->tW1, W1.data(), W1.size() * 4) || upload(m->tW2, W2.data(), W2.size() * sizeof(__half)) || upload(m->tWfc, Wfc.data(), Wfc.size() * 4) ||
         upload(m->tS1, S1.data(), S1.size() * 4) || upload(m->tS2b, S2b.data(), S2b.size() * 4) || upload(m->tBfc, Bfc.data(), Bfc.size() * 4))
         return fail(FSN_ECUDA, "upload of the TCN weights failed");
     for (int blk = 0; blk < 8; ++blk) {
         if (make_tmap_f32_2d(m->mapW1[blk], static_cast<float*>(m->tW1.p) + (size_t)blk * 3 * Hd * Cp, 3 * Hd, Cp, 256) ||
-            make_tmap_f32_2d(m->mapW2[blk], static_cast<float*>(m->tW2.p) + (size_t)blk * 3 * Cp * Hd, 3 * Cp, Hd, m->tcnNT))
+            make_tmap_f16_2d(m->mapW2[blk], static_cast<__half*>(m->tW2.p) + (size_t)blk * 3 * Cp * Hd, 3 * Cp, Hd, m->tcnNT))
             return fail(FSN_ECUDA, "cuTensorMapEncodeTiled failed for the TCN weights");
     }
     if (make_tmap_f32_2d(m->mapWfc, m->tWfc.p, 3 * Cp, Cp, m->tcnNT)) return fail(FSN_ECUDA, "cuTensorMapEncodeTiled failed (fc)");
@@ -580,14 +582,14 @@ static int ensure_ws(fsn_model* m, fsn_model::Lane& ln, int B, int T, cudaStream
         e |= ln.xa.ensure(trows * m->Cp * 4, true, s);
         e |= ln.xb.ensure(trows * m->Cp * 4, true, s);
         e |= ln.xr.ensure(trows * m->Cp * 4, true, s);
-        e |= ln.y1.ensure(trows * 512 * 4, true, s);
-        e |= ln.y2.ensure(trows * 512 * 4, true, s);
+        e |= ln.y1.ensure(trows * 512 * sizeof(__half), true, s);
+        e |= ln.y2.ensure(trows * 512 * sizeof(__half), true, s);
         e |= ln.stats.ensure((size_t)8 * 2 * 3 * B * 2 * sizeof(double), true, s);
         if (use_xfuse(m)) e |= ln.fbo.ensure(trows * m->Cp * 4, true, s);
         if (!e && regeo) {
             if (make_tmap_f32_2d(ln.mapX0, ln.x0.p, trows, m->Cp, 128) || make_tmap_f32_2d(ln.mapXa, ln.xa.p, trows, m->Cp, 128) ||
                 make_tmap_f32_2d(ln.mapXb, ln.xb.p, trows, m->Cp, 128) || make_tmap_f32_2d(ln.mapXr, ln.xr.p, trows, m->Cp, 128) ||
-                make_tmap_f32_2d(ln.mapY2, ln.y2.p, trows, 512, 128))
+                make_tmap_f16_2d(ln.mapY2, ln.y2.p, trows, 512, 128))
                 return fail(FSN_ECUDA, "cuTensorMapEncodeTiled failed for the activations");
         }
     } else {
@@ -766,21 +768,23 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
                 GemmTc5Launch g1 = g;
                 g1.epi = EPI5_PRELU_STATS; g1.Kp = Cp; g1.NT = 256; g1.ntiles_n = 2; g1.Npad = 512;
                 for (int b = 0; b < 3; ++b) { g1.bias[b] = P(m, key(b, "conv1x1.bias")); g1.prelu[b] = P(m, key(b, "prelu1.weight")); }
-                g1.stats_out = st1; g1.Y = static_cast<float*>(ln.y1.p); g1.ldY = 512;
+                g1.stats_out = st1; g1.Y16 = static_cast<__half*>(ln.y1.p); g1.ldY = 512;
                 int e = launch_gemm_tc5(curmap, m->mapW1[blk], g1, m->num_sms, s);
                 if (e) return fail(FSN_ECUDA, "TCN GEMM1 launch failed: %s", cudaGetErrorString((cudaError_t)e));
                 m->launches++;
 
                 DwTmLaunch dw{};
-                dw.X = static_cast<const float*>(ln.y1.p); dw.Y = static_cast<float*>(ln.y2.p);
-                dw.Z = Z; dw.B = B; dw.C = 512; dw.Tp = Tp; dw.dilation = dil[blk]; dw.tchunk = 48; dw.causal = c.tcn_causal ? 1 : 0;
+                dw.X = static_cast<const __half*>(ln.y1.p); dw.Y = static_cast<__half*>(ln.y2.p);
+                dw.Z = Z; dw.B = B; dw.C = 512; dw.Tp = Tp; dw.dilation = dil[blk]; dw.causal = c.tcn_causal ? 1 : 0;
                 dw.stats_in = st1; dw.stats_out = st2;
                 for (int b = 0; b < 3; ++b) {
                     dw.gamma[b] = P(m, key(b, "norm1.weight")); dw.beta[b] = P(m, key(b, "norm1.bias"));
                     dw.w[b] = P(m, key(b, "depthwise_conv.weight")); dw.b[b] = P(m, key(b, "depthwise_conv.bias"));
                     dw.prelu[b] = P(m, key(b, "prelu2.weight"));
                 }
-                launch_dwconv_tm(dw, s); m->launches++;
+                e = launch_dwconv_tm(dw, s);
+                if (e) return fail(FSN_ECUDA, "TCN depth-wise conv launch failed: %s", cudaGetErrorString((cudaError_t)e));
+                m->launches++;
 
                 float* nxtp = (blk & 1) ? static_cast<float*>(ln.xb.p) : static_cast<float*>(ln.xa.p);
                 GemmTc5Launch g2 = g;
@@ -943,7 +947,7 @@ static double ws_bytes_per_sample(const fsn_model* m, int T) {
     const fsn_config& c = m->cfg;
     const double F = c.num_freqs, Tp = T + c.look_ahead, rows = F;              // sequences per sample
     double b = 0;
-    if (c.model_kind == FSN_KIND_PLUS) b += 3 * F * Tp * 4 * 2 + 3 * Tp * (5.0 * m->Cp + 2 * 512) * 4;   // fb_in/out, X0/Xa/Xb/Xr/fbo, Y1/Y2
+    if (c.model_kind == FSN_KIND_PLUS) b += 3 * F * Tp * 4 * 2 + 3 * Tp * (5.0 * m->Cp + 512) * 4;       // fb_in/out, X0/Xa/Xb/Xr/fbo (fp32), Y1/Y2 (fp16)
     else b += F * Tp * 4 * 4 + Tp * (F + c.fb_hidden) * 4;
     b += rows * Tp * 128;                                                       // packed sub-band images (when used)
     b += rows * c.num_layers * c.sb_hidden * 4;                                  // cell state

@@ -185,11 +185,12 @@ void lstm_tc5r_pack_layer(int H, int Kin, int Kpad, const float* w_ih, const flo
 struct GemmF16Launch { long long M; int N, K; __half* C; long long ldc; };
 bool gemm_f16_supported(long long M, int N, int K);
 int launch_gemm_f16(const void* A, const void* B, const GemmF16Launch& a, int num_sms, cudaStream_t s);
+int make_tmap_f16_2d(void* out_map /*128 B, 64 B aligned*/, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);   // box = 64 halves x box_rows, SWIZZLE_128B
 
 // ---- k_gemm_tc5.cu (TCN on tcgen05, time-major activations) ----------------------------------
 enum { EPI5_PRELU_STATS = 1, EPI5_GLN_RES = 2, EPI5_OUT = 3 };
 struct GemmTc5Launch {
-    int Kp, NT, nstage, ntiles_n, Npad;        // K (multiple of 32), N tile, ring depth, N tiles and padded N per branch
+    int Kp, NT, nstage, ntiles_n, Npad;        // K (multiple of 32; GLN_RES: fp16 operands, multiple of 64), N tile, ring depth, N tiles and padded N per branch
     int rows_per_branch, tiles_m, nbranch, Tp, B;
     int epi;
     const float* bias[3];                      // PRELU_STATS / OUT: conv bias; GLN_RES: s2 + conv bias
@@ -197,7 +198,8 @@ struct GemmTc5Launch {
     const float* s1[3];                        // GLN_RES: sum_c W'[n, c]
     double* stats_out;                         // [Z, 2]
     const double* stats_in; double count_in;
-    float* Y; int ldY;                         // PRELU_STATS: output; GLN_RES: new residual stream
+    float* Y; int ldY;                         // GLN_RES: new residual stream (fp32)
+    __half* Y16;                               // PRELU_STATS: the hidden activation, fp16 [rows, ldY]
     const float* Xold; float* Xrelu;           // GLN_RES: residual input, optional relu'd copy
     float* out; int F, P, act;                 // OUT: [Z, F, P] (frequency-major) ...
     float* out_tm;                             // ... or, when set, time-major [(branch, b, t), ldY] (read by the LSTM's x-tile builders)
@@ -205,12 +207,12 @@ struct GemmTc5Launch {
 int make_tmap_f32_2d(void* out_map /*128 B, 64 B aligned*/, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 int launch_gemm_tc5(const void* mapA, const void* mapB, GemmTc5Launch a, int num_sms, cudaStream_t s);
 struct DwTmLaunch {
-    const float* X; float* Y;                  // [Z * Tp, C]
-    int Z, B, C, Tp, dilation, tchunk;
+    const __half* X; __half* Y;                // [Z * Tp, C] hidden activations, fp16
+    int Z, B, C, Tp, dilation;
     int causal;                                // 1: taps t-2d, t-d, t (TCNBlock(causal=True)); 0: t-d, t, t+d
     const double* stats_in; double* stats_out;
     const float* gamma[3]; const float* beta[3]; const float* w[3]; const float* b[3]; const float* prelu[3];
 };
-void launch_dwconv_tm(const DwTmLaunch& a, cudaStream_t s);
+int launch_dwconv_tm(const DwTmLaunch& a, cudaStream_t s);
 
 }  // namespace fsn

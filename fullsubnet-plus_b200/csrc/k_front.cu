@@ -19,7 +19,7 @@ namespace fsn {
 // =============================================================================================
 constexpr int TSSE_KMAX = 16;
 
-__global__ void __launch_bounds__(256) tsse_norm_kernel(TsseLaunch a) {
+__global__ void __launch_bounds__(1024) tsse_norm_kernel(TsseLaunch a) {
     extern __shared__ float sm[];
     const int b = blockIdx.x, br = blockIdx.y;
     const int F = a.F, T = a.T, Tp = a.Tp;
@@ -39,7 +39,15 @@ __global__ void __launch_bounds__(256) tsse_norm_kernel(TsseLaunch a) {
     for (int f = warp; f < F; f += nwarp) {
         const float* row = x + (size_t)f * T;
         float acc = 0.f, mx = -INFINITY, mn = INFINITY;
-        for (int t = lane; t < T; t += 32) { const float v = row[t]; acc += v; mx = fmaxf(mx, v); mn = fminf(mn, v); }
+        // 32 warps per CTA and eight independent loads per lane in flight: the pass is a pure read of the sample (HBM-bound)
+        for (int t0 = 0; t0 < T; t0 += 256) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int t = t0 + u * 32 + lane; v[u] = (t < T) ? __ldg(row + t) : 0.f; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (t0 + u * 32 + lane < T) { acc += v[u]; mx = fmaxf(mx, v[u]); mn = fminf(mn, v[u]); }
+        }
         acc = warp_sum(acc);
 #pragma unroll
         for (int o = 16; o; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(256) tsse_apply_kernel(TsseLaunch a) {
 void launch_tsse_norm(const TsseLaunch& a, cudaStream_t s) {
     size_t smem = sizeof(float) * ((size_t)a.F * (5 + 2 * TSSE_KMAX) + a.F / 2 + 8);
     cudaFuncSetAttribute(tsse_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    tsse_norm_kernel<<<dim3(a.B, a.nbranch), 256, smem, s>>>(a);
+    tsse_norm_kernel<<<dim3(a.B, a.nbranch), 1024, smem, s>>>(a);
     tsse_apply_kernel<<<dim3((a.P + 31) / 32, (a.F + 31) / 32, a.B * a.nbranch), 256, 0, s>>>(a);
 }
 

@@ -9,9 +9,11 @@
 // W[C_out, C_in]^T  with BOTH operands K-major -- the layout PyTorch already stores W in.  Tiles of 128 rows x 32 k
 // (A) and N_TILE x 32 k (B) are fetched by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a shared-memory ring,
 // multiplied with tcgen05.mma.kind::tf32 into double-buffered TMEM accumulators, and finished by four epilogue warps:
-//   EPI_PRELU_STATS : + bias, PReLU, per-sample sum / sum-of-squares for the following gLN, store (rounded to tf32)
+//   EPI_PRELU_STATS : + bias, PReLU, per-sample sum / sum-of-squares for the following gLN, store as fp16 (the hidden, 512-channel
+//                     activations of a block live in fp16: the same 10 mantissa bits the tf32 product consumed, half the bytes)
 //   EPI_GLN_RES     : gLN folded analytically -- conv(W, gLN(y)) = rstd * (W diag(gamma)) y - mean rstd s1 + s2 --
-//                     so the GEMM runs on the raw activation and the per-sample affine is applied here, + residual
+//                     so the GEMM runs on the raw activation and the per-sample affine is applied here, + residual (fp32 stream).
+//                     Its operands (hidden activation, folded weights) are fp16: kind::f16, 64-element k-blocks.
 //   EPI_OUT         : + bias, output activation, written transposed into the [branch, B, F, T'] layout the sub-band
 //                     packer reads.
 #include <cuda.h>
@@ -69,7 +71,9 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     __syncthreads();
     tc5_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int nkb = a.Kp / 32;
+    constexpr bool AH = (EPI == EPI5_GLN_RES);             // fp16 operands: a 128-byte swizzle atom holds 64 k-elements instead of 32
+    constexpr int KBW = AH ? 64 : 32;
+    const int nkb = a.Kp / KBW;
     const int tiles_per_branch = a.tiles_m * a.ntiles_n;
     const int total = a.nbranch * tiles_per_branch;
 
@@ -84,15 +88,15 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     mbar_wait(&empty[slot], ph ^ 1);
                     uint8_t* st = smem + (size_t)slot * stage_bytes;
                     mbar_arrive_expect_tx(&full[slot], stage_bytes);
-                    tma_load_2d(st, &mapA, kb * 32, arow, &full[slot]);
-                    tma_load_2d(st + G5_A_BYTES, &mapB, kb * 32, brow, &full[slot]);
+                    tma_load_2d(st, &mapA, kb * KBW, arow, &full[slot]);
+                    tma_load_2d(st + G5_A_BYTES, &mapB, kb * KBW, brow, &full[slot]);
                     if (++slot == nstage) { slot = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         {   // warp-uniform issue loop, instructions predicated on one elected lane (see elect_one)
-            const uint32_t idesc = umma_idesc_tf32(128, NT);
+            const uint32_t idesc = AH ? umma_idesc_f16(128, NT) : umma_idesc_tf32(128, NT);
             int slot = 0; uint32_t ph = 0, use[2] = {0, 0}, it = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
@@ -107,7 +111,10 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + G5_A_BYTES);
                     if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) umma_ss_tf32(d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+                        for (int kk = 0; kk < 4; ++kk) {                  // 32 bytes of K per instruction: 8 tf32 or 16 fp16 elements
+                            if (AH) umma_ss(d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+                            else umma_ss_tf32(d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+                        }
                         umma_commit(&empty[slot]);
                         if (kb == nkb - 1) umma_commit(&accfull[buf]);
                     }
@@ -170,13 +177,13 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         float t = __uint_as_float(v[i]) + bvec[i];
                         t = (t >= 0.f) ? t : slope * t;
                         ls += t; lq = fmaf(t, t, lq);
-                        y[i] = round_tf32(t);
+                        y[i] = fminf(fmaxf(t, -65504.f), 65504.f);
                     }
                     lsum += (double)ls; lsq += (double)lq;
                     if (valid) {
-                        float4* dst = reinterpret_cast<float4*>(a.Y + grow * a.ldY + n);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                        uint4* dst = reinterpret_cast<uint4*>(a.Y16 + grow * a.ldY + n);
+                        dst[0] = make_uint4(pack_half2(y[0], y[1]), pack_half2(y[2], y[3]), pack_half2(y[4], y[5]), pack_half2(y[6], y[7]));
+                        dst[1] = make_uint4(pack_half2(y[8], y[9]), pack_half2(y[10], y[11]), pack_half2(y[12], y[13]), pack_half2(y[14], y[15]));
                     }
                 } else if (EPI == EPI5_GLN_RES) {
                     if (valid) {
@@ -276,7 +283,7 @@ int launch_gemm_tc5(const void* mapA, const void* mapB, GemmTc5Launch a, int num
     const int stage_bytes = G5_A_BYTES + a.NT * 128;
     a.nstage = (227 * 1024 - 2048) / stage_bytes;
     if (a.nstage > 8) a.nstage = 8;
-    if (a.nstage < 2 || a.NT % 16 || a.NT > 256 || a.Kp % 32) return (int)cudaErrorInvalidValue;
+    if (a.nstage < 2 || a.NT % 16 || a.NT > 256 || a.Kp % (a.epi == EPI5_GLN_RES ? 64 : 32)) return (int)cudaErrorInvalidValue;
     const size_t smem = (size_t)a.nstage * stage_bytes + 1024 + 256;
     const int total = a.nbranch * a.tiles_m * a.ntiles_n;
     const int grid = total < num_sms ? total : num_sms;
@@ -295,57 +302,72 @@ int launch_gemm_tc5(const void* mapA, const void* mapB, GemmTc5Launch a, int num
 }
 
 // gLN1 apply -> depth-wise conv (k=3, dilation d, zero padding in the normalised domain; causal or symmetric taps) -> PReLU2 + gLN2 statistics,
-// on the time-major [rows, C] layout.  reference: causal_conv.py:100-106.  One CTA = one sample x 64 channels x all
-// frames: the slab (T' x 64 floats, 48 KB for T' = 190) is staged once in shared memory with the gLN already applied,
-// so every input element is read exactly once from HBM/L2 and the three taps come from shared memory.
-constexpr int DW_CH = 64;
+// on the time-major [rows, C] fp16 layout.  reference: causal_conv.py:100-106.  One CTA = one sample x 64 channels x DW_TCH frames
+// (+ a halo of 2d frames either side): the slab is staged once in shared memory in fp32 with the gLN already applied, so every input
+// element is read once from HBM/L2 (halo rows twice) and the three taps come from shared memory.  All arithmetic in fp32; the
+// statistics are taken before the result is rounded to fp16.  Clips of any length: the frame axis is chunked.
+constexpr int DW_CH = 64, DW_TCH = 256, DW_HALO = 18;    // 2 * max dilation (9) frames: covers both tap geometries
 __global__ void __launch_bounds__(256) dwconv_tm_kernel(DwTmLaunch a) {
-    extern __shared__ float slab[];                       // [Tp][DW_CH]
+    extern __shared__ float slab[];                       // [rows <= DW_TCH + 2 DW_HALO][DW_CH]
     __shared__ double red[16];
-    const int z = blockIdx.y, g = z / a.B, c0 = blockIdx.x * DW_CH;
+    const int z = blockIdx.z, g = z / a.B, c0 = blockIdx.x * DW_CH;
     const int C = a.C, Tp = a.Tp, d = a.dilation;
+    const int t0 = blockIdx.y * DW_TCH, t1 = min(t0 + DW_TCH, Tp);
+    const int lo = max(t0 - 2 * d, 0), hi = min(t1 + 2 * d, Tp);    // staged frames [lo, hi)
     const double cnt = (double)C * (double)Tp;
     const double mu = a.stats_in[2 * z] / cnt;
     const double var = a.stats_in[2 * z + 1] / cnt - mu * mu;
     const float mean = (float)mu, rstd = (float)(1.0 / sqrt((var > 0 ? var : 0) + 1e-8));
     const float slope = __ldg(a.prelu[g]);
     const size_t base = (size_t)z * Tp * C + c0;
-    const int cq = threadIdx.x & 15, tr = threadIdx.x >> 4;           // 16 float4 columns x 16 frame rows per pass
-    float4 ga, be, w0, w1, w2, bb;
+    const int cq = threadIdx.x & 7, tr = threadIdx.x >> 3;            // 8 columns of 8 channels x 32 frame rows per pass
+    float ga[8], be[8], w0[8], w1[8], w2[8], bb[8];
     {
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma[g] + c0) + cq);
-        const float4 bt = __ldg(reinterpret_cast<const float4*>(a.beta[g] + c0) + cq);
-        ga = make_float4(gm.x * rstd, gm.y * rstd, gm.z * rstd, gm.w * rstd);
-        be = make_float4(bt.x - mean * ga.x, bt.y - mean * ga.y, bt.z - mean * ga.z, bt.w - mean * ga.w);
-        const float* wp = a.w[g] + (size_t)(c0 + cq * 4) * 3;
-        w0 = make_float4(__ldg(wp + 0), __ldg(wp + 3), __ldg(wp + 6), __ldg(wp + 9));
-        w1 = make_float4(__ldg(wp + 1), __ldg(wp + 4), __ldg(wp + 7), __ldg(wp + 10));
-        w2 = make_float4(__ldg(wp + 2), __ldg(wp + 5), __ldg(wp + 8), __ldg(wp + 11));
-        bb = __ldg(reinterpret_cast<const float4*>(a.b[g] + c0) + cq);
+        const int cb = c0 + cq * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            ga[e] = __ldg(a.gamma[g] + cb + e) * rstd;
+            be[e] = __ldg(a.beta[g] + cb + e) - mean * ga[e];
+            const float* wp = a.w[g] + (size_t)(cb + e) * 3;
+            w0[e] = __ldg(wp); w1[e] = __ldg(wp + 1); w2[e] = __ldg(wp + 2);
+            bb[e] = __ldg(a.b[g] + cb + e);
+        }
     }
-    for (int t = tr; t < Tp; t += 16) {
-        const float4 v = *reinterpret_cast<const float4*>(a.X + base + (size_t)t * C + cq * 4);
-        reinterpret_cast<float4*>(slab + t * DW_CH)[cq] =
-            make_float4(fmaf(v.x, ga.x, be.x), fmaf(v.y, ga.y, be.y), fmaf(v.z, ga.z, be.z), fmaf(v.w, ga.w, be.w));
+    for (int t = lo + tr; t < hi; t += 32) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.X + base + (size_t)t * C + cq * 8));
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+        float4* dst = reinterpret_cast<float4*>(slab + (size_t)(t - lo) * DW_CH + cq * 4);   // channels 8cq..8cq+3 | (+32 floats) 8cq+4..8cq+7: conflict-free
+        const float2 p0 = __half22float2(h[0]), p1 = __half22float2(h[1]), p2 = __half22float2(h[2]), p3 = __half22float2(h[3]);
+        dst[0] = make_float4(fmaf(p0.x, ga[0], be[0]), fmaf(p0.y, ga[1], be[1]), fmaf(p1.x, ga[2], be[2]), fmaf(p1.y, ga[3], be[3]));
+        dst[8] = make_float4(fmaf(p2.x, ga[4], be[4]), fmaf(p2.y, ga[5], be[5]), fmaf(p3.x, ga[6], be[6]), fmaf(p3.y, ga[7], be[7]));
     }
     __syncthreads();
     float ls = 0.f, lq = 0.f;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = tr; t < Tp; t += 16) {
+    for (int t = t0 + tr; t < t1; t += 32) {
         // taps (w0, w1, w2): non-causal (t-d, t, t+d); causal (t-2d, t-d, t) -- padding 2d + chomp, causal_conv.py:74-75,104-105
         const int tl = a.causal ? t - 2 * d : t - d, tm = a.causal ? t - d : t, tr2 = a.causal ? t : t + d;
-        const float4 m = (tm >= 0) ? reinterpret_cast<const float4*>(slab + tm * DW_CH)[cq] : zero;
-        const float4 l = (tl >= 0) ? reinterpret_cast<const float4*>(slab + tl * DW_CH)[cq] : zero;
-        const float4 r = (tr2 < Tp) ? reinterpret_cast<const float4*>(slab + tr2 * DW_CH)[cq] : zero;
-        float o[4] = {fmaf(w0.x, l.x, fmaf(w1.x, m.x, fmaf(w2.x, r.x, bb.x))), fmaf(w0.y, l.y, fmaf(w1.y, m.y, fmaf(w2.y, r.y, bb.y))),
-                      fmaf(w0.z, l.z, fmaf(w1.z, m.z, fmaf(w2.z, r.z, bb.z))), fmaf(w0.w, l.w, fmaf(w1.w, m.w, fmaf(w2.w, r.w, bb.w)))};
+        float l[8], m[8], r[8];
+        auto tap = [&](int tt, float (&o)[8]) {
+            if (tt >= 0 && tt < Tp) {
+                const float4* src = reinterpret_cast<const float4*>(slab + (size_t)(tt - lo) * DW_CH + cq * 4);
+                const float4 x0 = src[0], x1 = src[8];
+                o[0] = x0.x; o[1] = x0.y; o[2] = x0.z; o[3] = x0.w; o[4] = x1.x; o[5] = x1.y; o[6] = x1.z; o[7] = x1.w;
+            } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            o[i] = (o[i] >= 0.f) ? o[i] : slope * o[i];
-            ls += o[i]; lq = fmaf(o[i], o[i], lq);
-            o[i] = round_tf32(o[i]);
+                for (int e = 0; e < 8; ++e) o[e] = 0.f;
+            }
+        };
+        tap(tl, l); tap(tm, m); tap(tr2, r);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float y = fmaf(w0[e], l[e], fmaf(w1[e], m[e], fmaf(w2[e], r[e], bb[e])));
+            y = (y >= 0.f) ? y : slope * y;
+            ls += y; lq = fmaf(y, y, lq);
+            o[e] = fminf(fmaxf(y, -65504.f), 65504.f);
         }
-        *reinterpret_cast<float4*>(a.Y + base + (size_t)t * C + cq * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(a.Y + base + (size_t)t * C + cq * 8) =
+            make_uint4(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]), pack_half2(o[4], o[5]), pack_half2(o[6], o[7]));
     }
     double s1 = warp_sum_d((double)ls), s2 = warp_sum_d((double)lq);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -359,10 +381,14 @@ __global__ void __launch_bounds__(256) dwconv_tm_kernel(DwTmLaunch a) {
     }
 }
 
-void launch_dwconv_tm(const DwTmLaunch& a, cudaStream_t s) {
-    const size_t smem = (size_t)a.Tp * DW_CH * sizeof(float);
-    cudaFuncSetAttribute(dwconv_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dwconv_tm_kernel<<<dim3(a.C / DW_CH, a.Z), 256, smem, s>>>(a);
+int launch_dwconv_tm(const DwTmLaunch& a, cudaStream_t s) {
+    if (a.C % DW_CH || 2 * a.dilation > DW_HALO) return (int)cudaErrorInvalidValue;
+    const int rows = (a.Tp < DW_TCH ? a.Tp : DW_TCH + 2 * DW_HALO);
+    const size_t smem = (size_t)rows * DW_CH * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(dwconv_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dwconv_tm_kernel<<<dim3(a.C / DW_CH, (a.Tp + DW_TCH - 1) / DW_TCH, a.Z), 256, smem, s>>>(a);
+    return (int)cudaGetLastError();
 }
 
 }  // namespace fsn
