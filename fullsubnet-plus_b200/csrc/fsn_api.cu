@@ -551,7 +551,7 @@ static int ensure_ws(fsn_model* m, fsn_model::Lane& ln, int B, int T, cudaStream
     e |= ln.fbout.ensure(act, true, s);
     e |= ln.mu.ensure((size_t)B * 4, true, s);
     e |= ln.sigma.ensure((size_t)B * 4, true, s);
-    e |= ln.tsse_scale.ensure((size_t)nbr * B * F * 4, true, s);
+    e |= ln.tsse_scale.ensure((size_t)nbr * B * F * 4 * (1 + tsse_row_floats()), true, s);      // per-row scale | row statistics
     e |= ln.sb_rowsum.ensure((size_t)B * 4 * F * 2 * 4, true, s);
     if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE) e |= ln.xn.ensure((size_t)nbr * B * F * Tp * 4, true, s);
     // images are re-zeroed whenever the geometry changes (rows beyond B*F and k >= I must stay zero)
@@ -584,7 +584,7 @@ static int ensure_ws(fsn_model* m, fsn_model::Lane& ln, int B, int T, cudaStream
         e |= ln.xr.ensure(trows * m->Cp * 4, true, s);
         e |= ln.y1.ensure(trows * 512 * sizeof(__half), true, s);
         e |= ln.y2.ensure(trows * 512 * sizeof(__half), true, s);
-        e |= ln.stats.ensure((size_t)8 * 2 * 3 * B * 2 * sizeof(double), true, s);
+        e |= ln.stats.ensure((size_t)8 * 2 * 3 * B * 2 * sizeof(double) + (size_t)8 * 3 * B * sizeof(float), true, s);   // gLN sums | per-block stream maxima
         if (use_xfuse(m)) e |= ln.fbo.ensure(trows * m->Cp * 4, true, s);
         if (!e && regeo) {
             if (make_tmap_f32_2d(ln.mapX0, ln.x0.p, trows, m->Cp, 128) || make_tmap_f32_2d(ln.mapXa, ln.xa.p, trows, m->Cp, 128) ||
@@ -740,6 +740,7 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
         }
         ta.out = static_cast<float*>(ln.fbin.p);
         ta.scale = static_cast<float*>(ln.tsse_scale.p);
+        ta.rows = ta.scale + (size_t)ta.nbranch * B * F;
         ta.out_tm = static_cast<float*>(ln.x0.p); ta.Cp = m->Cp;
         if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE) {
             NormLaunch na{};
@@ -749,11 +750,13 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
             for (int b = 0; b < 3; ++b) ta.x[b] = static_cast<const float*>(ln.xn.p) + (size_t)b * B * F * Tp;
             ta.T = Tp; ta.prenorm = 1;                                  // padded frames are part of the normalised signal
         }
-        launch_tsse_norm(ta, s); m->launches += 2;
-
         const int Z = 3 * B;
         double* stats = static_cast<double*>(ln.stats.p);
-        CK(cudaMemsetAsync(stats, 0, (size_t)8 * 2 * Z * 2 * sizeof(double), s));
+        float* amax = reinterpret_cast<float*>(stats + (size_t)8 * 2 * Z * 2);            // [8][Z]: max |x| of the stream entering block k, per sample
+        CK(cudaMemsetAsync(stats, 0, (size_t)8 * 2 * Z * 2 * sizeof(double) + (size_t)8 * Z * sizeof(float), s));
+        ta.amax = amax;                                                                    // block 0: written by the gate kernel
+        launch_tsse_norm(ta, s); m->launches += 3;
+
         static const int dil[8] = {1, 2, 5, 9, 1, 2, 5, 9};     // sequence_model.py:47-58
         {
             const int Cp = m->Cp;
@@ -768,7 +771,7 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
                 GemmTc5Launch g1 = g;
                 g1.epi = EPI5_PRELU_STATS; g1.Kp = Cp; g1.NT = 256; g1.ntiles_n = 2; g1.Npad = 512;
                 for (int b = 0; b < 3; ++b) { g1.bias[b] = P(m, key(b, "conv1x1.bias")); g1.prelu[b] = P(m, key(b, "prelu1.weight")); }
-                g1.stats_out = st1; g1.Y16 = static_cast<__half*>(ln.y1.p); g1.ldY = 512;
+                g1.stats_out = st1; g1.Y16 = static_cast<__half*>(ln.y1.p); g1.ldY = 512; g1.amax_in = amax + (size_t)blk * Z;
                 int e = launch_gemm_tc5(curmap, m->mapW1[blk], g1, m->num_sms, s);
                 if (e) return fail(FSN_ECUDA, "TCN GEMM1 launch failed: %s", cudaGetErrorString((cudaError_t)e));
                 m->launches++;
@@ -776,7 +779,7 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
                 DwTmLaunch dw{};
                 dw.X = static_cast<const __half*>(ln.y1.p); dw.Y = static_cast<__half*>(ln.y2.p);
                 dw.Z = Z; dw.B = B; dw.C = 512; dw.Tp = Tp; dw.dilation = dil[blk]; dw.causal = c.tcn_causal ? 1 : 0;
-                dw.stats_in = st1; dw.stats_out = st2;
+                dw.stats_in = st1; dw.stats_out = st2; dw.amax = amax + (size_t)blk * Z;
                 for (int b = 0; b < 3; ++b) {
                     dw.gamma[b] = P(m, key(b, "norm1.weight")); dw.beta[b] = P(m, key(b, "norm1.bias"));
                     dw.w[b] = P(m, key(b, "depthwise_conv.weight")); dw.b[b] = P(m, key(b, "depthwise_conv.bias"));
@@ -794,7 +797,7 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
                     g2.s1[b] = static_cast<const float*>(m->tS1.p) + ((size_t)blk * 3 + b) * Cp;
                 }
                 g2.stats_in = st2; g2.count_in = (double)512 * Tp;
-                g2.Xold = curp; g2.Y = nxtp; g2.ldY = Cp; g2.Xrelu = (blk == 7) ? static_cast<float*>(ln.xr.p) : nullptr;
+                g2.Xold = curp; g2.Y = nxtp; g2.ldY = Cp; g2.amax_out = (blk < 7) ? amax + (size_t)(blk + 1) * Z : nullptr; g2.Xrelu = (blk == 7) ? static_cast<float*>(ln.xr.p) : nullptr;
                 e = launch_gemm_tc5(ln.mapY2, m->mapW2[blk], g2, m->num_sms, s);
                 if (e) return fail(FSN_ECUDA, "TCN GEMM2 launch failed: %s", cudaGetErrorString((cudaError_t)e));
                 m->launches++;
@@ -827,6 +830,7 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
         ta.x[0] = d_mag; ta.nbranch = 1; ta.B = B; ta.F = F; ta.T = T; ta.Tp = Tp; ta.P = Pp; ta.attention = 0;
         ta.out = static_cast<float*>(ln.fbin.p);
         ta.scale = static_cast<float*>(ln.tsse_scale.p);
+        ta.rows = ta.scale + (size_t)ta.nbranch * B * F;
         if (c.norm_type != FSN_NORM_OFFLINE_LAPLACE) {
             NormLaunch na{};
             na.x[0] = d_mag; na.y = static_cast<float*>(ln.xn.p);
@@ -834,7 +838,7 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
             launch_input_norm(na, s); m->launches++;
             ta.x[0] = static_cast<const float*>(ln.xn.p); ta.T = Tp; ta.prenorm = 1;
         }
-        launch_tsse_norm(ta, s); m->launches += 2;
+        launch_tsse_norm(ta, s); m->launches += 3;
         launch_pad_copy(d_mag, static_cast<float*>(ln.magpad.p), B, F, T, Pp, s); m->launches++;
         const int Ipad = (F + 15) / 16 * 16, rows_pad = (B + 63) / 64 * 64;
         launch_fb_pack(static_cast<const float*>(ln.fbin.p), static_cast<__half*>(ln.fbx.p), B, F, Tp, Pp, rows_pad, Ipad, s); m->launches++;

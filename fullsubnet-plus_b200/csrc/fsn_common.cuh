@@ -60,6 +60,14 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Power-of-two down-scale for storing an activation in fp16 whose input stream has absolute maximum `amax` (per sample): exact
+// (no rounding), never amplifies (a bias term must not overflow when the stream is tiny), 1 for amax < 1.
+__device__ __forceinline__ float fp16_store_scale(float amax) {
+    int e = 0;
+    frexpf(fminf(amax, 3.0e38f), &e);                  // amax = m 2^e, m in [0.5, 1)
+    e = e < 0 ? 0 : (e > 126 ? 126 : e);
+    return __int_as_float((127 - e) << 23);            // 2^-e
+}
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -26,10 +26,13 @@ struct TsseLaunch {
     int attention;             // 0: norm only (fullsubnet.Model), 1 + FSN_ATTN_*: norm + that channel attention
     float* out;                // [nbranch, B, F, P]
     float* scale;              // [nbranch, B, F] per-row scale handed from the statistics kernel to the apply kernel
+    float* amax;               // optional [nbranch, B]: max |out| of the (sample, branch) -- the fp16 store scale of the first TCN block (fp16_store_scale)
+    float* rows;               // [nbranch, B, F, 35] row statistics handed from tsse_rowstats_kernel to the gate kernel (tsse_row_floats())
     int prenorm;               // 1: input is already normalised (input_norm_kernel), skip the utterance-mean division
     int sub;                   // subband_num (ECA, mag branch only): channels are groups of `sub` reflect-padded bins (fullsubnet_plus.py:146-153)
     float* out_tm; int Cp;     // optional time-major copy [(branch, b, t), Cp] for the tcgen05 TCN (pad columns stay zero)
 };
+inline size_t tsse_row_floats() { return 3 + 2 * 16; }
 void launch_tsse_norm(const TsseLaunch& a, cudaStream_t s);
 // norm types other than offline_laplace_norm (reference base_model.py:227-316): y[nbranch, B, F, Tp] = norm(pad(x))
 struct NormLaunch { const float* x[3]; float* y; int nbranch, B, F, T, Tp, type; };
@@ -199,7 +202,9 @@ struct GemmTc5Launch {
     double* stats_out;                         // [Z, 2]
     const double* stats_in; double count_in;
     float* Y; int ldY;                         // GLN_RES: new residual stream (fp32)
-    __half* Y16;                               // PRELU_STATS: the hidden activation, fp16 [rows, ldY]
+    __half* Y16;                               // PRELU_STATS: the hidden activation, fp16 [rows, ldY], stored times fp16_store_scale(amax_in[z])
+    const float* amax_in;                      // PRELU_STATS: [Z] max |x| of the block's input stream per sample
+    float* amax_out;                           // GLN_RES: [Z] max |x| of the new stream per sample (atomicMax on the bit pattern; zeroed by the caller)
     const float* Xold; float* Xrelu;           // GLN_RES: residual input, optional relu'd copy
     float* out; int F, P, act;                 // OUT: [Z, F, P] (frequency-major) ...
     float* out_tm;                             // ... or, when set, time-major [(branch, b, t), ldY] (read by the LSTM's x-tile builders)
@@ -211,6 +216,7 @@ struct DwTmLaunch {
     int Z, B, C, Tp, dilation;
     int causal;                                // 1: taps t-2d, t-d, t (TCNBlock(causal=True)); 0: t-d, t, t+d
     const double* stats_in; double* stats_out;
+    const float* amax;                         // [Z]: X holds the activation times fp16_store_scale(amax[z]); the statistics are unscaled
     const float* gamma[3]; const float* beta[3]; const float* w[3]; const float* b[3]; const float* prelu[3];
 };
 int launch_dwconv_tm(const DwTmLaunch& a, cudaStream_t s);

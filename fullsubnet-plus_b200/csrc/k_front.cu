@@ -15,9 +15,46 @@ namespace fsn {
 // conv(no padding) -> average pool is linear, so each pooled feature is
 //   b_k[c] + sum_j w_k[c,j] * mean_t x[c, j : T'-k+1+j]
 // i.e. 18 windowed means per channel, all derived from the row sum and the first / last 15 samples.
-// One CTA per (sample, branch); two passes over the [F, T] input (second pass hits L2).
+// Three kernels: row statistics over the whole GPU (one warp per (sample, branch, bin) row: the only pass that is bound by reading the
+// input), the gate per (sample, branch) from those 35 numbers per row, and the scaling pass (tsse_apply_kernel; its read hits L2).
 // =============================================================================================
 constexpr int TSSE_KMAX = 16;
+constexpr int TSSE_ROWW = 3 + 2 * TSSE_KMAX;         // per row: sum, max, min, KMAX exclusive prefix sums, KMAX exclusive suffix sums
+
+__global__ void __launch_bounds__(256) tsse_rowstats_kernel(TsseLaunch a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int F = a.F, T = a.T, Tp = a.Tp;
+    const int r = blockIdx.x * 8 + warp;                          // (branch, sample, bin)
+    if (r >= a.nbranch * a.B * F) return;
+    const int z = r / F, f = r % F, br = z / a.B, b = z % a.B;
+    const float* row = a.x[br] + ((size_t)b * F + f) * T;
+    float acc = 0.f, mx = -INFINITY, mn = INFINITY;
+    for (int t0 = 0; t0 < T; t0 += 256) {                         // eight independent loads per lane in flight
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int t = t0 + u * 32 + lane; v[u] = (t < T) ? __ldg(row + t) : 0.f; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (t0 + u * 32 + lane < T) { acc += v[u]; mx = fmaxf(mx, v[u]); mn = fminf(mn, v[u]); }
+    }
+    acc = warp_sum(acc);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
+    // exclusive prefix sums over the first / last KMAX samples of the padded row: lane j holds sample j (head) and
+    // sample Tp-1-j (tail; t >= T is the zero look-ahead pad), one shuffle scan each
+    float hv = (lane < TSSE_KMAX && lane < T) ? row[lane] : 0.f;
+    const int tt = Tp - 1 - lane;
+    float tv = (lane < TSSE_KMAX && tt >= 0 && tt < T) ? row[tt] : 0.f;
+    float hs = hv, ts = tv;
+#pragma unroll
+    for (int o = 1; o < TSSE_KMAX; o <<= 1) {
+        const float uh = __shfl_up_sync(0xffffffffu, hs, o), ut = __shfl_up_sync(0xffffffffu, ts, o);
+        if (lane >= o) { hs += uh; ts += ut; }
+    }
+    float* out = a.rows + (size_t)r * TSSE_ROWW;
+    if (lane == 0) { out[0] = acc; out[1] = mx; out[2] = mn; }
+    if (lane < TSSE_KMAX) { out[3 + lane] = hs - hv; out[3 + TSSE_KMAX + lane] = ts - tv; }
+}
 
 __global__ void __launch_bounds__(1024) tsse_norm_kernel(TsseLaunch a) {
     extern __shared__ float sm[];
@@ -33,37 +70,18 @@ __global__ void __launch_bounds__(1024) tsse_norm_kernel(TsseLaunch a) {
     float* Mn = Mx + F;
     __shared__ float s_inv;
 
-    const float* x = a.x[br] + (size_t)b * F * T;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-
-    for (int f = warp; f < F; f += nwarp) {
-        const float* row = x + (size_t)f * T;
-        float acc = 0.f, mx = -INFINITY, mn = INFINITY;
-        // 32 warps per CTA and eight independent loads per lane in flight: the pass is a pure read of the sample (HBM-bound)
-        for (int t0 = 0; t0 < T; t0 += 256) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { const int t = t0 + u * 32 + lane; v[u] = (t < T) ? __ldg(row + t) : 0.f; }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (t0 + u * 32 + lane < T) { acc += v[u]; mx = fmaxf(mx, v[u]); mn = fminf(mn, v[u]); }
+    {
+        const float* rows = a.rows + ((size_t)br * a.B + b) * F * TSSE_ROWW;
+        for (int e = threadIdx.x; e < F * TSSE_ROWW; e += blockDim.x) {
+            const int f = e / TSSE_ROWW, j = e % TSSE_ROWW;
+            const float v = rows[e];
+            if (j == 0) S[f] = v;
+            else if (j == 1) Mx[f] = v;
+            else if (j == 2) Mn[f] = v;
+            else if (j < 3 + TSSE_KMAX) Pfx[f * TSSE_KMAX + j - 3] = v;
+            else Sfx[f * TSSE_KMAX + j - 3 - TSSE_KMAX] = v;
         }
-        acc = warp_sum(acc);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
-        if (lane == 0) { S[f] = acc; Mx[f] = mx; Mn[f] = mn; }
-        // exclusive prefix sums over the first / last KMAX samples of the padded row: lane j holds sample j (head) and
-        // sample Tp-1-j (tail; t >= T is the zero look-ahead pad), one shuffle scan each
-        float hv = (lane < TSSE_KMAX && lane < T) ? row[lane] : 0.f;
-        const int tt = Tp - 1 - lane;
-        float tv = (lane < TSSE_KMAX && tt >= 0 && tt < T) ? row[tt] : 0.f;
-        float hs = hv, ts = tv;
-#pragma unroll
-        for (int o = 1; o < TSSE_KMAX; o <<= 1) {
-            const float uh = __shfl_up_sync(0xffffffffu, hs, o), ut = __shfl_up_sync(0xffffffffu, ts, o);
-            if (lane >= o) { hs += uh; ts += ut; }
-        }
-        if (lane < TSSE_KMAX) { Pfx[f * TSSE_KMAX + lane] = hs - hv; Sfx[f * TSSE_KMAX + lane] = ts - tv; }
     }
     __syncthreads();
     if (warp == 0) {
@@ -131,31 +149,65 @@ __global__ void __launch_bounds__(1024) tsse_norm_kernel(TsseLaunch a) {
                 gate[c] = 1.0f / (1.0f + __expf(-y));
             }
         } else {
+            // two small dense layers (F -> F/2 -> F): four output rows per warp at a time so that 4 x ceil(F/32) independent weight loads are
+            // in flight per lane (with one row per warp and 8 warps this phase was 50 dependent L2 round trips = 55 us of the 69 us kernel)
             const int Cr = F / 2;
-            for (int o = warp; o < Cr; o += nwarp) {
-                float acc = 0.f, acm = 0.f;
+            for (int o0 = warp * 4; o0 < Cr; o0 += nwarp * 4) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f}, acm[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int c = lane; c < F; c += 32) {
-                    const float w = p.fc1_w[(size_t)o * F + c];
-                    acc = fmaf(w, sq[c], acc);
-                    acm = fmaf(w, Mx[c], acm);
+                    const float sv = sq[c], mv = Mx[c];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float w = (o0 + j < Cr) ? __ldg(p.fc1_w + (size_t)(o0 + j) * F + c) : 0.f;
+                        acc[j] = fmaf(w, sv, acc[j]);
+                        acm[j] = fmaf(w, mv, acm[j]);
+                    }
                 }
-                acc = warp_sum(acc);
-                float v = fmaxf(acc + p.fc1_b[o], 0.f);
-                if (kind == FSN_ATTN_CBAM) { acm = warp_sum(acm); v += fmaxf(acm + p.fc1_b[o], 0.f); }   // shared fc1 on both squeezes (:324-329)
-                if (lane == 0) f1[o] = v;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a1 = warp_sum(acc[j]);
+                    float v = 0.f;
+                    if (o0 + j < Cr) v = fmaxf(a1 + p.fc1_b[o0 + j], 0.f);
+                    if (kind == FSN_ATTN_CBAM) { const float a2 = warp_sum(acm[j]); if (o0 + j < Cr) v += fmaxf(a2 + p.fc1_b[o0 + j], 0.f); }   // shared fc1 on both squeezes (:324-329)
+                    if (lane == 0 && o0 + j < Cr) f1[o0 + j] = v;
+                }
             }
             __syncthreads();
-            for (int o = warp; o < F; o += nwarp) {
-                float acc = 0.f;
-                for (int c = lane; c < Cr; c += 32) acc = fmaf(p.fc2_w[(size_t)o * Cr + c], f1[c], acc);
-                acc = warp_sum(acc);
-                if (lane == 0) gate[o] = 1.0f / (1.0f + __expf(-(acc + p.fc2_b[o])));
+            for (int o0 = warp * 4; o0 < F; o0 += nwarp * 4) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int c = lane; c < Cr; c += 32) {
+                    const float fv = f1[c];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j] = fmaf((o0 + j < F) ? __ldg(p.fc2_w + (size_t)(o0 + j) * Cr + c) : 0.f, fv, acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a1 = warp_sum(acc[j]);
+                    if (lane == 0 && o0 + j < F) gate[o0 + j] = 1.0f / (1.0f + __expf(-(a1 + p.fc2_b[o0 + j])));
+                }
             }
         }
         __syncthreads();
     }
     // per-row scale (gate * 1/(mean + 1e-5)); the bulk multiply + time-major transpose runs in tsse_apply_kernel on the whole GPU
-    for (int f = threadIdx.x; f < F; f += blockDim.x) a.scale[((size_t)br * a.B + b) * F + f] = a.attention ? gate[f] * inv : inv;
+    float amax = 0.f;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const float sc = a.attention ? gate[f] * inv : inv;
+        a.scale[((size_t)br * a.B + b) * F + f] = sc;
+        const float* rw = a.rows + (((size_t)br * a.B + b) * F + f) * TSSE_ROWW;       // row max / min (Mx / Mn may hold the CBAM squeeze by now)
+        amax = fmaxf(amax, fmaxf(fabsf(rw[1]), fabsf(rw[2])) * fabsf(sc));
+    }
+    if (a.amax) {                                                                      // max |x0| of this (sample, branch): scale of the fp16 hidden activation
+        __shared__ float s_amax[32];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (lane == 0) s_amax[warp] = amax;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < nwarp; ++i) amax = fmaxf(amax, s_amax[i]);
+            a.amax[(size_t)br * a.B + b] = amax;
+        }
+    }
 }
 
 // out[z][f][t] = x[z][f][t] * scale[z][f] (zero in the look-ahead pad) in both layouts; one CTA per 32 x 32 tile.
@@ -187,6 +239,7 @@ __global__ void __launch_bounds__(256) tsse_apply_kernel(TsseLaunch a) {
 void launch_tsse_norm(const TsseLaunch& a, cudaStream_t s) {
     size_t smem = sizeof(float) * ((size_t)a.F * (5 + 2 * TSSE_KMAX) + a.F / 2 + 8);
     cudaFuncSetAttribute(tsse_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tsse_rowstats_kernel<<<(a.nbranch * a.B * a.F + 7) / 8, 256, 0, s>>>(a);
     tsse_norm_kernel<<<dim3(a.B, a.nbranch), 1024, smem, s>>>(a);
     tsse_apply_kernel<<<dim3((a.P + 31) / 32, (a.F + 31) / 32, a.B * a.nbranch), 256, 0, s>>>(a);
 }
@@ -395,15 +448,34 @@ __global__ void __launch_bounds__(256) sb_stats_kernel(SbPackLaunch a) {
 }
 
 // Same sums for full-band outputs stored TIME-major (fb_st > 1: element (b, f, t) at fb[q] + b fb_sb + f fb_sf + t fb_st with
-// fb_sf == 1): one CTA per (sample, source), threads over bins, every thread walks the frames -> coalesced rows.
-__global__ void __launch_bounds__(256) sb_colsum_kernel(SbPackLaunch a) {
+// fb_sf == 1): one CTA per (sample, source); threadIdx.x walks the bins (coalesced rows), threadIdx.y splits the frames into
+// blockDim.y interleaved slices, eight independent loads per thread in flight; the slices are added in a fixed order (deterministic).
+__global__ void __launch_bounds__(1024) sb_colsum_kernel(SbPackLaunch a) {
+    extern __shared__ float part[];                              // [blockDim.y][blockDim.x][2]
     const int b = blockIdx.x, q = blockIdx.y, F = a.F, Tp = a.Tp, nsrc = 1 + a.nfb;
+    const int ny = blockDim.y, ty = threadIdx.y;
     const float* base = ((q == 0) ? a.fb[0] : (q == 1) ? a.fb[1] : a.fb[2]) + (size_t)b * a.fb_sb;
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    for (int f0 = 0; f0 < F; f0 += blockDim.x) {
+        const int f = f0 + threadIdx.x;
         float acc = 0.f, acq = 0.f;
-        for (int t = 0; t < Tp; ++t) { const float v = base[(size_t)t * a.fb_st + f]; acc += v; acq = fmaf(v, v, acq); }
-        const size_t r = ((size_t)b * nsrc + 1 + q) * F + f;
-        a.rowsum[2 * r] = acc; a.rowsum[2 * r + 1] = acq;
+        if (f < F) {
+            for (int t0 = ty; t0 < Tp; t0 += 8 * ny) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int t = t0 + u * ny; v[u] = (t < Tp) ? __ldg(base + (size_t)t * a.fb_st + f) : 0.f; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { acc += v[u]; acq = fmaf(v[u], v[u], acq); }
+            }
+        }
+        part[(ty * blockDim.x + threadIdx.x) * 2] = acc;
+        part[(ty * blockDim.x + threadIdx.x) * 2 + 1] = acq;
+        __syncthreads();
+        if (ty == 0 && f < F) {
+            for (int y = 1; y < ny; ++y) { acc += part[(y * blockDim.x + threadIdx.x) * 2]; acq += part[(y * blockDim.x + threadIdx.x) * 2 + 1]; }
+            const size_t r = ((size_t)b * nsrc + 1 + q) * F + f;
+            a.rowsum[2 * r] = acc; a.rowsum[2 * r + 1] = acq;
+        }
+        __syncthreads();
     }
 }
 
@@ -412,7 +484,8 @@ void launch_sb_stats(const SbPackLaunch& a, cudaStream_t s) {
         SbPackLaunch w = a;
         w.nfb = 0;                                               // rows of the window source only ...
         sb_rowsum_strided_kernel<<<(a.B * a.F + 7) / 8, 256, 0, s>>>(w, 1 + a.nfb);
-        sb_colsum_kernel<<<dim3(a.B, a.nfb), 256, 0, s>>>(a);    // ... the full-band outputs by columns
+        const int bx = (a.F + 31) / 32 * 32 < 512 ? (a.F + 31) / 32 * 32 : 512, by = 1024 / bx;
+        sb_colsum_kernel<<<dim3(a.B, a.nfb), dim3(bx, by), (size_t)bx * by * 2 * sizeof(float), s>>>(a);    // ... the full-band outputs by columns
     } else {
         sb_rowsum_kernel<<<(a.B * (1 + a.nfb) * a.F + 7) / 8, 256, 0, s>>>(a);
     }

@@ -47,13 +47,53 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 }
 __device__ __forceinline__ float round_tf32(float x) { return __uint_as_float(f2tf32(x)); }
 
+// ---- coalesced epilogue I/O --------------------------------------------------------------------------------------------------
+// tcgen05.ld hands every epilogue thread ONE ROW of the tile (32x32b shape), so a direct global store touches 32 different 128-byte
+// lines per instruction with 16 bytes each: the L1 tag stage (one line per cycle) -- not HBM -- bounded these kernels (ncu, round 2:
+// 2.6 M store + 2.8 M load sector accesses in the second convolution = 20 us of its 48).  Each warp therefore owns a 2 KB staging tile
+// (32 rows x 64 bytes, 16-byte units XOR-swizzled): rows go in thread-per-row, come out with lane l <-> (row (l >> 2) + 8 i, unit l & 3),
+// i.e. 8 rows x 64 contiguous bytes per instruction (both views are bank-conflict free), and the same in reverse for the residual.
+constexpr int G5_STG_BYTES = 32 * 64;
+__device__ __forceinline__ uint4* g5_stg(uint8_t* t, int row, int unit) {
+    return reinterpret_cast<uint4*>(t + row * 64 + ((unit ^ ((row >> 1) & 3)) << 4));
+}
+// every lane holds the 64 bytes of its row; row r of the warp lives at gbase + r * pitch (bytes); rows >= nvalid are not written
+__device__ __forceinline__ void g5_store_rows64(uint8_t* t, int lane, const uint4 (&v)[4], uint8_t* gbase, size_t pitch, int nvalid) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *g5_stg(t, lane, q) = v[q];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = (lane >> 2) + 8 * i;
+        const uint4 u = *g5_stg(t, row, lane & 3);
+        if (row < nvalid) *reinterpret_cast<uint4*>(gbase + (size_t)row * pitch + (lane & 3) * 16) = u;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void g5_load_rows64_issue(int lane, const uint8_t* gbase, size_t pitch, int nvalid, uint4 (&g)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = (lane >> 2) + 8 * i;
+        g[i] = (row < nvalid) ? *reinterpret_cast<const uint4*>(gbase + (size_t)row * pitch + (lane & 3) * 16) : make_uint4(0, 0, 0, 0);
+    }
+}
+__device__ __forceinline__ void g5_load_rows64_commit(uint8_t* t, int lane, const uint4 (&g)[4], uint4 (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *g5_stg(t, (lane >> 2) + 8 * i, lane & 3) = g[i];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = *g5_stg(t, lane, q);
+    __syncwarp();
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(G5_THREADS, 1)
 gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmTc5Launch a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int NT = a.NT, nstage = a.nstage, stage_bytes = G5_A_BYTES + NT * 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)nstage * stage_bytes);
+    uint8_t* stg_all = smem + (size_t)nstage * stage_bytes;                  // [G5_EPI_WARPS][G5_STG_BYTES] epilogue staging tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + G5_EPI_WARPS * G5_STG_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = full + nstage;
     uint64_t* accfull = empty + nstage;
@@ -146,95 +186,126 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 rstd = (float)(1.0 / sqrt((var > 0 ? var : 0) + 1e-8));
             }
             const float slope = (EPI == EPI5_PRELU_STATS) ? __ldg(a.prelu[br]) : 0.f;
+            // fp16 store scale of the hidden activation: a power of two from the absolute maximum of this sample's input stream (the
+            // normalised real / imaginary branches reach 1e5 and beyond -- 1 / mean(real) is unbounded); undone exactly by the gLN that follows
+            const float ysc = (EPI == EPI5_PRELU_STATS && valid) ? fp16_store_scale(__ldg(a.amax_in + z)) : 1.f;
+            float rowmax = 0.f;
             const float* bias = a.bias[br];
             const float* s1 = a.s1[br];
             double lsum = 0.0, lsq = 0.0;
             mbar_wait(&accfull[buf], use[buf] & 1);
             ++use[buf];
             tc5_fence_after();
-            float4 xpre[4];
-            if (EPI == EPI5_GLN_RES && valid && cbeg < cend) {
-                const float4* xo = reinterpret_cast<const float4*>(a.Xold + grow * a.ldY + n0 + cbeg * 16);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) xpre[i] = xo[i];
-            }
-            for (int c = cbeg; c < cend; ++c) {
-                uint32_t v[16];
-                tmem_ld16(tl + buf * 256 + c * 16, v);
-                tmem_wait_ld();
-                const int n = n0 + c * 16;
-                float y[16];
-                if (EPI == EPI5_PRELU_STATS) {
+            // coalesced I/O of this warp's 32 rows (see g5_store_rows64): row 0 of the warp, rows valid, staging tile
+            uint8_t* stg = stg_all + (warp - 2) * G5_STG_BYTES;
+            const size_t wrow0 = (size_t)br * a.rows_per_branch + (size_t)mt * 128 + q * 32;
+            int nvalid = a.rows_per_branch - (mt * 128 + q * 32);
+            nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
+            if (EPI == EPI5_PRELU_STATS) {
+                // two 16-column chunks per pass: 32 fp16 values = 64 bytes per row
+                const size_t pitch = (size_t)a.ldY * sizeof(__half);
+                for (int c = cbeg; c < cend; c += 2) {
+                    uint32_t v[32];
+                    tmem_ld16(tl + buf * 256 + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                    tmem_ld16(tl + buf * 256 + c * 16 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                    tmem_wait_ld();
+                    const int n = n0 + c * 16;
                     float ls = 0.f, lq = 0.f;
-                    float bvec[16];
+                    uint32_t hp[16];
 #pragma unroll
-                    for (int i4 = 0; i4 < 4; ++i4) {
+                    for (int i4 = 0; i4 < 8; ++i4) {
                         const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n) + i4);
-                        bvec[4 * i4] = b4.x; bvec[4 * i4 + 1] = b4.y; bvec[4 * i4 + 2] = b4.z; bvec[4 * i4 + 3] = b4.w;
-                    }
+                        const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+                        float y[4];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float t = __uint_as_float(v[i]) + bvec[i];
-                        t = (t >= 0.f) ? t : slope * t;
-                        ls += t; lq = fmaf(t, t, lq);
-                        y[i] = fminf(fmaxf(t, -65504.f), 65504.f);
+                        for (int e = 0; e < 4; ++e) {
+                            float t = __uint_as_float(v[4 * i4 + e]) + bv[e];
+                            t = (t >= 0.f) ? t : slope * t;
+                            ls += t; lq = fmaf(t, t, lq);
+                            y[e] = fminf(fmaxf(t * ysc, -65504.f), 65504.f);
+                        }
+                        hp[2 * i4] = pack_half2(y[0], y[1]);
+                        hp[2 * i4 + 1] = pack_half2(y[2], y[3]);
                     }
                     lsum += (double)ls; lsq += (double)lq;
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(a.Y16 + grow * a.ldY + n);
-                        dst[0] = make_uint4(pack_half2(y[0], y[1]), pack_half2(y[2], y[3]), pack_half2(y[4], y[5]), pack_half2(y[6], y[7]));
-                        dst[1] = make_uint4(pack_half2(y[8], y[9]), pack_half2(y[10], y[11]), pack_half2(y[12], y[13]), pack_half2(y[14], y[15]));
-                    }
-                } else if (EPI == EPI5_GLN_RES) {
-                    if (valid) {
-                        float4 xcur[4] = {xpre[0], xpre[1], xpre[2], xpre[3]};
-                        if (c + 1 < cend) {                     // residual of the next chunk: in flight during this chunk's math
-                            const float4* xn = reinterpret_cast<const float4*>(a.Xold + grow * a.ldY + n + 16);
+                    const uint4 ov[4] = {make_uint4(hp[0], hp[1], hp[2], hp[3]), make_uint4(hp[4], hp[5], hp[6], hp[7]),
+                                         make_uint4(hp[8], hp[9], hp[10], hp[11]), make_uint4(hp[12], hp[13], hp[14], hp[15])};
+                    g5_store_rows64(stg, lane, ov, reinterpret_cast<uint8_t*>(a.Y16 + wrow0 * a.ldY + n), pitch, nvalid);
+                }
+            } else if (EPI == EPI5_GLN_RES) {
+                const size_t pitch = (size_t)a.ldY * sizeof(float);
+                const uint8_t* xbase = reinterpret_cast<const uint8_t*>(a.Xold + wrow0 * a.ldY + n0);
+                uint4 gnx[4], xcur[4];
+                if (cbeg < cend) {
+                    g5_load_rows64_issue(lane, xbase + (size_t)cbeg * 64, pitch, nvalid, gnx);
+                    g5_load_rows64_commit(stg, lane, gnx, xcur);
+                }
+                for (int c = cbeg; c < cend; ++c) {
+                    if (c + 1 < cend) g5_load_rows64_issue(lane, xbase + (size_t)(c + 1) * 64, pitch, nvalid, gnx);   // residual of the next chunk: in flight during this chunk's math
+                    uint32_t v[16];
+                    tmem_ld16(tl + buf * 256 + c * 16, v);
+                    tmem_wait_ld();
+                    const int n = n0 + c * 16;
+                    uint4 ov[4], orl[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) xpre[i] = xn[i];
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const float xa[4] = {__uint_as_float(xcur[i4].x), __uint_as_float(xcur[i4].y), __uint_as_float(xcur[i4].z), __uint_as_float(xcur[i4].w)};
+                        const float4 s14 = __ldg(reinterpret_cast<const float4*>(s1 + n) + i4), b4 = __ldg(reinterpret_cast<const float4*>(bias + n) + i4);
+                        const float s1v[4] = {s14.x, s14.y, s14.z, s14.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float val = fmaf(rstd, __uint_as_float(v[i4 * 4 + e]), fmaf(-mean * rstd, s1v[e], bv[e]));
+                            o[e] = xa[e] + val;
+                            if (valid) rowmax = fmaxf(rowmax, fabsf(o[e]));
                         }
-                        float4* dst = reinterpret_cast<float4*>(a.Y + grow * a.ldY + n);
-                        float4* dr = a.Xrelu ? reinterpret_cast<float4*>(a.Xrelu + grow * a.ldY + n) : nullptr;
-#pragma unroll
-                        for (int i4 = 0; i4 < 4; ++i4) {
-                            const float4 xv = xcur[i4];
-                            const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
-                            const float4 s14 = __ldg(reinterpret_cast<const float4*>(s1 + n) + i4), b4 = __ldg(reinterpret_cast<const float4*>(bias + n) + i4);
-                            const float s1v[4] = {s14.x, s14.y, s14.z, s14.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
-                            float o[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int i = i4 * 4 + e;
-                                const float val = fmaf(rstd, __uint_as_float(v[i]), fmaf(-mean * rstd, s1v[e], bv[e]));
-                                o[e] = xa[e] + val;
-                            }
-                            dst[i4] = make_float4(o[0], o[1], o[2], o[3]);
-                            if (dr) dr[i4] = make_float4(fmaxf(o[0], 0.f), fmaxf(o[1], 0.f), fmaxf(o[2], 0.f), fmaxf(o[3], 0.f));
-                        }
+                        ov[i4] = make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
+                        orl[i4] = make_uint4(__float_as_uint(fmaxf(o[0], 0.f)), __float_as_uint(fmaxf(o[1], 0.f)), __float_as_uint(fmaxf(o[2], 0.f)),
+                                             __float_as_uint(fmaxf(o[3], 0.f)));
                     }
-                } else if (a.out_tm) {
-                    // time-major output [(branch, b, t), Npad]: the layout the sub-band LSTM's x-tile builders read (k_lstm_tc5d.cu);
-                    // each thread owns a row -> 64 contiguous bytes per chunk (pad columns: zero weights, zero bias)
-                    if (valid) {
-                        float4* dst = reinterpret_cast<float4*>(a.out_tm + grow * a.ldY + n);
+                    g5_store_rows64(stg, lane, ov, reinterpret_cast<uint8_t*>(a.Y + wrow0 * a.ldY + n), pitch, nvalid);
+                    if (a.Xrelu) g5_store_rows64(stg, lane, orl, reinterpret_cast<uint8_t*>(a.Xrelu + wrow0 * a.ldY + n), pitch, nvalid);
+                    if (c + 1 < cend) g5_load_rows64_commit(stg, lane, gnx, xcur);
+                }
+            } else {
+                for (int c = cbeg; c < cend; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(tl + buf * 256 + c * 16, v);
+                    tmem_wait_ld();
+                    const int n = n0 + c * 16;
+                    if (a.out_tm) {
+                        // time-major output [(branch, b, t), Npad]: the layout the sub-band LSTM's x-tile builders read (k_lstm_tc5d.cu)
+                        // (pad columns: zero weights, zero bias)
+                        uint4 ov[4];
 #pragma unroll
                         for (int i4 = 0; i4 < 4; ++i4) {
                             const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n) + i4);
-                            dst[i4] = make_float4(apply_act(__uint_as_float(v[4 * i4]) + b4.x, a.act), apply_act(__uint_as_float(v[4 * i4 + 1]) + b4.y, a.act),
-                                                  apply_act(__uint_as_float(v[4 * i4 + 2]) + b4.z, a.act), apply_act(__uint_as_float(v[4 * i4 + 3]) + b4.w, a.act));
+                            ov[i4] = make_uint4(__float_as_uint(apply_act(__uint_as_float(v[4 * i4]) + b4.x, a.act)), __float_as_uint(apply_act(__uint_as_float(v[4 * i4 + 1]) + b4.y, a.act)),
+                                                __float_as_uint(apply_act(__uint_as_float(v[4 * i4 + 2]) + b4.z, a.act)), __float_as_uint(apply_act(__uint_as_float(v[4 * i4 + 3]) + b4.w, a.act)));
                         }
-                    }
-                } else {
+                        g5_store_rows64(stg, lane, ov, reinterpret_cast<uint8_t*>(a.out_tm + wrow0 * a.ldY + n), (size_t)a.ldY * sizeof(float), nvalid);
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (valid && n + i < a.F)
-                            a.out[((size_t)z * a.F + n + i) * a.P + tt] = apply_act(__uint_as_float(v[i]) + __ldg(bias + n + i), a.act);
+                        for (int i = 0; i < 16; ++i) {
+                            if (valid && n + i < a.F)
+                                a.out[((size_t)z * a.F + n + i) * a.P + tt] = apply_act(__uint_as_float(v[i]) + __ldg(bias + n + i), a.act);
+                        }
                     }
                 }
             }
             tc5_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&accempty[buf]);
+            if (EPI == EPI5_GLN_RES && a.amax_out) {      // max |x| of the new stream per sample (max is order-independent: deterministic)
+                const int key = valid ? z : -1;
+                if (__match_any_sync(0xffffffffu, key) == 0xffffffffu) {
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) rowmax = fmaxf(rowmax, __shfl_xor_sync(0xffffffffu, rowmax, o));
+                    if (lane == 0 && valid) atomicMax(reinterpret_cast<int*>(a.amax_out + z), __float_as_int(rowmax));
+                } else if (valid) {
+                    atomicMax(reinterpret_cast<int*>(a.amax_out + z), __float_as_int(rowmax));
+                }
+            }
             if (EPI == EPI5_PRELU_STATS) {
                 // rows of a warp almost always belong to one sample: reduce in the warp, one atomic pair per warp
                 const int key = valid ? z : -1;
@@ -281,10 +352,11 @@ int make_tmap_f32_2d(void* out_map, const void* base, uint64_t rows, uint64_t co
 
 int launch_gemm_tc5(const void* mapA, const void* mapB, GemmTc5Launch a, int num_sms, cudaStream_t s) {
     const int stage_bytes = G5_A_BYTES + a.NT * 128;
-    a.nstage = (227 * 1024 - 2048) / stage_bytes;
+    a.nstage = (227 * 1024 - 2048 - G5_EPI_WARPS * G5_STG_BYTES) / stage_bytes;
     if (a.nstage > 8) a.nstage = 8;
     if (a.nstage < 2 || a.NT % 16 || a.NT > 256 || a.Kp % (a.epi == EPI5_GLN_RES ? 64 : 32)) return (int)cudaErrorInvalidValue;
-    const size_t smem = (size_t)a.nstage * stage_bytes + 1024 + 256;
+    if (a.epi == EPI5_PRELU_STATS && a.NT % 64) return (int)cudaErrorInvalidValue;     // its epilogue takes 32 columns per pass and warp half
+    const size_t smem = (size_t)a.nstage * stage_bytes + G5_EPI_WARPS * G5_STG_BYTES + 1024 + 256;
     const int total = a.nbranch * a.tiles_m * a.ntiles_n;
     const int grid = total < num_sms ? total : num_sms;
     const CUtensorMap& mA = *reinterpret_cast<const CUtensorMap*>(mapA);
@@ -319,19 +391,29 @@ __global__ void __launch_bounds__(256) dwconv_tm_kernel(DwTmLaunch a) {
     const double var = a.stats_in[2 * z + 1] / cnt - mu * mu;
     const float mean = (float)mu, rstd = (float)(1.0 / sqrt((var > 0 ? var : 0) + 1e-8));
     const float slope = __ldg(a.prelu[g]);
+    const float unscale = 1.0f / fp16_store_scale(__ldg(a.amax + z));     // exact: a power of two
     const size_t base = (size_t)z * Tp * C + c0;
     const int cq = threadIdx.x & 7, tr = threadIdx.x >> 3;            // 8 columns of 8 channels x 32 frame rows per pass
+    // per-channel constants: staged once per CTA (64 channels x 6 values) -- as 48 scalar loads per thread they were 85 % of the kernel's
+    // global load requests (ncu, round 2)
+    __shared__ __align__(16) float cst[6][DW_CH];                     // gamma, beta, w0, w1, w2, bias
+    if (threadIdx.x < DW_CH) {
+        const int ch = c0 + threadIdx.x;
+        cst[0][threadIdx.x] = __ldg(a.gamma[g] + ch);
+        cst[1][threadIdx.x] = __ldg(a.beta[g] + ch);
+        const float* wp = a.w[g] + (size_t)ch * 3;
+        cst[2][threadIdx.x] = __ldg(wp); cst[3][threadIdx.x] = __ldg(wp + 1); cst[4][threadIdx.x] = __ldg(wp + 2);
+        cst[5][threadIdx.x] = __ldg(a.b[g] + ch);
+    }
+    __syncthreads();
     float ga[8], be[8], w0[8], w1[8], w2[8], bb[8];
-    {
-        const int cb = c0 + cq * 8;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            ga[e] = __ldg(a.gamma[g] + cb + e) * rstd;
-            be[e] = __ldg(a.beta[g] + cb + e) - mean * ga[e];
-            const float* wp = a.w[g] + (size_t)(cb + e) * 3;
-            w0[e] = __ldg(wp); w1[e] = __ldg(wp + 1); w2[e] = __ldg(wp + 2);
-            bb[e] = __ldg(a.b[g] + cb + e);
-        }
+    for (int e = 0; e < 8; ++e) {
+        const int ch = cq * 8 + e;
+        const float gr = cst[0][ch] * rstd;
+        ga[e] = gr * unscale;                                  // X holds y * 2^-k: (y - mean) rstd gamma + beta = X (2^k rstd gamma) + (beta - mean rstd gamma)
+        be[e] = cst[1][ch] - mean * gr;
+        w0[e] = cst[2][ch]; w1[e] = cst[3][ch]; w2[e] = cst[4][ch]; bb[e] = cst[5][ch];
     }
     for (int t = lo + tr; t < hi; t += 32) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.X + base + (size_t)t * C + cq * 8));
