@@ -193,14 +193,22 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const float* bias = a.bias[br];
             const float* s1 = a.s1[br];
             double lsum = 0.0, lsq = 0.0;
-            mbar_wait(&accfull[buf], use[buf] & 1);
-            ++use[buf];
-            tc5_fence_after();
             // coalesced I/O of this warp's 32 rows (see g5_store_rows64): row 0 of the warp, rows valid, staging tile
             uint8_t* stg = stg_all + (warp - 2) * G5_STG_BYTES;
             const size_t wrow0 = (size_t)br * a.rows_per_branch + (size_t)mt * 128 + q * 32;
             int nvalid = a.rows_per_branch - (mt * 128 + q * 32);
             nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
+            // GLN_RES: the residual of the first two chunks does not depend on the MMAs -- in flight while this warp waits for the accumulator
+            // (the loads miss to HBM; with one chunk ahead the 4-5 chunks of a warp were a chain of dependent DRAM round trips)
+            uint4 gA[4], gB[4];
+            const uint8_t* xbase = (EPI == EPI5_GLN_RES) ? reinterpret_cast<const uint8_t*>(a.Xold + wrow0 * a.ldY + n0) : nullptr;
+            if (EPI == EPI5_GLN_RES) {
+                if (cbeg < cend) g5_load_rows64_issue(lane, xbase + (size_t)cbeg * 64, (size_t)a.ldY * sizeof(float), nvalid, gA);
+                if (cbeg + 1 < cend) g5_load_rows64_issue(lane, xbase + (size_t)(cbeg + 1) * 64, (size_t)a.ldY * sizeof(float), nvalid, gB);
+            }
+            mbar_wait(&accfull[buf], use[buf] & 1);
+            ++use[buf];
+            tc5_fence_after();
             if (EPI == EPI5_PRELU_STATS) {
                 // two 16-column chunks per pass: 32 fp16 values = 64 bytes per row
                 const size_t pitch = (size_t)a.ldY * sizeof(__half);
@@ -234,14 +242,9 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
             } else if (EPI == EPI5_GLN_RES) {
                 const size_t pitch = (size_t)a.ldY * sizeof(float);
-                const uint8_t* xbase = reinterpret_cast<const uint8_t*>(a.Xold + wrow0 * a.ldY + n0);
-                uint4 gnx[4], xcur[4];
-                if (cbeg < cend) {
-                    g5_load_rows64_issue(lane, xbase + (size_t)cbeg * 64, pitch, nvalid, gnx);
-                    g5_load_rows64_commit(stg, lane, gnx, xcur);
-                }
-                for (int c = cbeg; c < cend; ++c) {
-                    if (c + 1 < cend) g5_load_rows64_issue(lane, xbase + (size_t)(c + 1) * 64, pitch, nvalid, gnx);   // residual of the next chunk: in flight during this chunk's math
+                uint4 xcur[4];
+                if (cbeg < cend) g5_load_rows64_commit(stg, lane, gA, xcur);
+                auto chunk = [&](int c) {
                     uint32_t v[16];
                     tmem_ld16(tl + buf * 256 + c * 16, v);
                     tmem_wait_ld();
@@ -265,7 +268,17 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     }
                     g5_store_rows64(stg, lane, ov, reinterpret_cast<uint8_t*>(a.Y + wrow0 * a.ldY + n), pitch, nvalid);
                     if (a.Xrelu) g5_store_rows64(stg, lane, orl, reinterpret_cast<uint8_t*>(a.Xrelu + wrow0 * a.ldY + n), pitch, nvalid);
-                    if (c + 1 < cend) g5_load_rows64_commit(stg, lane, gnx, xcur);
+                };
+                // chunks in pairs over two register buffers: every residual load is issued two chunk-times before it is needed
+                for (int c = cbeg; c < cend; c += 2) {
+                    if (c + 2 < cend) g5_load_rows64_issue(lane, xbase + (size_t)(c + 2) * 64, pitch, nvalid, gA);
+                    chunk(c);
+                    if (c + 1 < cend) {
+                        g5_load_rows64_commit(stg, lane, gB, xcur);
+                        if (c + 3 < cend) g5_load_rows64_issue(lane, xbase + (size_t)(c + 3) * 64, pitch, nvalid, gB);
+                        chunk(c + 1);
+                        if (c + 2 < cend) g5_load_rows64_commit(stg, lane, gA, xcur);
+                    }
                 }
             } else {
                 for (int c = cbeg; c < cend; ++c) {
@@ -393,9 +406,9 @@ __global__ void __launch_bounds__(256) dwconv_tm_kernel(DwTmLaunch a) {
     const float slope = __ldg(a.prelu[g]);
     const float unscale = 1.0f / fp16_store_scale(__ldg(a.amax + z));     // exact: a power of two
     const size_t base = (size_t)z * Tp * C + c0;
-    const int cq = threadIdx.x & 7, tr = threadIdx.x >> 3;            // 8 columns of 8 channels x 32 frame rows per pass
-    // per-channel constants: staged once per CTA (64 channels x 6 values) -- as 48 scalar loads per thread they were 85 % of the kernel's
-    // global load requests (ncu, round 2)
+    const int cq = threadIdx.x & 15, tr = threadIdx.x >> 4;           // 16 columns of 4 channels x 16 frame rows per pass
+    // per-channel constants: staged once per CTA (64 channels x 6 values) -- as scalar loads per thread they were 85 % of the kernel's
+    // global load requests (ncu, round 2).  Four channels per thread keep the kernel at 4 CTAs per SM (48 registers).
     __shared__ __align__(16) float cst[6][DW_CH];                     // gamma, beta, w0, w1, w2, bias
     if (threadIdx.x < DW_CH) {
         const int ch = c0 + threadIdx.x;
@@ -406,50 +419,40 @@ __global__ void __launch_bounds__(256) dwconv_tm_kernel(DwTmLaunch a) {
         cst[5][threadIdx.x] = __ldg(a.b[g] + ch);
     }
     __syncthreads();
-    float ga[8], be[8], w0[8], w1[8], w2[8], bb[8];
+    float ga[4], be[4], w0[4], w1[4], w2[4], bb[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int ch = cq * 8 + e;
+    for (int e = 0; e < 4; ++e) {
+        const int ch = cq * 4 + e;
         const float gr = cst[0][ch] * rstd;
         ga[e] = gr * unscale;                                  // X holds y * 2^-k: (y - mean) rstd gamma + beta = X (2^k rstd gamma) + (beta - mean rstd gamma)
         be[e] = cst[1][ch] - mean * gr;
         w0[e] = cst[2][ch]; w1[e] = cst[3][ch]; w2[e] = cst[4][ch]; bb[e] = cst[5][ch];
     }
-    for (int t = lo + tr; t < hi; t += 32) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.X + base + (size_t)t * C + cq * 8));
-        const __half2* h = reinterpret_cast<const __half2*>(&v);
-        float4* dst = reinterpret_cast<float4*>(slab + (size_t)(t - lo) * DW_CH + cq * 4);   // channels 8cq..8cq+3 | (+32 floats) 8cq+4..8cq+7: conflict-free
-        const float2 p0 = __half22float2(h[0]), p1 = __half22float2(h[1]), p2 = __half22float2(h[2]), p3 = __half22float2(h[3]);
-        dst[0] = make_float4(fmaf(p0.x, ga[0], be[0]), fmaf(p0.y, ga[1], be[1]), fmaf(p1.x, ga[2], be[2]), fmaf(p1.y, ga[3], be[3]));
-        dst[8] = make_float4(fmaf(p2.x, ga[4], be[4]), fmaf(p2.y, ga[5], be[5]), fmaf(p3.x, ga[6], be[6]), fmaf(p3.y, ga[7], be[7]));
+    for (int t = lo + tr; t < hi; t += 16) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(a.X + base + (size_t)t * C + cq * 4));
+        const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), p1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+        *reinterpret_cast<float4*>(slab + (size_t)(t - lo) * DW_CH + cq * 4) =
+            make_float4(fmaf(p0.x, ga[0], be[0]), fmaf(p0.y, ga[1], be[1]), fmaf(p1.x, ga[2], be[2]), fmaf(p1.y, ga[3], be[3]));
     }
     __syncthreads();
     float ls = 0.f, lq = 0.f;
-    for (int t = t0 + tr; t < t1; t += 32) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = t0 + tr; t < t1; t += 16) {
         // taps (w0, w1, w2): non-causal (t-d, t, t+d); causal (t-2d, t-d, t) -- padding 2d + chomp, causal_conv.py:74-75,104-105
         const int tl = a.causal ? t - 2 * d : t - d, tm = a.causal ? t - d : t, tr2 = a.causal ? t : t + d;
-        float l[8], m[8], r[8];
-        auto tap = [&](int tt, float (&o)[8]) {
-            if (tt >= 0 && tt < Tp) {
-                const float4* src = reinterpret_cast<const float4*>(slab + (size_t)(tt - lo) * DW_CH + cq * 4);
-                const float4 x0 = src[0], x1 = src[8];
-                o[0] = x0.x; o[1] = x0.y; o[2] = x0.z; o[3] = x0.w; o[4] = x1.x; o[5] = x1.y; o[6] = x1.z; o[7] = x1.w;
-            } else {
+        const float4 m = (tm >= 0) ? *reinterpret_cast<const float4*>(slab + (size_t)(tm - lo) * DW_CH + cq * 4) : zero;
+        const float4 l = (tl >= 0) ? *reinterpret_cast<const float4*>(slab + (size_t)(tl - lo) * DW_CH + cq * 4) : zero;
+        const float4 r = (tr2 < Tp) ? *reinterpret_cast<const float4*>(slab + (size_t)(tr2 - lo) * DW_CH + cq * 4) : zero;
+        const float lv[4] = {l.x, l.y, l.z, l.w}, mv[4] = {m.x, m.y, m.z, m.w}, rv[4] = {r.x, r.y, r.z, r.w};
+        float o[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = 0.f;
-            }
-        };
-        tap(tl, l); tap(tm, m); tap(tr2, r);
-        float o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float y = fmaf(w0[e], l[e], fmaf(w1[e], m[e], fmaf(w2[e], r[e], bb[e])));
+        for (int e = 0; e < 4; ++e) {
+            float y = fmaf(w0[e], lv[e], fmaf(w1[e], mv[e], fmaf(w2[e], rv[e], bb[e])));
             y = (y >= 0.f) ? y : slope * y;
             ls += y; lq = fmaf(y, y, lq);
             o[e] = fminf(fmaxf(y, -65504.f), 65504.f);
         }
-        *reinterpret_cast<uint4*>(a.Y + base + (size_t)t * C + cq * 8) =
-            make_uint4(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]), pack_half2(o[4], o[5]), pack_half2(o[6], o[7]));
+        *reinterpret_cast<uint2*>(a.Y + base + (size_t)t * C + cq * 4) = make_uint2(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]));
     }
     double s1 = warp_sum_d((double)ls), s2 = warp_sum_d((double)lq);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
