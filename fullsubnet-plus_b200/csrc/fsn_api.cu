@@ -380,6 +380,8 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     { const char* e = getenv("FSN_NO_XFUSE"); m->env_no_xfuse = e && atoi(e) != 0; }
     { const char* e = getenv("FSN_TC5_SPLIT"); if (e && *e) m->env_split = atoi(e); }
     { const char* e = getenv("FSN_FRONT_OVERLAP"); m->env_front_overlap = e && atoi(e) != 0; }
+    // FSN_PDL=0: launch the ~30 kernels of the front-end chain without programmatic dependent launch (process-wide; default on)
+    { const char* e = getenv("FSN_PDL"); fsn_chain_launch_set(!(e && atoi(e) == 0)); }
     { const char* e = getenv("FSN_WS_CAP_GB"); if (e && atof(e) > 0) m->ws_cap_bytes = atof(e) * 1e9; }
     build_specs(m);
     for (int i = 0; i < fsn_model::NEV; ++i) { cudaEventCreate(&m->ev0[i]); cudaEventCreate(&m->ev1[i]); cudaEventCreate(&m->evf0[i]); cudaEventCreate(&m->evf1[i]); }

@@ -60,6 +60,14 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Programmatic dependent launch (front-end chain, ~30 short kernels per forward): a kernel launched with launch_chain() may start
+// while its predecessor in the stream is still draining -- its CTAs are placed as SMs free up and run their prologue (barrier
+// init, TMEM allocation) -- and MUST execute pdl_wait() before it touches anything the predecessor reads or writes; pdl_wait returns
+// when the predecessor grid has completed and its memory is visible (a no-op for a normally launched kernel).  pdl_trigger() lets
+// the successor begin launching once every CTA of this grid has executed it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Power-of-two down-scale for storing an activation in fp16 whose input stream has absolute maximum `amax` (per sample): exact
 // (no rounding), never amplifies (a bias term must not overflow when the stream is tiny), 1 for amax < 1.
 __device__ __forceinline__ float fp16_store_scale(float amax) {

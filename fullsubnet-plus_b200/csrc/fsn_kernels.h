@@ -6,6 +6,21 @@
 
 namespace fsn {
 
+// Launch a kernel of the front-end chain; with `chained` (fsn_chain_launch_enabled(): FSN_PDL, read once at model creation) it gets the
+// programmatic-stream-serialization attribute -- every kernel launched through this helper executes pdl_wait() (fsn_common.cuh).
+bool fsn_chain_launch_enabled();
+void fsn_chain_launch_set(bool on);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at; cfg.numAttrs = fsn_chain_launch_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- k_front.cu ------------------------------------------------------------------------------
 struct TsseParams {            // device pointers, one set per branch
     const float* conv_w[3];    // [C, k]

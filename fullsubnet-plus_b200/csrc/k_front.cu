@@ -9,6 +9,10 @@
 
 namespace fsn {
 
+static bool g_chain_launch = true;
+bool fsn_chain_launch_enabled() { return g_chain_launch; }
+void fsn_chain_launch_set(bool on) { g_chain_launch = on; }
+
 // =============================================================================================
 // K1 + K2: x / (mean(x) + 1e-5), then the TSSE gate.
 // reference: audio_zen/model/base_model.py:210-225, audio_zen/model/module/attention_model.py:78-98
@@ -22,6 +26,8 @@ constexpr int TSSE_KMAX = 16;
 constexpr int TSSE_ROWW = 3 + 2 * TSSE_KMAX;         // per row: sum, max, min, KMAX exclusive prefix sums, KMAX exclusive suffix sums
 
 __global__ void __launch_bounds__(256) tsse_rowstats_kernel(TsseLaunch a) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int F = a.F, T = a.T, Tp = a.Tp;
     const int r = blockIdx.x * 8 + warp;                          // (branch, sample, bin)
@@ -58,6 +64,8 @@ __global__ void __launch_bounds__(256) tsse_rowstats_kernel(TsseLaunch a) {
 
 __global__ void __launch_bounds__(1024) tsse_norm_kernel(TsseLaunch a) {
     extern __shared__ float sm[];
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x, br = blockIdx.y;
     const int F = a.F, T = a.T, Tp = a.Tp;
     float* S = sm;                                  // [F] row sums
@@ -213,6 +221,8 @@ __global__ void __launch_bounds__(1024) tsse_norm_kernel(TsseLaunch a) {
 // out[z][f][t] = x[z][f][t] * scale[z][f] (zero in the look-ahead pad) in both layouts; one CTA per 32 x 32 tile.
 __global__ void __launch_bounds__(256) tsse_apply_kernel(TsseLaunch a) {
     __shared__ float tr[32][33];
+    pdl_trigger();
+    pdl_wait();
     const int z = blockIdx.z, br = z / a.B, b = z % a.B, F = a.F, T = a.T, Tp = a.Tp;
     const int f0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -239,9 +249,9 @@ __global__ void __launch_bounds__(256) tsse_apply_kernel(TsseLaunch a) {
 void launch_tsse_norm(const TsseLaunch& a, cudaStream_t s) {
     size_t smem = sizeof(float) * ((size_t)a.F * (5 + 2 * TSSE_KMAX) + a.F / 2 + 8);
     cudaFuncSetAttribute(tsse_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    tsse_rowstats_kernel<<<(a.nbranch * a.B * a.F + 7) / 8, 256, 0, s>>>(a);
-    tsse_norm_kernel<<<dim3(a.B, a.nbranch), 1024, smem, s>>>(a);
-    tsse_apply_kernel<<<dim3((a.P + 31) / 32, (a.F + 31) / 32, a.B * a.nbranch), 256, 0, s>>>(a);
+    launch_chain(tsse_rowstats_kernel, dim3((a.nbranch * a.B * a.F + 7) / 8), dim3(256), 0, s, a);
+    launch_chain(tsse_norm_kernel, dim3(a.B, a.nbranch), dim3(1024), smem, s, a);
+    launch_chain(tsse_apply_kernel, dim3((a.P + 31) / 32, (a.F + 31) / 32, a.B * a.nbranch), dim3(256), 0, s, a);
 }
 
 
@@ -391,6 +401,8 @@ void launch_conv1x1(const ConvLaunch& a, cudaStream_t s) {
 // =============================================================================================
 // row sums (and sums of squares) of the window source and the full-band outputs: one warp per row, the whole GPU
 __global__ void __launch_bounds__(256) sb_rowsum_kernel(SbPackLaunch a) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int F = a.F, Tp = a.Tp, nsrc = 1 + a.nfb;
     const int r = blockIdx.x * 8 + warp;                       // (b, which, f)
@@ -406,6 +418,8 @@ __global__ void __launch_bounds__(256) sb_rowsum_kernel(SbPackLaunch a) {
 
 // window-source rows only, written into the [b][nsrc][f] slots of the full table (the full-band sources come from sb_colsum_kernel)
 __global__ void __launch_bounds__(256) sb_rowsum_strided_kernel(SbPackLaunch a, int nsrc) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int F = a.F, Tp = a.Tp;
     const int r0 = blockIdx.x * 8 + warp;                      // (b, f)
@@ -420,6 +434,8 @@ __global__ void __launch_bounds__(256) sb_rowsum_strided_kernel(SbPackLaunch a, 
 }
 
 __global__ void __launch_bounds__(256) sb_stats_kernel(SbPackLaunch a) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x, F = a.F, Tp = a.Tp, nsrc = 1 + a.nfb;
     __shared__ double red[16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
@@ -452,6 +468,8 @@ __global__ void __launch_bounds__(256) sb_stats_kernel(SbPackLaunch a) {
 // blockDim.y interleaved slices, eight independent loads per thread in flight; the slices are added in a fixed order (deterministic).
 __global__ void __launch_bounds__(1024) sb_colsum_kernel(SbPackLaunch a) {
     extern __shared__ float part[];                              // [blockDim.y][blockDim.x][2]
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x, q = blockIdx.y, F = a.F, Tp = a.Tp, nsrc = 1 + a.nfb;
     const int ny = blockDim.y, ty = threadIdx.y;
     const float* base = ((q == 0) ? a.fb[0] : (q == 1) ? a.fb[1] : a.fb[2]) + (size_t)b * a.fb_sb;
@@ -483,13 +501,13 @@ void launch_sb_stats(const SbPackLaunch& a, cudaStream_t s) {
     if (a.fb_st > 1) {                                           // window source frequency-major, full-band outputs time-major
         SbPackLaunch w = a;
         w.nfb = 0;                                               // rows of the window source only ...
-        sb_rowsum_strided_kernel<<<(a.B * a.F + 7) / 8, 256, 0, s>>>(w, 1 + a.nfb);
+        launch_chain(sb_rowsum_strided_kernel, dim3((a.B * a.F + 7) / 8), dim3(256), 0, s, w, 1 + a.nfb);
         const int bx = (a.F + 31) / 32 * 32 < 512 ? (a.F + 31) / 32 * 32 : 512, by = 1024 / bx;
-        sb_colsum_kernel<<<dim3(a.B, a.nfb), dim3(bx, by), (size_t)bx * by * 2 * sizeof(float), s>>>(a);    // ... the full-band outputs by columns
+        launch_chain(sb_colsum_kernel, dim3(a.B, a.nfb), dim3(bx, by), (size_t)bx * by * 2 * sizeof(float), s, a);    // ... the full-band outputs by columns
     } else {
-        sb_rowsum_kernel<<<(a.B * (1 + a.nfb) * a.F + 7) / 8, 256, 0, s>>>(a);
+        launch_chain(sb_rowsum_kernel, dim3((a.B * (1 + a.nfb) * a.F + 7) / 8), dim3(256), 0, s, a);
     }
-    sb_stats_kernel<<<a.B, 256, 0, s>>>(a);
+    launch_chain(sb_stats_kernel, dim3(a.B), dim3(256), 0, s, a);
 }
 
 // One CTA = (sample, 32 consecutive bins, 32 frames).  The window source rows [f0 - Ns, f0 + 31 + Ns] (reflected) and the

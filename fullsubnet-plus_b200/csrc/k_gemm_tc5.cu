@@ -111,6 +111,10 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     __syncthreads();
     tc5_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // chained launch: barriers and tensor memory are set up while the previous kernel of the chain drains; nothing it wrote is read
+    // (and nothing it reads is overwritten) before this point
+    pdl_trigger();
+    pdl_wait();
     constexpr bool AH = (EPI == EPI5_GLN_RES);             // fp16 operands: a 128-byte swizzle atom holds 64 k-elements instead of 32
     constexpr int KBW = AH ? 64 : 32;
     const int nkb = a.Kp / KBW;
@@ -378,7 +382,8 @@ int launch_gemm_tc5(const void* mapA, const void* mapB, GemmTc5Launch a, int num
 #define G5_LAUNCH(E)                                                                                              \
     e = cudaFuncSetAttribute(gemm_tc5_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
     if (e != cudaSuccess) return (int)e;                                                                          \
-    gemm_tc5_kernel<E><<<grid, G5_THREADS, smem, s>>>(mA, mB, a);
+    e = launch_chain(gemm_tc5_kernel<E>, dim3(grid), dim3(G5_THREADS), smem, s, mA, mB, a);                       \
+    if (e != cudaSuccess) return (int)e;
     if (a.epi == EPI5_PRELU_STATS) { G5_LAUNCH(EPI5_PRELU_STATS) }
     else if (a.epi == EPI5_GLN_RES) { G5_LAUNCH(EPI5_GLN_RES) }
     else { G5_LAUNCH(EPI5_OUT) }
@@ -395,6 +400,8 @@ constexpr int DW_CH = 64, DW_TCH = 256, DW_HALO = 18;    // 2 * max dilation (9)
 __global__ void __launch_bounds__(256) dwconv_tm_kernel(DwTmLaunch a) {
     extern __shared__ float slab[];                       // [rows <= DW_TCH + 2 DW_HALO][DW_CH]
     __shared__ double red[16];
+    pdl_trigger();
+    pdl_wait();
     const int z = blockIdx.z, g = z / a.B, c0 = blockIdx.x * DW_CH;
     const int C = a.C, Tp = a.Tp, d = a.dilation;
     const int t0 = blockIdx.y * DW_TCH, t1 = min(t0 + DW_TCH, Tp);
@@ -472,7 +479,8 @@ int launch_dwconv_tm(const DwTmLaunch& a, cudaStream_t s) {
     const size_t smem = (size_t)rows * DW_CH * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(dwconv_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    dwconv_tm_kernel<<<dim3(a.C / DW_CH, (a.Tp + DW_TCH - 1) / DW_TCH, a.Z), 256, smem, s>>>(a);
+    e = launch_chain(dwconv_tm_kernel, dim3(a.C / DW_CH, (a.Tp + DW_TCH - 1) / DW_TCH, a.Z), dim3(256), smem, s, a);
+    if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();
 }
 
