@@ -100,6 +100,7 @@ struct fsn_model {
     // (two lanes, two streams).  Off by default: measured zero-sum on B200 -- the LSTM kernel runs at the board's power cap, and
     // what the front end gains on the 18 idle SMs the LSTM loses in clock (profiles/r02_front_overlap.txt).
     bool env_front_overlap = false;
+    int env_pdl = -1;                                  // FSN_PDL: 0 / 1 / -1 (auto: small batches only)
     double ws_cap_bytes = 48e9;                        // FSN_WS_CAP_GB: larger batches are run as sub-batches (plain forward entry points)
     bool env_no_ws = false, env_no_xfuse = false;      // FSN_NO_XFUSE=1: packed sub-band images instead of the fused unfold (A/B only)
     // pipelined execution: front-end stream, LSTM stream (higher priority), copy-in / copy-out streams, per-slot events
@@ -380,8 +381,11 @@ extern "C" int fsn_model_create(const fsn_config* cfg, fsn_model** out) {
     { const char* e = getenv("FSN_NO_XFUSE"); m->env_no_xfuse = e && atoi(e) != 0; }
     { const char* e = getenv("FSN_TC5_SPLIT"); if (e && *e) m->env_split = atoi(e); }
     { const char* e = getenv("FSN_FRONT_OVERLAP"); m->env_front_overlap = e && atoi(e) != 0; }
-    // FSN_PDL=0: launch the ~30 kernels of the front-end chain without programmatic dependent launch (process-wide; default on)
-    { const char* e = getenv("FSN_PDL"); fsn_chain_launch_set(!(e && atoi(e) == 0)); }
+    // FSN_PDL: programmatic dependent launch of the ~30 kernels of the front-end chain.  0 = never, 1 = always, unset = only for small
+    // batches (the column-split regime, where the forward is launch-latency-bound: B = 1 3.21 -> 3.17 ms).  At B = 64 the chain itself gets
+    // 0.05 ms shorter but the pipelined step LOSES 0.1-0.4 ms: the denser front end no longer leaves gaps for the side stream's iSTFT
+    // kernels, which then run under the power-capped LSTM instead (same-box A/B, scripts/gpu_r2_w.sh).
+    { const char* e = getenv("FSN_PDL"); m->env_pdl = e ? (atoi(e) != 0 ? 1 : 0) : -1; }
     { const char* e = getenv("FSN_WS_CAP_GB"); if (e && atof(e) > 0) m->ws_cap_bytes = atof(e) * 1e9; }
     build_specs(m);
     for (int i = 0; i < fsn_model::NEV; ++i) { cudaEventCreate(&m->ev0[i]); cudaEventCreate(&m->ev1[i]); cudaEventCreate(&m->evf0[i]); cudaEventCreate(&m->evf1[i]); }
@@ -697,6 +701,9 @@ static int forward_impl(fsn_model* m, fsn_model::Lane& ln, const float* d_mag, c
     if (B < 1 || T < 1) return fail(FSN_EINVAL, "bad batch/frames");
     if (c.model_kind == FSN_KIND_PLUS && (!d_real || !d_imag)) return fail(FSN_EINVAL, "FullSubNet_Plus.forward needs mag, real and imag");
     const int F = c.num_freqs, Tp = T + c.look_ahead, Pp = (Tp + 3) & ~3;
+    // chained (programmatic dependent) launches of this thread's front-end kernels: see env_pdl; "small" = at most 16 row-tile pairs,
+    // the regime of the LSTM kernel's column split
+    fsn_chain_launch_set(m->env_pdl == 1 || (m->env_pdl < 0 && ((long long)B * F + 255) / 256 <= 16));
     if (c.model_kind == FSN_KIND_PLUS && c.channel_attention == FSN_ATTN_TSSE)
         for (int i = 0; i < 3; ++i)
             if (Tp < c.kersize[i]) return fail(FSN_EINVAL, "sequence shorter than the TSSE kernel size");

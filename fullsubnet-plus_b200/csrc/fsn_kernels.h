@@ -6,8 +6,9 @@
 
 namespace fsn {
 
-// Launch a kernel of the front-end chain; with `chained` (fsn_chain_launch_enabled(): FSN_PDL, read once at model creation) it gets the
-// programmatic-stream-serialization attribute -- every kernel launched through this helper executes pdl_wait() (fsn_common.cuh).
+// Launch a kernel of the front-end chain; when chained launches are on for the calling thread (fsn_chain_launch_set, decided per
+// forward from the FSN_PDL knob read at model creation and the batch size) it gets the programmatic-stream-serialization attribute --
+// every kernel launched through this helper executes pdl_wait() (fsn_common.cuh).
 bool fsn_chain_launch_enabled();
 void fsn_chain_launch_set(bool on);
 template <typename... KArgs, typename... Args>

@@ -9,7 +9,7 @@
 
 namespace fsn {
 
-static bool g_chain_launch = true;
+static thread_local bool g_chain_launch = false;       // set by the forward of the calling thread right before it enqueues the chain
 bool fsn_chain_launch_enabled() { return g_chain_launch; }
 void fsn_chain_launch_set(bool on) { g_chain_launch = on; }
 
