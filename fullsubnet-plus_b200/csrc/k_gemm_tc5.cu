@@ -1,21 +1,25 @@
 // TCN full-band model (K3 of SURVEY.md 2a) on the 5th-generation tensor cores: the 1x1 convolutions of the eight
-// TCNBlocks and the output Linear as persistent TF32 tcgen05 GEMMs over time-major activations.
+// TCNBlocks and the output Linear as persistent tcgen05 GEMMs over time-major activations, plus the depth-wise convolution between them.
 //
 // reference: TCNBlock.forward (audio_zen/model/module/causal_conv.py:96-108) and SequenceModel.forward, TCN branch
 // (audio_zen/model/module/sequence_model.py:106-112).
 //
 // Formulation.  Activations are stored time-major, rows = (branch, sample, frame), columns = channels (padded to a
 // multiple of 32 floats = one 128-byte swizzle atom), so every 1x1 convolution is  D[rows, C_out] = X[rows, C_in] *
-// W[C_out, C_in]^T  with BOTH operands K-major -- the layout PyTorch already stores W in.  Tiles of 128 rows x 32 k
-// (A) and N_TILE x 32 k (B) are fetched by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a shared-memory ring,
-// multiplied with tcgen05.mma.kind::tf32 into double-buffered TMEM accumulators, and finished by four epilogue warps:
-//   EPI_PRELU_STATS : + bias, PReLU, per-sample sum / sum-of-squares for the following gLN, store as fp16 (the hidden, 512-channel
-//                     activations of a block live in fp16: the same 10 mantissa bits the tf32 product consumed, half the bytes)
+// W[C_out, C_in]^T  with BOTH operands K-major -- the layout PyTorch already stores W in.  Tiles of 128 rows x 128 bytes of k
+// (A) and N_TILE x 128 bytes of k (B) are fetched by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a shared-memory ring,
+// multiplied with tcgen05.mma (kind::tf32 on the fp32 residual stream, kind::f16 on the fp16 hidden activations) into double-
+// buffered TMEM accumulators, and finished by eight epilogue warps whose global loads / stores go through per-warp staging tiles
+// (g5_store_rows64: 8 rows x 64 contiguous bytes per instruction instead of 32 rows x 16 bytes):
+//   EPI_PRELU_STATS : + bias, PReLU, per-sample sum / sum-of-squares for the following gLN, store as fp16 times a per-sample power of
+//                     two (fp16_store_scale: the hidden, 512-channel activations of a block live in fp16 -- the same 10 mantissa
+//                     bits the tf32 product consumed, half the bytes; the normalised real / imag streams reach 1e6 and beyond)
 //   EPI_GLN_RES     : gLN folded analytically -- conv(W, gLN(y)) = rstd * (W diag(gamma)) y - mean rstd s1 + s2 --
-//                     so the GEMM runs on the raw activation and the per-sample affine is applied here, + residual (fp32 stream).
+//                     so the GEMM runs on the raw activation and the per-sample affine is applied here, + residual (fp32 stream),
+//                     + the running max |x| per sample of the new stream (the next block's store scale).
 //                     Its operands (hidden activation, folded weights) are fp16: kind::f16, 64-element k-blocks.
-//   EPI_OUT         : + bias, output activation, written transposed into the [branch, B, F, T'] layout the sub-band
-//                     packer reads.
+//   EPI_OUT         : + bias, output activation, written time-major (the layout the sub-band LSTM's x-tile builders read) or,
+//                     for the packed path, transposed into [branch, B, F, T'].
 #include <cuda.h>
 
 #include "fsn_common.cuh"
