@@ -470,3 +470,26 @@ def test_internal_batch_split_under_a_workspace_cap(built_lib, monkeypatch):
         assert ms.last_launch_count() > m.last_launch_count()          # it really ran several sub-batches
         assert O.rel_l2(b.cpu().numpy(), a.cpu().numpy()) < 1e-5
         assert O.rel_l2(torch.view_as_real(eb).cpu().numpy(), torch.view_as_real(ea).cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("B", [2, 20])
+def test_chained_front_end_launches_match_plain_launches(built_lib, monkeypatch, B):
+    """FSN_PDL (read at model creation): programmatic dependent launch of the front-end kernel chain (every kernel runs
+    griddepcontrol.launch_dependents / griddepcontrol.wait).  Default geometry; B = 2 is inside the automatic small-batch regime, B = 20
+    outside it, so both settings are forced.  The two paths run the same kernels in the same order: equal up to the order of the fp64
+    atomics of the gLN statistics, over several back-to-back forwards (the chain of forward i+1 follows the LSTM of forward i)."""
+    cfg = O.default_plus_config()
+    params = O.make_params_plus(cfg, seed=0)
+    X = O.stft(O.synth_clips(B, seed0=7000))
+    mag, real, imag = (np.abs(X)[:, None].astype(np.float32), X.real[:, None].astype(np.float32), X.imag[:, None].astype(np.float32))
+    monkeypatch.setenv("FSN_PDL", "0")
+    m0 = _plus(cfg, params)
+    monkeypatch.setenv("FSN_PDL", "1")
+    m1 = _plus(cfg, params)
+    monkeypatch.delenv("FSN_PDL")
+    with torch.no_grad():
+        outs0 = [m0(_t(mag), _t(real), _t(imag)).clone() for _ in range(3)]
+        outs1 = [m1(_t(mag), _t(real), _t(imag)).clone() for _ in range(3)]
+    for a, b in zip(outs0, outs1):
+        assert O.rel_l2(b.cpu().numpy(), a.cpu().numpy()) < 1e-5
+    assert O.rel_l2(outs1[2].cpu().numpy(), outs1[0].cpu().numpy()) < 1e-5
